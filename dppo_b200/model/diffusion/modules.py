@@ -1,0 +1,80 @@
+"""
+Small building blocks of the denoiser networks (host-side parameter containers).
+
+SinusoidalPosEmb -> /root/reference/dppo/model/diffusion/modules.py:14-27
+Downsample1d / Upsample1d / Conv1dBlock -> /root/reference/dppo/model/diffusion/modules.py:30-95
+"""
+
+import math
+
+import torch
+from torch import nn
+
+
+class SinusoidalPosEmb(nn.Module):
+    """t -> [sin(t f_j), cos(t f_j)], f_j = exp(-j ln(1e4) / (dim/2 - 1)), j < dim/2."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, t):
+        half = self.dim // 2
+        rate = math.log(10000) / (half - 1)
+        freq = torch.exp(torch.arange(half, device=t.device) * -rate)
+        phase = t[:, None] * freq[None, :]
+        return torch.cat((phase.sin(), phase.cos()), dim=-1)
+
+
+class Downsample1d(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.conv = nn.Conv1d(dim, dim, 3, 2, 1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample1d(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.conv = nn.ConvTranspose1d(dim, dim, 4, 2, 1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class _AddAxis(nn.Module):
+    """(B, C, L) -> (B, C, 1, L); parameter-free stand-in for the reference's einops Rearrange layer."""
+
+    def forward(self, x):
+        return x.unsqueeze(2)
+
+
+class _DropAxis(nn.Module):
+    def forward(self, x):
+        return x.squeeze(2)
+
+
+class Conv1dBlock(nn.Module):
+    """Conv1d -> GroupNorm -> activation; parameters live at `block.0.*` (conv) and `block.2.*` (norm)."""
+
+    def __init__(self, inp_channels, out_channels, kernel_size, n_groups=None, activation_type="Mish", eps=1e-5):
+        super().__init__()
+        if activation_type == "Mish":
+            act = nn.Mish()
+        elif activation_type == "ReLU":
+            act = nn.ReLU()
+        else:
+            raise ValueError("Unknown activation type for Conv1dBlock")
+        grouped = n_groups is not None
+        self.block = nn.Sequential(
+            nn.Conv1d(inp_channels, out_channels, kernel_size, padding=kernel_size // 2),
+            _AddAxis() if grouped else nn.Identity(),
+            nn.GroupNorm(n_groups, out_channels, eps=eps) if grouped else nn.Identity(),
+            _DropAxis() if grouped else nn.Identity(),
+            act,
+        )
+
+    def forward(self, x):
+        return self.block(x)

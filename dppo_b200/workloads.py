@@ -1,0 +1,93 @@
+"""
+The five BASELINE.json workloads as plain dicts (plus YAML-faithful / literal variants).
+
+Every value is taken from the reference YAML cited in `yaml`; `n_envs` is the BASELINE.json figure (synthetic envs).
+The dicts carry constructor keywords only — they are consumed by dppo_b200 (build_model), by the golden-vector
+generator (which feeds the same keywords to the reference classes) and by the tests (oracle NetCfg / DiffCfg).
+"""
+
+from copy import deepcopy
+
+_GYM_PPO = dict(
+    gamma_denoising=0.99, clip_ploss_coef=0.01, clip_ploss_coef_base=0.01, clip_ploss_coef_rate=3,
+    randn_clip_value=3, min_sampling_denoising_std=0.1, min_logprob_denoising_std=0.1,
+)
+_ROBOMIMIC_PPO = dict(
+    gamma_denoising=0.99, clip_ploss_coef=0.01, clip_ploss_coef_base=0.001, clip_ploss_coef_rate=3,
+    randn_clip_value=3, min_sampling_denoising_std=0.1, min_logprob_denoising_std=0.1,
+)
+_CRITIC_256 = dict(mlp_dims=[256, 256, 256], activation_type="Mish", residual_style=True)
+
+WORKLOADS = {
+    # cfg1: dppo/cfg/gym/finetune/hopper-v2/ft_ppo_diffusion_mlp.yaml
+    "hopper": dict(
+        yaml="gym/finetune/hopper-v2/ft_ppo_diffusion_mlp.yaml",
+        n_envs=40, obs_dim=11, action_dim=3, horizon_steps=4, act_steps=4, cond_steps=1,
+        denoising_steps=20, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+        actor=dict(kind="mlp", time_dim=16, mlp_dims=[512, 512, 512], activation_type="ReLU", residual_style=True),
+        critic=_CRITIC_256, ppo=_GYM_PPO,
+        train=dict(n_steps=500, gamma=0.99, gae_lambda=0.95, batch_size=50000, update_epochs=5, vf_coef=0.5,
+                   target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=0, max_episode_steps=1000),
+    ),
+    # cfg2: dppo/cfg/gym/finetune/walker2d-v2/ft_ppo_diffusion_mlp.yaml scaled to 4096 synthetic envs
+    "walker2d": dict(
+        yaml="gym/finetune/walker2d-v2/ft_ppo_diffusion_mlp.yaml",
+        n_envs=4096, obs_dim=17, action_dim=6, horizon_steps=4, act_steps=4, cond_steps=1,
+        denoising_steps=20, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+        actor=dict(kind="mlp", time_dim=16, mlp_dims=[512, 512, 512], activation_type="ReLU", residual_style=True),
+        critic=_CRITIC_256, ppo=_GYM_PPO,
+        train=dict(n_steps=50, gamma=0.99, gae_lambda=0.95, batch_size=50000, update_epochs=5, vf_coef=0.5,
+                   target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=0, max_episode_steps=1000),
+    ),
+    # cfg3: dppo/cfg/robomimic/finetune/transport/ft_ppo_diffusion_mlp.yaml with BASELINE.json's literal K=100
+    "transport": dict(
+        yaml="robomimic/finetune/transport/ft_ppo_diffusion_mlp.yaml",
+        n_envs=50, obs_dim=59, action_dim=14, horizon_steps=8, act_steps=8, cond_steps=1,
+        denoising_steps=100, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+        actor=dict(kind="mlp", time_dim=32, mlp_dims=[1024, 1024, 1024], activation_type="Mish", residual_style=True),
+        critic=_CRITIC_256, ppo=_ROBOMIMIC_PPO,
+        train=dict(n_steps=400, gamma=0.999, gae_lambda=0.95, batch_size=10000, update_epochs=5, vf_coef=0.5,
+                   target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=2, max_episode_steps=800),
+    ),
+    # cfg4: dppo/cfg/furniture/finetune/one_leg_low/ft_ppo_diffusion_mlp.yaml (YAML-faithful: DDIM-5 of K=100, eta=1)
+    "furniture": dict(
+        yaml="furniture/finetune/one_leg_low/ft_ppo_diffusion_mlp.yaml",
+        n_envs=1000, obs_dim=58, action_dim=10, horizon_steps=8, act_steps=8, cond_steps=1,
+        denoising_steps=100, ft_denoising_steps=5, use_ddim=True, ddim_steps=5,
+        eta=dict(base_eta=1, min_eta=0.1, max_eta=1.0),
+        actor=dict(kind="mlp", time_dim=32, mlp_dims=[1024] * 7, cond_mlp_dims=[512, 64], use_layernorm=True,
+                   activation_type="Mish", residual_style=True),
+        critic=dict(mlp_dims=[512, 512, 512], activation_type="Mish", residual_style=True),
+        ppo=dict(gamma_denoising=0.9, clip_ploss_coef=0.001, clip_ploss_coef_base=0.001, clip_ploss_coef_rate=3,
+                 randn_clip_value=3, min_sampling_denoising_std=0.04),
+        train=dict(n_steps=88, gamma=0.999, gae_lambda=0.95, batch_size=17600, update_epochs=5, vf_coef=0.5,
+                   target_kl=1, actor_lr=1e-5, critic_lr=1e-3, n_critic_warmup_itr=1, max_episode_steps=700),
+    ),
+    # cfg5: dppo/cfg/robomimic/finetune/square/ft_ppo_diffusion_unet.yaml + BASELINE.json's DDIM-10, 1024 envs
+    "square_unet": dict(
+        yaml="robomimic/finetune/square/ft_ppo_diffusion_unet.yaml",
+        n_envs=1024, obs_dim=23, action_dim=7, horizon_steps=4, act_steps=4, cond_steps=1,
+        denoising_steps=20, ft_denoising_steps=10, use_ddim=True, ddim_steps=10,
+        eta=dict(base_eta=1, min_eta=0.1, max_eta=1.0),
+        actor=dict(kind="unet", diffusion_step_embed_dim=16, dim=64, dim_mults=[1, 2], kernel_size=5, n_groups=8,
+                   smaller_encoder=False, cond_predict_scale=True),
+        critic=_CRITIC_256, ppo=_ROBOMIMIC_PPO,
+        train=dict(n_steps=40, gamma=0.999, gae_lambda=0.95, batch_size=10000, update_epochs=10, vf_coef=0.5,
+                   target_kl=1, actor_lr=2e-5, critic_lr=1e-3, n_critic_warmup_itr=2, max_episode_steps=400),
+    ),
+}
+
+# variants: same networks, different schedules
+WORKLOADS["transport_k20"] = dict(deepcopy(WORKLOADS["transport"]), denoising_steps=20)
+WORKLOADS["furniture_ddpm100"] = dict(deepcopy(WORKLOADS["furniture"]), use_ddim=False, ddim_steps=None, eta=None)
+
+
+def get_workload(name: str) -> dict:
+    if name not in WORKLOADS:
+        raise KeyError(f"unknown workload {name!r}; have {sorted(WORKLOADS)}")
+    return deepcopy(WORKLOADS[name])
+
+
+def chain_evals(w: dict) -> int:
+    """Number of network evaluations per sampled action chunk (S in SURVEY.md §8)."""
+    return w["ddim_steps"] if w["use_ddim"] else w["denoising_steps"]
