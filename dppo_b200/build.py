@@ -1,0 +1,50 @@
+"""
+In-tree build of libdppo_b200.so (hand-written sm_100a CUDA behind the C ABI of include/dppo_b200.h).
+
+    python -m dppo_b200.build            # rebuilds when a source is newer than the library
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the working tree to the GPU box.
+"""
+
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "lib", "libdppo_b200.so")
+SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "update.cu", "umma_selftest.cu"]
+HEADERS = ["common.cuh", "internal.h", os.path.join("..", "..", "include", "dppo_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile the library if it is missing or older than its sources; returns the path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

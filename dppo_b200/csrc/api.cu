@@ -1,0 +1,215 @@
+// C-ABI entry points: context, schedule rows, weight packing, dispatch.  See include/dppo_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "internal.h"
+
+namespace dppo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return DPPO_ERR_CUDA;
+}
+
+int pack_mlp_impl(dppo_ctx* ctx, int which, const float* const* p, int n_params, cudaStream_t st);
+int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
+                      int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
+                      const float* chains_in, float* logp, cudaStream_t st);
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Per-step rows.  DDPM follows reference diffusion_vpg.py:214-223 (+ the chain rule :305-311); DDIM :167-213.
+static int build_rows(dppo_ctx* c, const dppo_sched_desc* s) {
+  c->rows.assign(c->S, StepRow{});
+  for (int i = 0; i < c->S; ++i) {
+    StepRow& r = c->rows[i];
+    if (!c->use_ddim) {
+      const int t = c->K - 1 - i;
+      r.t = t;
+      r.ft = t < c->ft;
+      r.slot = t <= c->ft ? c->ft - t : -1;
+      r.f0 = s->sqrt_recip_alphas_cumprod[t];
+      r.f1 = s->sqrt_recipm1_alphas_cumprod[t];
+      r.f2 = s->ddpm_mu_coef1[t];
+      r.f3 = s->ddpm_mu_coef2[t];
+      r.std_train = expf(0.5f * s->ddpm_logvar_clipped[t]);
+      r.f2_det = r.f2, r.f3_det = r.f3, r.std_det = r.std_train;
+    } else {
+      r.t = s->ddim_t[i];
+      r.ft = i >= c->S - c->ft;
+      r.slot = i >= c->S - c->ft - 1 ? i - (c->S - c->ft - 1) : -1;
+      const float a = s->ddim_alphas[i], ap = s->ddim_alphas_prev[i];
+      r.f0 = powf(a, 0.5f);
+      r.f1 = s->ddim_sqrt_one_minus_alphas[i];
+      r.f2 = powf(ap, 0.5f);
+      // sigma = clamp(eta * ((1-ap)/(1-a) * (1 - a/ap))^0.5, min=1e-10)
+      const float base = powf((1.f - ap) / (1.f - a) * (1.f - a / ap), 0.5f);
+      const float sig = fmaxf(c->eta * base, 1e-10f);
+      r.f3 = sqrtf(fmaxf(1.f - ap - sig * sig, 0.f));
+      r.std_train = expf(0.5f * logf(sig * sig));
+      const float sig0 = fmaxf(0.f * base, 1e-10f);
+      r.f2_det = r.f2;
+      r.f3_det = sqrtf(fmaxf(1.f - ap - sig0 * sig0, 0.f));
+      r.std_det = 0.f;
+    }
+  }
+  return 0;
+}
+
+static int build_geometry(dppo_ctx* c) {
+  const dppo_mlp_desc& n = c->net;
+  MlpGeom& g = c->g;
+  g.D = n.action_dim * n.horizon_steps;
+  g.Dc_in = n.cond_dim;
+  g.CH = n.cond_hidden;
+  g.CO = n.cond_out;
+  g.Dc = g.CH ? g.CO : n.cond_dim;
+  g.td = n.time_dim;
+  g.H = n.hidden_dim;
+  g.nb = n.n_blocks;
+  g.act = n.activation;
+  g.ln = n.use_layernorm;
+  if (g.D < 1 || g.D > 128) return set_error("Ta*Da = %d outside [1,128]", g.D), DPPO_ERR_INVALID;
+  if (g.H % 128 || g.H < 128 || g.H > 1024) return set_error("hidden_dim %d must be a multiple of 128 in [128,1024]", g.H), DPPO_ERR_INVALID;
+  if (g.td % 2 || g.td < 4 || g.td > 64) return set_error("time_dim %d unsupported", g.td), DPPO_ERR_INVALID;
+  if (g.nb < 1 || g.nb > 8) return set_error("n_blocks %d unsupported", g.nb), DPPO_ERR_INVALID;
+  if (g.CH && (g.CH % 128 || g.CH > g.H || g.CO > 128 || g.CO < 1 || g.Dc_in > g.H))
+    return set_error("cond_mlp dims (%d,%d) unsupported", g.CH, g.CO), DPPO_ERR_INVALID;
+  if (g.act != DPPO_ACT_RELU && g.act != DPPO_ACT_MISH) return set_error("activation %d unsupported", g.act), DPPO_ERR_INVALID;
+  g.MT = g.H / 128;
+  g.KCH = g.H / 64;
+  g.NE = g.H <= 512 ? 64 : 32;
+  g.KC0 = ceil_div(g.D + g.Dc, 64);
+  if (g.KC0 > g.KCH) return set_error("layer-0 width %d exceeds hidden_dim", g.D + g.Dc), DPPO_ERR_INVALID;
+  g.KCc = g.CH ? ceil_div(g.Dc_in, 64) : 0;
+  g.MTc = g.CH / 128;
+  g.nsplit = c->precision == DPPO_PRECISION_SPLIT3 ? 2 : 1;
+  // fp32 side table
+  size_t o = 0;
+  g.off_tb = o, o += (size_t)c->K * g.H;
+  g.off_blk = o, g.blk_stride = (size_t)(g.ln ? 6 : 2) * g.H, o += g.blk_stride * g.nb;
+  g.off_bout = o, o += 128;
+  g.off_bc0 = o, o += g.CH;
+  g.off_bc1 = o, o += 128;
+  g.n_side = o;
+  // tile stream
+  g.n_cond_tiles = g.CH ? (size_t)g.nsplit * (g.MTc * g.KCc + g.CH / 64) : 0;
+  g.n_step_tiles = (size_t)g.nsplit * (g.MT * g.KC0 + (size_t)g.nb * 2 * g.MT * g.KCH + g.KCH);
+  g.off_cond_tiles = 0;
+  g.off_step_tiles = g.n_cond_tiles * 16384;
+  g.blob_bytes = (g.n_cond_tiles + g.n_step_tiles) * 16384;
+  return 0;
+}
+
+}  // namespace dppo
+
+using namespace dppo;
+
+extern "C" const char* dppo_last_error(void) { return g_err; }
+extern "C" int dppo_version(void) { return 100; }
+
+extern "C" int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const dppo_sched_desc* s, int precision,
+                               int device) {
+  if (!out || !actor || !s) return set_error("dppo_ctx_create: null argument"), DPPO_ERR_INVALID;
+  if (precision != DPPO_PRECISION_SPLIT3 && precision != DPPO_PRECISION_BF16)
+    return set_error("dppo_ctx_create: unknown precision %d", precision), DPPO_ERR_INVALID;
+  DPPO_CUDA(cudaSetDevice(device));
+  dppo_ctx* c = new dppo_ctx();
+  c->device = device;
+  c->precision = precision;
+  c->net = *actor;
+  c->K = s->denoising_steps;
+  c->ft = s->ft_denoising_steps;
+  c->use_ddim = s->use_ddim;
+  c->S = s->use_ddim ? s->ddim_steps : s->denoising_steps;
+  c->eta = s->eta;
+  c->x0_clip = s->denoised_clip_value;
+  c->randn_clip = s->randn_clip_value;
+  c->final_clip = s->final_action_clip_value;
+  c->eps_clip = s->eps_clip_value;
+  c->min_logprob_std = s->min_logprob_denoising_std;
+  int rc = DPPO_OK;
+  if (c->K < 1 || c->S < 1 || c->ft < 0 || c->ft > c->S) {
+    set_error("dppo_ctx_create: bad schedule K=%d S=%d ft=%d", c->K, c->S, c->ft);
+    rc = DPPO_ERR_INVALID;
+  } else if (!s->sqrt_recip_alphas_cumprod || !s->sqrt_recipm1_alphas_cumprod || !s->ddpm_mu_coef1 ||
+             !s->ddpm_mu_coef2 || !s->ddpm_logvar_clipped ||
+             (s->use_ddim && (!s->ddim_t || !s->ddim_alphas || !s->ddim_alphas_prev || !s->ddim_sqrt_one_minus_alphas))) {
+    set_error("dppo_ctx_create: missing schedule table");
+    rc = DPPO_ERR_INVALID;
+  } else {
+    rc = build_geometry(c);
+  }
+  if (rc == DPPO_OK) {
+    build_rows(c, s);
+    int dev_sms = 0;
+    if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && dev_sms > 0)
+      c->sm_count = dev_sms;
+    cudaError_t e = cudaMalloc(&c->d_rows, sizeof(StepRow) * c->S);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_rows, c->rows.data(), sizeof(StepRow) * c->S, cudaMemcpyHostToDevice);
+    for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
+      e = cudaMalloc(&c->nets[w].tiles, c->g.blob_bytes);
+      if (e == cudaSuccess) e = cudaMalloc(&c->nets[w].side, c->g.n_side * sizeof(float));
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "dppo_ctx_create allocation");
+  }
+  if (rc != DPPO_OK) {
+    dppo_ctx_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return DPPO_OK;
+}
+
+extern "C" int dppo_ctx_destroy(dppo_ctx* c) {
+  if (!c) return DPPO_OK;
+  cudaFree(c->d_rows);
+  for (int w = 0; w < 2; ++w) {
+    cudaFree(c->nets[w].tiles);
+    cudaFree(c->nets[w].side);
+  }
+  delete c;
+  return DPPO_OK;
+}
+
+extern "C" int dppo_pack_mlp(dppo_ctx* ctx, int which, const float* const* params, int n_params, void* stream) {
+  if (!ctx || !params) return set_error("dppo_pack_mlp: null argument"), DPPO_ERR_INVALID;
+  if (which != DPPO_NET_ACTOR && which != DPPO_NET_ACTOR_FT) return set_error("dppo_pack_mlp: which=%d", which), DPPO_ERR_INVALID;
+  for (int i = 0; i < n_params; ++i)
+    if (!params[i]) return set_error("dppo_pack_mlp: parameter %d is null", i), DPPO_ERR_INVALID;
+  return pack_mlp_impl(ctx, which, params, n_params, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, const float* noise, uint64_t seed,
+                                 uint64_t offset, int64_t env_offset, int deterministic, int use_base_policy,
+                                 float min_std, float* traj, float* chain, void* stream) {
+  if (!ctx || !state || !traj) return set_error("dppo_sample_chain: null argument"), DPPO_ERR_INVALID;
+  if (n_envs < 0) return set_error("dppo_sample_chain: n_envs=%d", n_envs), DPPO_ERR_INVALID;
+  if (n_envs == 0) return DPPO_OK;
+  if (!ctx->nets[0].packed || (!use_base_policy && !ctx->nets[1].packed))
+    return set_error("dppo_sample_chain: weights not packed (call dppo_pack_mlp for actor and actor_ft)"), DPPO_ERR_STATE;
+  return sample_chain_impl(ctx, state, n_envs, noise, seed, offset, env_offset, deterministic, use_base_policy, min_std,
+                           traj, chain, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const float* chains, int n_rows,
+                                   int use_base_policy, float* logp, void* stream) {
+  if (!ctx || !state || !chains || !logp) return set_error("dppo_chain_logprobs: null argument"), DPPO_ERR_INVALID;
+  if (n_rows < 0) return set_error("dppo_chain_logprobs: n_rows=%d", n_rows), DPPO_ERR_INVALID;
+  if (n_rows == 0 || ctx->ft == 0) return DPPO_OK;
+  if (!ctx->nets[use_base_policy ? 0 : 1].packed)
+    return set_error("dppo_chain_logprobs: weights not packed"), DPPO_ERR_STATE;
+  return sample_chain_impl(ctx, state, n_rows, nullptr, 0, 0, 0, 0, use_base_policy, ctx->min_logprob_std, nullptr,
+                           nullptr, chains, logp, static_cast<cudaStream_t>(stream));
+}

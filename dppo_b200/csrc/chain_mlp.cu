@@ -1,0 +1,546 @@
+// Persistent denoise-chain kernel for the DiffusionMLP denoiser (sm_100a: tcgen05.mma + TMEM + bulk TMA copies).
+//
+// Replaces, for one tile of NE environments per CTA and ALL S denoising steps in one launch:
+//   VPGDiffusion.forward / p_mean_var          reference dppo/model/diffusion/diffusion_vpg.py:139-315
+//   DiffusionMLP.forward + ResidualMLP         reference dppo/model/diffusion/mlp_diffusion.py:218-250, common/mlp.py:84-154
+//   VPGDiffusion.get_logprobs (EVAL mode)      reference dppo/model/diffusion/diffusion_vpg.py:319-396
+//
+// Formulation ("swap-AB"): every Linear is D[f, e] = sum_k W[f, k] * X[e, k] with the WEIGHTS as the MMA A operand
+// (M = 128 output features per tile, streamed from L2 through a ring of 16 KiB pre-swizzled tiles by cp.async.bulk)
+// and the ACTIVATIONS of the NE environments as the B operand (N = NE, resident in shared memory as bf16 hi [+ lo]).
+// Accumulators live in TMEM: region h (residual stream, MT*NE columns) and region y (block hidden / output layer).
+// The residual add is free: the second Linear of a block accumulates straight onto h in TMEM.
+//
+// Warp roles (320 threads): warp 0 = weight-tile producer, warp 1 = MMA issuer (+ TMEM allocator),
+// warps 2..9 = epilogue (TMEM -> registers -> bias / LayerNorm / activation -> bf16 split -> shared memory, and the
+// posterior-mean / noise-injection / chain-store step after the output layer).
+//
+// Precision: SPLIT3 issues x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (three bf16 MMAs, fp32 accumulate), BF16 issues one.
+#include "common.cuh"
+#include "internal.h"
+
+namespace dppo {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr uint32_t kTile = 16384;
+constexpr int kMaxStages = 12;
+
+struct ChainArgs {
+  // geometry
+  int D, Dc_in, Dc, H, nb, act, ln, CH, CO, MT, KCH, KC0, KCc, MTc, nsplit, nstage;
+  uint32_t off_tb, off_blk, blk_stride, off_bout, off_bc0, off_bc1;
+  const uint8_t* tiles[2];
+  const float* side[2];
+  uint32_t n_cond_tiles, n_step_tiles;
+  size_t off_step_tiles;
+  // schedule
+  const StepRow* rows;
+  int S, ft, first_step, eval_mode, use_ddim;
+  int deterministic, use_base;
+  float min_std, x0_clip, randn_clip, final_clip, eps_clip;
+  // io
+  const float* state;
+  int E;
+  const float* noise;
+  float* traj;
+  float* chain;
+  const float* chains_in;
+  float* logp;
+  uint64_t seed, offset;
+  int64_t env_offset;
+};
+
+// ---------------------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t offset, uint64_t elem, uint32_t slot) {
+  uint32_t c0 = uint32_t(elem), c1 = uint32_t(elem >> 32), c2 = slot, c3 = uint32_t(offset);
+  uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32) ^ uint32_t(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+  const float u1 = (float(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (float(c1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+  if (ACT == DPPO_ACT_RELU) return fmaxf(x, 0.f);
+  return mish_f(x);
+}
+
+// store one activation value into a K-major SWIZZLE_128B operand (rows = NE environments)
+template <int NE>
+__device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, int row, int k, float v, bool split) {
+  const uint32_t off = sw128_offset(uint32_t(row), uint32_t(k), NE);
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+  if (split) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+struct Smem {
+  uint8_t *x_hi, *x_lo, *x0_hi, *x0_lo, *ring;
+  uint64_t *full, *empty, *layer_done, *x_ready;
+  uint32_t* tmem_slot;
+  float* ln_part;  // [kEpiWarps][2][32]
+};
+
+template <int NE>
+__device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
+  Smem s;
+  const uint32_t xb = uint32_t(NE) * a.H * 2, x0b = uint32_t(a.KC0) * NE * 128;
+  uint8_t* p = base;
+  s.x_hi = p, p += xb;
+  s.x_lo = p, p += (a.nsplit == 2 ? xb : 0);
+  s.x0_hi = p, p += x0b;
+  s.x0_lo = p, p += (a.nsplit == 2 ? x0b : 0);
+  s.ring = p, p += size_t(a.nstage) * kTile;
+  s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
+  s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
+  s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.x_ready = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
+  s.ln_part = reinterpret_cast<float*>(p);
+  return s;
+}
+
+static size_t smem_fixed_bytes(const MlpGeom& g) {
+  const size_t xb = size_t(g.NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * g.NE * 128 * g.nsplit;
+  return xb + x0b + 16 * kMaxStages + 32 + kEpiWarps * 2 * 32 * 4 + 1024 /* alignment slack */;
+}
+
+// ============================================================================================== the kernel
+template <int NE, int ACT, bool LN>
+__global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs a) {
+  constexpr int CPT = NE / 2;  // accumulator columns (environments) per epilogue thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const Smem s = carve<NE>(smem, a);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = a.nsplit == 2;
+  const int env0 = blockIdx.x * NE;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.nstage; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.layer_done, 1);
+    mbar_init(s.x_ready, kEpiThreads);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t col_h = 0, col_y = uint32_t(a.MT) * NE;
+
+  if (warp == 0) {
+    // ======================================================================================= weight-tile producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int cur_net = -1;
+      for (int step = a.first_step; step < a.S; ++step) {
+        const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
+        for (int part = 0; part < 2; ++part) {
+          const uint8_t* src;
+          uint32_t n;
+          if (part == 0) {
+            if (!(a.CH && net != cur_net)) continue;
+            src = a.tiles[net], n = a.n_cond_tiles;
+          } else {
+            src = a.tiles[net] + a.off_step_tiles, n = a.n_step_tiles;
+          }
+          for (uint32_t i = 0; i < n; ++i) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&s.full[stage], kTile);
+            bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
+            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+          }
+        }
+        cur_net = net;
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, NE);
+      uint32_t stage = 0, phase = 0, xr_phase = 0;
+      auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc) {
+        mbar_wait(s.x_ready, xr_phase);
+        xr_phase ^= 1;
+        tc_fence_after();
+        const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+        for (int mt = 0; mt < MTl; ++mt) {
+          const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
+          for (int kc = 0; kc < KCl; ++kc) {
+            const uint32_t boff = uint32_t(kc) * NE * 128;
+            mbar_wait(&s.full[stage], phase);
+            tc_fence_after();
+            uint32_t wa = smem_u32(s.ring + size_t(stage) * kTile);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d, umma_desc(wa + k * 32), umma_desc(bh + boff + k * 32), idesc, (acc || kc > 0 || k > 0) ? 1u : 0u);
+            if (split) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc(wa + k * 32), umma_desc(bl + boff + k * 32), idesc, 1u);
+            }
+            umma_commit(&s.empty[stage]);
+            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+            if (split) {
+              mbar_wait(&s.full[stage], phase);
+              tc_fence_after();
+              wa = smem_u32(s.ring + size_t(stage) * kTile);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc(wa + k * 32), umma_desc(bh + boff + k * 32), idesc, 1u);
+              umma_commit(&s.empty[stage]);
+              if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+            }
+          }
+        }
+        umma_commit(s.layer_done);
+      };
+      int cur_net = -1;
+      for (int step = a.first_step; step < a.S; ++step) {
+        const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
+        if (a.CH && net != cur_net) {
+          run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false);
+          run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false);
+        }
+        cur_net = net;
+        run_layer(s.x0_hi, s.x0_lo, a.MT, a.KC0, col_h, false);
+        for (int b = 0; b < a.nb; ++b) {
+          run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_y, false);
+          run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_h, true);
+        }
+        run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false);
+      }
+    }
+  } else {
+    // ======================================================================================= epilogue warps
+    const int et = threadIdx.x - 64;     // 0..255
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the NE columns
+    const int fl = q * 32 + lane;        // feature (TMEM lane) within an m-tile / action element index
+    const int col0 = half * CPT;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint32_t ld_phase = 0;
+    float xreg[CPT];
+
+    auto wait_layer = [&]() {
+      mbar_wait(s.layer_done, ld_phase);
+      ld_phase ^= 1;
+      tc_fence_after();
+    };
+    auto signal_x = [&]() {
+      tmem_wait_st();
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(s.x_ready);
+    };
+    // raw observation -> X (input of the cond_mlp), zero padded to the 64-wide chunks it occupies
+    auto stage_cond_input = [&]() {
+      const int kw = a.KCc * 64;
+      for (int i = et; i < NE * kw; i += kEpiThreads) {
+        const int e = i / kw, k = i % kw;
+        const int env = env0 + e;
+        const float v = (env < a.E && k < a.Dc_in) ? a.state[size_t(env) * a.Dc_in + k] : 0.f;
+        store_operand<NE>(s.x_hi, s.x_lo, e, k, v, split);
+      }
+    };
+    // generic hidden-layer epilogue: v = acc + bias; [store back]; [LayerNorm]; activation; -> X
+    auto epi_hidden = [&](uint32_t region, int MTl, const float* bias, bool store_back, bool identity,
+                          const float* ln_g, const float* ln_b) {
+      float mean[LN ? CPT : 1], rstd[LN ? CPT : 1];
+      if (LN && ln_g != nullptr) {
+        float s1[CPT], s2[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) s1[c] = 0.f, s2[c] = 0.f;
+        for (int mt = 0; mt < MTl; ++mt) {
+          float v[CPT];
+          tmem_ld(tmem + lane_addr + region + uint32_t(mt) * NE + col0, v);
+          const float b = bias[mt * 128 + fl];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const float x = v[c] + b;
+            s1[c] += x, s2[c] += x * x;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+            s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+          }
+        }
+        float* mine = s.ln_part + (warp - 2) * 64;
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) mine[c] = s1[c], mine[32 + c] = s2[c];
+        }
+        named_bar_sync(1, kEpiThreads);
+        const float inv_n = 1.f / float(MTl * 128);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float* part = s.ln_part + (half * 4 + w) * 64;
+            t1 += part[c], t2 += part[32 + c];
+          }
+          const float m = t1 * inv_n;
+          const float var = fmaxf(t2 * inv_n - m * m, 0.f);
+          mean[LN ? c : 0] = m, rstd[LN ? c : 0] = rsqrtf(var + 1e-6f);
+        }
+      }
+      for (int mt = 0; mt < MTl; ++mt) {
+        float v[CPT];
+        const uint32_t taddr = tmem + lane_addr + region + uint32_t(mt) * NE + col0;
+        tmem_ld(taddr, v);
+        const int f = mt * 128 + fl;
+        const float b = bias[f];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) v[c] += b;
+        if (store_back) tmem_st(taddr, v);
+        float g = 1.f, be = 0.f;
+        if (LN && ln_g != nullptr) g = ln_g[f], be = ln_b[f];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          float x = v[c];
+          if (LN && ln_g != nullptr) x = (x - mean[LN ? c : 0]) * rstd[LN ? c : 0] * g + be;
+          if (!identity) x = activate<ACT>(x);
+          store_operand<NE>(s.x_hi, s.x_lo, col0 + c, f, x, split);
+        }
+      }
+    };
+
+    // ------------------------------------------------------------------------------------ prologue
+    {
+      // zero the layer-0 operand (padding columns must read as 0), then place the conditioning columns
+      const uint32_t x0_bytes = uint32_t(a.KC0) * NE * 128;
+      for (uint32_t i = et * 16; i < x0_bytes; i += kEpiThreads * 16) {
+        *reinterpret_cast<uint4*>(s.x0_hi + i) = make_uint4(0, 0, 0, 0);
+        if (split) *reinterpret_cast<uint4*>(s.x0_lo + i) = make_uint4(0, 0, 0, 0);
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (a.CH == 0) {
+        for (int i = et; i < NE * a.Dc; i += kEpiThreads) {
+          const int e = i / a.Dc, k = i % a.Dc;
+          const int env = env0 + e;
+          const float v = env < a.E ? a.state[size_t(env) * a.Dc_in + k] : 0.f;
+          store_operand<NE>(s.x0_hi, s.x0_lo, e, a.D + k, v, split);
+        }
+      } else {
+        stage_cond_input();
+      }
+      // x_T (sampling) or the first stored chain entry (evaluation)
+      if (fl < a.D) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int env = env0 + col0 + c;
+          float x = 0.f;
+          if (env < a.E) {
+            if (a.eval_mode)
+              x = a.chains_in[(size_t(env) * (a.ft + 1)) * a.D + fl];
+            else if (a.noise)
+              x = a.noise[size_t(env) * a.D + fl];
+            else
+              x = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + fl, 0u);
+            if (!a.eval_mode && a.chain && a.ft == a.S) a.chain[(size_t(env) * (a.ft + 1)) * a.D + fl] = x;
+          }
+          xreg[c] = x;
+          store_operand<NE>(s.x0_hi, s.x0_lo, col0 + c, fl, x, split);
+        }
+      }
+      signal_x();
+    }
+
+    // ------------------------------------------------------------------------------------ step loop
+    int cur_net = -1;
+    for (int step = a.first_step; step < a.S; ++step) {
+      const StepRow row = a.rows[step];
+      const int net = (row.ft && !a.use_base) ? 1 : 0;
+      const float* side = a.side[net];
+      if (a.CH && net != cur_net) {
+        // cond_mlp: Linear -> act -> Linear, output becomes the conditioning columns of the layer-0 operand
+        wait_layer();
+        epi_hidden(col_y, a.MTc, side + a.off_bc0, false, false, nullptr, nullptr);
+        signal_x();
+        wait_layer();
+        {
+          float v[CPT];
+          tmem_ld(tmem + lane_addr + col_y + col0, v);
+          if (fl < a.CO) {
+            const float b = side[a.off_bc1 + fl];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) store_operand<NE>(s.x0_hi, s.x0_lo, col0 + c, a.D + fl, v[c] + b, split);
+          }
+        }
+        signal_x();
+      }
+      cur_net = net;
+
+      // layer 0: h = W0 [x | cond] + TB[t]   (TB folds bias + time embedding)
+      wait_layer();
+      {
+        const float* blk0 = side + a.off_blk;
+        epi_hidden(col_h, a.MT, side + a.off_tb + size_t(row.t) * a.H, true, false, a.ln ? blk0 + 2 * a.H : nullptr,
+                   a.ln ? blk0 + 3 * a.H : nullptr);
+      }
+      signal_x();
+      for (int b = 0; b < a.nb; ++b) {
+        const float* blk = side + a.off_blk + size_t(b) * a.blk_stride;
+        // l1: y = W1 act(norm1(h)) + b1
+        wait_layer();
+        epi_hidden(col_y, a.MT, blk, false, false, a.ln ? blk + 4 * a.H : nullptr, a.ln ? blk + 5 * a.H : nullptr);
+        signal_x();
+        // l2: h += W2 act(norm2(y)) + b2
+        wait_layer();
+        if (b + 1 < a.nb) {
+          const float* nxt = blk + a.blk_stride;
+          epi_hidden(col_h, a.MT, blk + a.H, true, false, a.ln ? nxt + 2 * a.H : nullptr, a.ln ? nxt + 3 * a.H : nullptr);
+        } else {
+          epi_hidden(col_h, a.MT, blk + a.H, false, true, nullptr, nullptr);
+        }
+        signal_x();
+      }
+
+      // output layer + posterior
+      wait_layer();
+      {
+        float v[CPT];
+        tmem_ld(tmem + lane_addr + col_y + col0, v);
+        if (fl < a.D) {
+          const float bo = side[a.off_bout + fl];
+          const bool last = step == a.S - 1;
+          const int d_eval = step - a.first_step;
+          float stdv, f2 = row.f2, f3 = row.f3;
+          if (a.eval_mode) {
+            stdv = fmaxf(row.std_train, a.min_std);
+          } else if (a.deterministic) {
+            f2 = row.f2_det, f3 = row.f3_det;
+            stdv = a.use_ddim ? 0.f : (row.t == 0 ? 0.f : fmaxf(row.std_train, 1e-3f));
+          } else {
+            stdv = fmaxf(row.std_train, a.min_std);
+          }
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const int env = env0 + col0 + c;
+            float eps = v[c] + bo;
+            const float x = xreg[c];
+            float x0, mu;
+            if (!a.use_ddim) {
+              x0 = row.f0 * x - row.f1 * eps;
+              if (a.x0_clip >= 0.f) x0 = fminf(fmaxf(x0, -a.x0_clip), a.x0_clip);
+              mu = f2 * x0 + f3 * x;
+            } else {
+              x0 = (x - row.f1 * eps) / row.f0;
+              if (a.x0_clip >= 0.f) {
+                x0 = fminf(fmaxf(x0, -a.x0_clip), a.x0_clip);
+                eps = (x - row.f0 * x0) / row.f1;
+              }
+              if (a.eps_clip >= 0.f) eps = fminf(fmaxf(eps, -a.eps_clip), a.eps_clip);
+              mu = f2 * x0 + f3 * eps;
+            }
+            float xn = 0.f;
+            if (env < a.E) {
+              if (a.eval_mode) {
+                xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + fl];
+                const float diff = xn - mu;
+                const float lp = -(diff * diff) / (2.f * (stdv * stdv)) - logf(stdv) - 0.91893853320467274f;
+                a.logp[(size_t(env) * a.ft + d_eval) * a.D + fl] = lp;
+              } else {
+                float z;
+                if (a.noise)
+                  z = a.noise[(size_t(step + 1) * a.E + env) * a.D + fl];
+                else
+                  z = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + fl, uint32_t(step + 1));
+                z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
+                xn = mu + stdv * z;
+                if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
+                if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + fl] = xn;
+                if (last) a.traj[size_t(env) * a.D + fl] = xn;
+              }
+            }
+            xreg[c] = xn;
+            store_operand<NE>(s.x0_hi, s.x0_lo, col0 + c, fl, xn, split);
+          }
+        }
+        // the next step switches network and has a cond_mlp: its input must be staged before the hand-off
+        if (a.CH && step + 1 < a.S) {
+          const int nnet = (a.rows[step + 1].ft && !a.use_base) ? 1 : 0;
+          if (nnet != net) stage_cond_input();
+        }
+      }
+      signal_x();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================================== host launch
+template <int NE, int ACT, bool LN>
+static int launch(const ChainArgs& a, size_t smem_bytes, cudaStream_t st) {
+  auto kfn = chain_mlp_kernel<NE, ACT, LN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(chain_mlp_kernel)");
+    configured = true;
+  }
+  const int grid = (a.E + NE - 1) / NE;
+  kfn<<<grid, kThreads, smem_bytes, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "chain_mlp_kernel launch");
+  return DPPO_OK;
+}
+
+int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
+                      int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
+                      const float* chains_in, float* logp, cudaStream_t st) {
+  const MlpGeom& g = ctx->g;
+  ChainArgs a{};
+  a.D = g.D, a.Dc_in = g.Dc_in, a.Dc = g.Dc, a.H = g.H, a.nb = g.nb, a.act = g.act, a.ln = g.ln, a.CH = g.CH, a.CO = g.CO;
+  a.MT = g.MT, a.KCH = g.KCH, a.KC0 = g.KC0, a.KCc = g.KCc, a.MTc = g.MTc, a.nsplit = g.nsplit;
+  a.off_tb = uint32_t(g.off_tb), a.off_blk = uint32_t(g.off_blk), a.blk_stride = uint32_t(g.blk_stride);
+  a.off_bout = uint32_t(g.off_bout), a.off_bc0 = uint32_t(g.off_bc0), a.off_bc1 = uint32_t(g.off_bc1);
+  for (int w = 0; w < 2; ++w) a.tiles[w] = ctx->nets[w].tiles, a.side[w] = ctx->nets[w].side;
+  a.n_cond_tiles = uint32_t(g.n_cond_tiles), a.n_step_tiles = uint32_t(g.n_step_tiles);
+  a.off_step_tiles = g.off_step_tiles;
+  a.rows = ctx->d_rows, a.S = ctx->S, a.ft = ctx->ft, a.use_ddim = ctx->use_ddim;
+  a.eval_mode = chains_in != nullptr;
+  a.first_step = a.eval_mode ? ctx->S - ctx->ft : 0;
+  a.deterministic = deterministic, a.use_base = use_base;
+  a.min_std = min_std, a.x0_clip = ctx->x0_clip, a.randn_clip = ctx->randn_clip, a.final_clip = ctx->final_clip;
+  a.eps_clip = ctx->eps_clip;
+  a.state = state, a.E = E, a.noise = noise, a.traj = traj, a.chain = chain, a.chains_in = chains_in, a.logp = logp;
+  a.seed = seed, a.offset = offset, a.env_offset = env_offset;
+
+  const size_t fixed = smem_fixed_bytes(g);
+  const size_t budget = 232448;
+  if (fixed + 2 * kTile > budget) return set_error("chain kernel: geometry needs %zu B of shared memory", fixed), DPPO_ERR_INVALID;
+  int nstage = int((budget - fixed) / kTile);
+  if (nstage > kMaxStages) nstage = kMaxStages;
+  a.nstage = nstage;
+  const size_t smem_bytes = fixed + size_t(nstage) * kTile;
+
+#define DPPO_LAUNCH(NE_, ACT_)                                             \
+  (g.ln ? launch<NE_, ACT_, true>(a, smem_bytes, st) : launch<NE_, ACT_, false>(a, smem_bytes, st))
+  if (g.NE == 64) return g.act == DPPO_ACT_RELU ? DPPO_LAUNCH(64, DPPO_ACT_RELU) : DPPO_LAUNCH(64, DPPO_ACT_MISH);
+  return g.act == DPPO_ACT_RELU ? DPPO_LAUNCH(32, DPPO_ACT_RELU) : DPPO_LAUNCH(32, DPPO_ACT_MISH);
+#undef DPPO_LAUNCH
+}
+
+}  // namespace dppo

@@ -1,0 +1,417 @@
+// Update-side kernels (HBM-bound, no tensor cores):
+//   gae_kernel            per-env reverse scan, float64           reference train_ppo_diffusion_agent.py:255-279
+//   logprob_rows_kernel   Gaussian log-density of (x_prev -> x_next) given the network output eps
+//                                                                  reference diffusion_vpg.py:165-224,453-458
+//   adv_stats_kernel      minibatch advantage mean / unbiased std / min / max          diffusion_ppo.py:129-136
+//   ppo_loss_kernel       fused gather + log-prob + clipped-ratio loss + value loss, forward and closed-form backward
+//                         (one group of G lanes per minibatch row, float4 loads, shuffle reductions)
+//                                                                  reference diffusion_ppo.py:57-199, SURVEY.md §3.3
+#include <math.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace dppo {
+
+// ------------------------------------------------------------------------------------------------ GAE
+__global__ void gae_kernel(const double* __restrict__ reward, const double* __restrict__ terminated,
+                           const double* __restrict__ values, const double* __restrict__ next_value, int n_steps,
+                           int E, double gamma, double lam, double scale, double* __restrict__ adv,
+                           double* __restrict__ ret) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double last = 0.0;
+  double nextv = next_value[e];
+  for (int t = n_steps - 1; t >= 0; --t) {
+    const size_t i = size_t(t) * E + e;
+    const double live = 1.0 - terminated[i];
+    const double v = values[i];
+    const double delta = reward[i] * scale + gamma * nextv * live - v;
+    last = delta + gamma * lam * live * last;
+    adv[i] = last;
+    ret[i] = last + v;
+    nextv = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ posterior helpers
+struct Posterior {
+  float mu;
+  float dmu_deps;  // d mu / d eps including the x0 clamp mask
+};
+
+__device__ __forceinline__ Posterior posterior(const StepRow& r, bool ddim, float x0_clip, float eps_clip, float x,
+                                               float eps) {
+  Posterior p;
+  if (!ddim) {
+    float x0 = r.f0 * x - r.f1 * eps;
+    float m = 1.f;
+    if (x0_clip >= 0.f) {
+      m = (x0 >= -x0_clip && x0 <= x0_clip) ? 1.f : 0.f;
+      x0 = fminf(fmaxf(x0, -x0_clip), x0_clip);
+    }
+    p.mu = r.f2 * x0 + r.f3 * x;
+    p.dmu_deps = -r.f2 * r.f1 * m;
+  } else {
+    float x0 = (x - r.f1 * eps) / r.f0;
+    const float dx0 = -r.f1 / r.f0;
+    if (x0_clip >= 0.f) {
+      const float m = (x0 >= -x0_clip && x0 <= x0_clip) ? 1.f : 0.f;
+      x0 = fminf(fmaxf(x0, -x0_clip), x0_clip);
+      float e2 = (x - r.f0 * x0) / r.f1;
+      float me = 1.f;
+      if (eps_clip >= 0.f) {
+        me = (e2 >= -eps_clip && e2 <= eps_clip) ? 1.f : 0.f;
+        e2 = fminf(fmaxf(e2, -eps_clip), eps_clip);
+      }
+      p.mu = r.f2 * x0 + r.f3 * e2;
+      p.dmu_deps = (r.f2 - r.f3 * me * r.f0 / r.f1) * dx0 * m;
+    } else {
+      float e2 = eps, me = 1.f;
+      if (eps_clip >= 0.f) {
+        me = (e2 >= -eps_clip && e2 <= eps_clip) ? 1.f : 0.f;
+        e2 = fminf(fmaxf(e2, -eps_clip), eps_clip);
+      }
+      p.mu = r.f2 * x0 + r.f3 * e2;
+      p.dmu_deps = r.f2 * dx0 + r.f3 * me;
+    }
+  }
+  return p;
+}
+
+constexpr float kHalfLog2Pi = 0.91893853320467274f;
+
+__global__ void logprob_rows_kernel(const float* __restrict__ eps, const float* __restrict__ x_prev,
+                                    const float* __restrict__ x_next, const int64_t* __restrict__ dinds,
+                                    const StepRow* __restrict__ rows, int row0, int ddim, float x0_clip,
+                                    float eps_clip, float min_std, int D, long long total, float* __restrict__ logp,
+                                    float* __restrict__ dlogp_deps) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = int(i / D);
+  const StepRow r = rows[row0 + int(dinds[b])];
+  const Posterior p = posterior(r, ddim != 0, x0_clip, eps_clip, x_prev[i], eps[i]);
+  const float sd = fmaxf(r.std_train, min_std);
+  const float diff = x_next[i] - p.mu;
+  logp[i] = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - kHalfLog2Pi;
+  if (dlogp_deps) dlogp_deps[i] = diff / (sd * sd) * p.dmu_deps;
+}
+
+// ------------------------------------------------------------------------------------------------ advantage stats
+// one block; ws[0..3] (double) = mean, unbiased std, min, max of advantages[inds[i] / ft]
+__global__ void adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ inds, int n, int ft,
+                                 double* __restrict__ ws) {  // inds == nullptr: advantages are already per row
+  __shared__ double sh[32];
+  __shared__ double s_mean;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  double acc = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float a = adv[inds ? inds[i] / ft : i];
+    acc += a;
+    mn = fminf(mn, a), mx = fmaxf(mx, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ float smn[32], smx[32];
+  if (lane == 0) sh[wid] = acc, smn[wid] = mn, smx[wid] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    float a = INFINITY, b = -INFINITY;
+    for (int w = 0; w < nw; ++w) t += sh[w], a = fminf(a, smn[w]), b = fmaxf(b, smx[w]);
+    s_mean = t / n;
+    ws[0] = s_mean, ws[2] = a, ws[3] = b;
+  }
+  __syncthreads();
+  const double mean = s_mean;
+  acc = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double d = double(adv[inds ? inds[i] / ft : i]) - mean;
+    acc += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += sh[w];
+    ws[1] = n > 1 ? sqrt(t / (n - 1)) : NAN;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused loss
+struct LossArgs {
+  const float *chains, *old_lp, *returns, *old_values, *adv, *eps, *vpred;
+  const float* x_next;    // direct mode only (chains = x_prev rows)
+  const int64_t* dinds;   // direct mode only: denoising index per row
+  int direct;             // 1: inputs are already gathered per row (PPODiffusion.loss signature)
+  const int64_t* inds;    // gather mode: this rank's slice of the minibatch
+  const StepRow* rows;
+  int row0;             // S - ft
+  int n_rows, global_rows, D, ft, ddim;
+  int horizon_elems;    // reward_horizon * Da
+  int norm_adv;
+  float x0_clip, eps_clip, min_std;
+  float gamma_denoising, clip_coef, clip_base, clip_rate, clip_v;
+  float adv_lo, adv_hi;
+  float *grad_eps, *grad_v;
+  double* ws;  // [0..3] adv stats (in), [8..12] sums (out)
+};
+
+template <int G, int VEC>
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const LossArgs a) {
+  constexpr int kMaxFt = 128;
+  __shared__ float s_disc[kMaxFt], s_clip[kMaxFt];
+  __shared__ double s_sum[5];
+  const int tid = threadIdx.x;
+  if (tid < 5) s_sum[tid] = 0.0;
+  for (int d = tid; d < a.ft; d += blockDim.x) {
+    s_disc[d] = float(pow(double(a.gamma_denoising), double(a.ft - d - 1)));
+    if (a.ft > 1) {
+      const float t = float(d) / float(a.ft - 1);
+      s_clip[d] = a.clip_base + (a.clip_coef - a.clip_base) * (expf(a.clip_rate * t) - 1.f) /
+                                    float(exp(double(a.clip_rate)) - 1.0);
+    } else {
+      s_clip[d] = a.clip_coef;  // the reference divides 0/0 here (NaN); documented deviation
+    }
+  }
+  __syncthreads();
+  const float adv_mean = float(a.ws[0]), adv_std = float(a.ws[1]);
+  const float lo = a.adv_lo, hi = a.adv_hi;  // -inf / +inf for quantiles 0 / 1 (clamp to [min, max] = no-op)
+  const int rows_per_block = 256 / G;
+  const int lg = tid % G;
+  const int row = blockIdx.x * rows_per_block + tid / G;
+  const bool row_ok = row < a.n_rows;
+  constexpr int NJ = VEC == 4 ? 1 : 4;  // scalar variant: G = 32, up to 128 elements per row
+  float dl[NJ * VEC];
+  float new_sum = 0.f, old_sum = 0.f;
+  int b = 0, d = 0;
+  if (row_ok) {
+    if (a.direct) {
+      b = row, d = int(a.dinds[row]);
+    } else {
+      const int64_t idx = a.inds[row];
+      b = int(idx / a.ft), d = int(idx % a.ft);
+    }
+  }
+  const StepRow r = a.rows[a.row0 + d];
+  const float sd = fmaxf(r.std_train, a.min_std);
+  const float inv_var = 1.f / (sd * sd);
+  const float log_sd = logf(sd);
+  const float w_h = 1.f / float(a.horizon_elems);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e0 = (lg + j * G) * VEC;
+    __align__(16) float xe[VEC];
+    __align__(16) float xp[VEC];
+    __align__(16) float xn[VEC];
+    __align__(16) float ol[VEC];
+    const bool ok = row_ok && e0 < a.D;
+    if (ok) {
+      const size_t pe = size_t(row) * a.D + e0;
+      const size_t pc = a.direct ? pe : (size_t(b) * (a.ft + 1) + d) * a.D + e0;
+      const size_t pl = a.direct ? pe : (size_t(b) * a.ft + d) * a.D + e0;
+      const float* nxt = a.direct ? a.x_next + pe : a.chains + pc + a.D;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(xe) = *reinterpret_cast<const float4*>(a.eps + pe);
+        *reinterpret_cast<float4*>(xp) = *reinterpret_cast<const float4*>(a.chains + pc);
+        *reinterpret_cast<float4*>(xn) = *reinterpret_cast<const float4*>(nxt);
+        *reinterpret_cast<float4*>(ol) = *reinterpret_cast<const float4*>(a.old_lp + pl);
+      } else {
+        xe[0] = a.eps[pe], xp[0] = a.chains[pc], xn[0] = nxt[0], ol[0] = a.old_lp[pl];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float g = 0.f;
+      if (ok && e0 + v < a.horizon_elems) {
+        const Posterior p = posterior(r, a.ddim != 0, a.x0_clip, a.eps_clip, xp[v], xe[v]);
+        const float diff = xn[v] - p.mu;
+        const float lp = -(diff * diff) * 0.5f * inv_var - log_sd - kHalfLog2Pi;
+        const float m_lp = (lp >= -5.f && lp <= 2.f) ? 1.f : 0.f;
+        new_sum += fminf(fmaxf(lp, -5.f), 2.f);
+        old_sum += fminf(fmaxf(ol[v], -5.f), 2.f);
+        g = w_h * m_lp * diff * inv_var * p.dmu_deps;
+      }
+      dl[j * VEC + v] = g;
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    new_sum += __shfl_xor_sync(0xffffffffu, new_sum, o);
+    old_sum += __shfl_xor_sync(0xffffffffu, old_sum, o);
+  }
+  float g_new = 0.f;
+  if (row_ok) {
+    const float newlp = new_sum * w_h, oldlp = old_sum * w_h;
+    float A = a.adv[b];
+    if (a.norm_adv) A = (A - adv_mean) / (adv_std + 1e-8f);
+    A = fminf(fmaxf(A, lo), hi);
+    A *= s_disc[d];
+    const float logratio = newlp - oldlp;
+    const float ratio = expf(logratio);
+    const float c = s_clip[d];
+    const float u = -A * ratio;
+    const float w = -A * fminf(fmaxf(ratio, 1.f - c), 1.f + c);
+    const bool dead = (A > 0.f && ratio > 1.f + c) || (A < 0.f && ratio < 1.f - c);
+    const float inv_b = 1.f / float(a.global_rows);
+    g_new = dead ? 0.f : -A * ratio * inv_b;
+    if (lg == 0) {
+      // value loss
+      const float v = a.vpred[row], R = a.returns[b];
+      float vl, gv;
+      if (a.clip_v >= 0.f) {
+        const float ov = a.old_values[b];
+        const float dv = v - ov;
+        const float vc = ov + fminf(fmaxf(dv, -a.clip_v), a.clip_v);
+        const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+        const float mc = (dv >= -a.clip_v && dv <= a.clip_v) ? 1.f : 0.f;
+        vl = 0.5f * fmaxf(l1, l2);
+        gv = l1 > l2 ? (v - R) : (l1 < l2 ? (vc - R) * mc : 0.5f * (v - R) + 0.5f * (vc - R) * mc);
+      } else {
+        vl = 0.5f * (v - R) * (v - R);
+        gv = v - R;
+      }
+      a.grad_v[row] = gv * inv_b;
+      atomicAdd(&s_sum[0], double(fmaxf(u, w)));
+      atomicAdd(&s_sum[1], double(vl));
+      atomicAdd(&s_sum[2], double((ratio - 1.f) - logratio));
+      atomicAdd(&s_sum[3], fabsf(ratio - 1.f) > c ? 1.0 : 0.0);
+      atomicAdd(&s_sum[4], double(ratio));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e0 = (lg + j * G) * VEC;
+    if (row_ok && e0 < a.D) {
+      const size_t pe = size_t(row) * a.D + e0;
+      if (VEC == 4) {
+        float4 o4 = make_float4(g_new * dl[0], g_new * dl[1], g_new * dl[2], g_new * dl[3]);
+        *reinterpret_cast<float4*>(a.grad_eps + pe) = o4;
+      } else {
+        a.grad_eps[pe] = g_new * dl[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 5) atomicAdd(&a.ws[8 + tid], s_sum[tid]);
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ ws, int global_rows, float* __restrict__ scalars) {
+  const int i = threadIdx.x;
+  if (i < 5) scalars[i] = float(ws[8 + i] / double(global_rows));
+  if (i == 5) scalars[5] = 0.f;
+  if (i == 6) scalars[6] = float(ws[0]);
+  if (i == 7) scalars[7] = float(ws[1]);
+}
+
+}  // namespace dppo
+
+using namespace dppo;
+
+extern "C" int dppo_gae_f64(const double* reward, const double* terminated, const double* values,
+                            const double* next_value, int n_steps, int n_envs, double gamma, double lam, double scale,
+                            double* adv, double* ret, void* stream) {
+  if (!reward || !terminated || !values || !next_value || !adv || !ret)
+    return set_error("dppo_gae_f64: null argument"), DPPO_ERR_INVALID;
+  if (n_steps < 0 || n_envs < 0) return set_error("dppo_gae_f64: negative size"), DPPO_ERR_INVALID;
+  if (n_steps == 0 || n_envs == 0) return DPPO_OK;
+  gae_kernel<<<(n_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(reward, terminated, values, next_value,
+                                                                                   n_steps, n_envs, gamma, lam, scale, adv, ret);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "gae_kernel launch");
+}
+
+extern "C" int dppo_logprob_rows(dppo_ctx* ctx, const float* eps, const float* x_prev, const float* x_next,
+                                 const int64_t* dinds, int n_rows, float* logp, float* dlogp_deps, void* stream) {
+  if (!ctx || !eps || !x_prev || !x_next || !dinds || !logp) return set_error("dppo_logprob_rows: null argument"), DPPO_ERR_INVALID;
+  if (n_rows <= 0) return n_rows == 0 ? DPPO_OK : (set_error("dppo_logprob_rows: n_rows < 0"), DPPO_ERR_INVALID);
+  const long long total = (long long)n_rows * ctx->g.D;
+  logprob_rows_kernel<<<unsigned((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      eps, x_prev, x_next, dinds, ctx->d_rows, ctx->S - ctx->ft, ctx->use_ddim, ctx->x0_clip, ctx->eps_clip,
+      ctx->min_logprob_std, ctx->g.D, total, logp, dlogp_deps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "logprob_rows_kernel launch");
+}
+
+static int loss_impl(dppo_ctx* ctx, LossArgs a, const int64_t* stat_inds, const dppo_loss_hp* hp, float* scalars,
+                     void* workspace, void* stream, const char* who) {
+  const int D = ctx->g.D;
+  if (a.n_rows < 0 || a.global_rows < 1 || a.n_rows > a.global_rows)
+    return set_error("%s: bad row counts %d of %d", who, a.n_rows, a.global_rows), DPPO_ERR_INVALID;
+  if (hp->ft_denoising_steps != ctx->ft || hp->horizon_steps * hp->action_dim != D)
+    return set_error("%s: hyper-parameters disagree with the context", who), DPPO_ERR_INVALID;
+  if (hp->ft_denoising_steps > 128 || hp->ft_denoising_steps < 1)
+    return set_error("%s: ft_denoising_steps %d outside [1,128]", who, hp->ft_denoising_steps), DPPO_ERR_INVALID;
+  if (hp->reward_horizon < 1 || hp->reward_horizon > hp->horizon_steps)
+    return set_error("%s: reward_horizon %d", who, hp->reward_horizon), DPPO_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* ws = static_cast<double*>(workspace);
+  DPPO_CUDA(cudaMemsetAsync(ws, 0, 16 * sizeof(double), st));
+  adv_stats_kernel<<<1, 1024, 0, st>>>(a.adv, stat_inds, a.global_rows, ctx->ft, ws);
+  a.rows = ctx->d_rows, a.row0 = ctx->S - ctx->ft;
+  a.D = D, a.ft = ctx->ft, a.ddim = ctx->use_ddim;
+  a.horizon_elems = hp->reward_horizon * hp->action_dim, a.norm_adv = hp->norm_adv;
+  a.x0_clip = ctx->x0_clip, a.eps_clip = ctx->eps_clip, a.min_std = ctx->min_logprob_std;
+  a.gamma_denoising = hp->gamma_denoising, a.clip_coef = hp->clip_ploss_coef, a.clip_base = hp->clip_ploss_coef_base;
+  a.clip_rate = hp->clip_ploss_coef_rate, a.clip_v = hp->clip_vloss_coef, a.adv_lo = hp->adv_clip_lo, a.adv_hi = hp->adv_clip_hi;
+  a.ws = ws;
+  const int n_rows = a.n_rows;
+  if (n_rows > 0) {
+    if (D % 4 == 0) {
+      const int v4 = D / 4;
+      if (v4 <= 4) {
+        ppo_loss_kernel<4, 4><<<(n_rows + 63) / 64, 256, 0, st>>>(a);
+      } else if (v4 <= 8) {
+        ppo_loss_kernel<8, 4><<<(n_rows + 31) / 32, 256, 0, st>>>(a);
+      } else if (v4 <= 16) {
+        ppo_loss_kernel<16, 4><<<(n_rows + 15) / 16, 256, 0, st>>>(a);
+      } else {
+        ppo_loss_kernel<32, 4><<<(n_rows + 7) / 8, 256, 0, st>>>(a);
+      }
+    } else {
+      ppo_loss_kernel<32, 1><<<(n_rows + 7) / 8, 256, 0, st>>>(a);
+    }
+  }
+  loss_finalize_kernel<<<1, 32, 0, st>>>(ws, a.global_rows, scalars);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, who);
+}
+
+extern "C" int dppo_ppo_loss_fwd_bwd(dppo_ctx* ctx, const float* chains, const float* old_logprobs,
+                                     const float* returns, const float* old_values, const float* advantages,
+                                     const int64_t* inds_all, int row_begin, const float* eps, const float* vpred,
+                                     int n_rows, int global_rows, const dppo_loss_hp* hp, float* grad_eps,
+                                     float* grad_vpred, float* scalars, void* workspace, void* stream) {
+  if (!ctx || !chains || !old_logprobs || !returns || !old_values || !advantages || !inds_all || !eps || !vpred || !hp ||
+      !grad_eps || !grad_vpred || !scalars || !workspace)
+    return set_error("dppo_ppo_loss_fwd_bwd: null argument"), DPPO_ERR_INVALID;
+  if (row_begin < 0 || row_begin + n_rows > global_rows)
+    return set_error("dppo_ppo_loss_fwd_bwd: bad row range [%d, %d) of %d", row_begin, row_begin + n_rows, global_rows),
+           DPPO_ERR_INVALID;
+  LossArgs a{};
+  a.chains = chains, a.old_lp = old_logprobs, a.returns = returns, a.old_values = old_values, a.adv = advantages;
+  a.eps = eps, a.vpred = vpred, a.inds = inds_all + row_begin, a.direct = 0;
+  a.n_rows = n_rows, a.global_rows = global_rows, a.grad_eps = grad_eps, a.grad_v = grad_vpred;
+  return loss_impl(ctx, a, inds_all, hp, scalars, workspace, stream, "dppo_ppo_loss_fwd_bwd");
+}
+
+extern "C" int dppo_ppo_loss_rows(dppo_ctx* ctx, const float* x_prev, const float* x_next, const float* old_logprobs,
+                                  const float* returns, const float* old_values, const float* advantages,
+                                  const int64_t* denoising_inds, const float* eps, const float* vpred, int n_rows,
+                                  const dppo_loss_hp* hp, float* grad_eps, float* grad_vpred, float* scalars,
+                                  void* workspace, void* stream) {
+  if (!ctx || !x_prev || !x_next || !old_logprobs || !returns || !old_values || !advantages || !denoising_inds || !eps ||
+      !vpred || !hp || !grad_eps || !grad_vpred || !scalars || !workspace)
+    return set_error("dppo_ppo_loss_rows: null argument"), DPPO_ERR_INVALID;
+  LossArgs a{};
+  a.chains = x_prev, a.x_next = x_next, a.old_lp = old_logprobs, a.returns = returns, a.old_values = old_values;
+  a.adv = advantages, a.dinds = denoising_inds, a.eps = eps, a.vpred = vpred, a.direct = 1;
+  a.n_rows = n_rows, a.global_rows = n_rows, a.grad_eps = grad_eps, a.grad_v = grad_vpred;
+  return loss_impl(ctx, a, nullptr, hp, scalars, workspace, stream, "dppo_ppo_loss_rows");
+}

@@ -1,0 +1,186 @@
+"""
+Policy-gradient diffusion policy: frozen base denoiser + fine-tuned copy + critic, with the K-step sampler and the
+chain log-probabilities running in libdppo_b200.so.
+
+VPGDiffusion -> /root/reference/dppo/model/diffusion/diffusion_vpg.py:27-461.  Method names, arguments, return shapes
+and `state_dict()` keys (`network.*`, `actor.*`, `actor_ft.*`, `critic.*`, `eta.*`) are the reference's; the bodies
+call the C ABI (include/dppo_b200.h) instead of ~113 eager ops per denoising step:
+
+  forward                 -> dppo_sample_chain      (one persistent tcgen05 kernel for all envs x all S steps)
+  get_logprobs (no grad)  -> dppo_chain_logprobs    (same kernel, teacher-forced over the ft window)
+  get_logprobs_subsample  -> actor_ft (autograd) + dppo_logprob_rows (closed-form derivative kept for backward)
+
+There is no CPU or eager fallback for these methods.
+"""
+
+import copy
+import logging
+import os
+
+import torch
+
+from dppo_b200.engine import ChainEngine
+from dppo_b200.model.diffusion.diffusion import DiffusionModel, Sample
+
+log = logging.getLogger(__name__)
+
+
+class _LogProbRows(torch.autograd.Function):
+    """logp(eps) of dppo_logprob_rows with d logp / d eps = (x_next - mu)/sigma^2 * d mu/d eps from the same kernel."""
+
+    @staticmethod
+    def forward(ctx, eps, engine, x_prev, x_next, denoising_inds):
+        shape = eps.shape
+        logp, fac = engine.logprob_rows(eps.detach(), x_prev, x_next, denoising_inds, want_grad_factor=True)
+        ctx.save_for_backward(fac)
+        ctx.shape = shape
+        return logp.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (fac,) = ctx.saved_tensors
+        return (grad_out.reshape(fac.shape) * fac).reshape(ctx.shape), None, None, None, None
+
+
+class VPGDiffusion(DiffusionModel):
+    def __init__(
+        self,
+        actor,
+        critic,
+        ft_denoising_steps,
+        ft_denoising_steps_d=0,
+        ft_denoising_steps_t=0,
+        network_path=None,
+        min_sampling_denoising_std=0.1,
+        min_logprob_denoising_std=0.1,
+        eta=None,
+        learn_eta=False,
+        engine_precision=None,
+        **kwargs,
+    ):
+        super().__init__(network=actor, network_path=network_path, **kwargs)
+        if ft_denoising_steps > self.denoising_steps or (self.use_ddim and ft_denoising_steps > self.ddim_steps):
+            raise ValueError("ft_denoising_steps exceeds the number of denoising steps")
+        if learn_eta and not self.use_ddim:
+            raise ValueError("Cannot learn eta with DDPM.")
+        self.ft_denoising_steps = ft_denoising_steps
+        self.ft_denoising_steps_d = ft_denoising_steps_d
+        self.ft_denoising_steps_t = ft_denoising_steps_t
+        self.ft_denoising_steps_cnt = 0
+        self.min_sampling_denoising_std = min_sampling_denoising_std
+        self.min_logprob_denoising_std = min_logprob_denoising_std
+        self.learn_eta = learn_eta
+        if eta is not None:
+            self.eta = eta.to(self.device)
+            if not learn_eta:
+                for p in self.eta.parameters():
+                    p.requires_grad = False
+        self.actor = self.network
+        self.actor_ft = copy.deepcopy(self.actor)
+        for p in self.actor.parameters():
+            p.requires_grad = False
+        self.critic = critic.to(self.device)
+        if network_path is not None:
+            ckpt = torch.load(network_path, map_location=self.device, weights_only=True)
+            if "ema" not in ckpt:
+                self.load_state_dict(ckpt["model"], strict=False)
+        # "split3" (3 x bf16 hi/lo MMAs, fp32-level parity) or "bf16" (single pass, fast mode)
+        self.engine_precision = engine_precision or os.environ.get("DPPO_B200_PRECISION", "split3")
+        self._engine = None
+        self._rng_offset = 0
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine(self):
+        """The kernel context (created on first use; rebuilt when the fine-tuning window is annealed)."""
+        if self._engine is None or self._engine.ft != int(self.ft_denoising_steps):
+            self._engine = ChainEngine(self, precision=self.engine_precision)
+        self._engine.sync_weights(0, self.actor)
+        self._engine.sync_weights(1, self.actor_ft)
+        return self._engine
+
+    # ------------------------------------------------------------------ annealing (reference :102-136)
+    def step(self):
+        if type(self.min_sampling_denoising_std) is not float:
+            self.min_sampling_denoising_std.step()
+        self.ft_denoising_steps_cnt += 1
+        if (
+            self.ft_denoising_steps_d > 0
+            and self.ft_denoising_steps_t > 0
+            and self.ft_denoising_steps_cnt % self.ft_denoising_steps_t == 0
+        ):
+            self.ft_denoising_steps = max(0, self.ft_denoising_steps - self.ft_denoising_steps_d)
+            self.actor = self.actor_ft
+            self.actor_ft = copy.deepcopy(self.actor)
+            for p in self.actor.parameters():
+                p.requires_grad = False
+            log.info("Annealed fine-tuning denoising steps to %d", self.ft_denoising_steps)
+
+    def get_min_sampling_denoising_std(self):
+        if type(self.min_sampling_denoising_std) is float:
+            return self.min_sampling_denoising_std
+        return self.min_sampling_denoising_std()
+
+    # ------------------------------------------------------------------ sampling (reference :227-315)
+    @torch.no_grad()
+    def forward(self, cond, deterministic=False, return_chain=True, use_base_policy=False, noise=None):
+        """
+        cond["state"]: (B, To, Do).  Returns Sample(trajectories (B, Ta, Da), chains (B, ft+1, Ta, Da)).
+        `noise` (S+1, B, Ta, Da) injects the draws the reference takes from torch.randn / randn_like (parity tests);
+        without it the kernel draws Philox normals seeded from torch's generator.
+        """
+        eng = self.engine()
+        state = cond["state"]
+        B = state.shape[0]
+        seed = offset = 0
+        if noise is None:
+            seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+            self._rng_offset += 1
+            offset = self._rng_offset
+        traj, chain = eng.sample(
+            state.to(self.device), noise=noise, seed=seed, offset=offset, deterministic=deterministic,
+            use_base_policy=use_base_policy, min_sampling_std=float(self.get_min_sampling_denoising_std()),
+            return_chain=return_chain,
+        )
+        traj = traj.view(B, self.horizon_steps, self.action_dim)
+        if chain is not None:
+            chain = chain.view(B, self.ft_denoising_steps + 1, self.horizon_steps, self.action_dim)
+        return Sample(traj, chain)
+
+    # ------------------------------------------------------------------ log-probabilities (reference :319-461)
+    def _ft_timesteps(self, denoising_inds):
+        if self.use_ddim:
+            t_single = self.ddim_t[-self.ft_denoising_steps:]
+        else:
+            t_single = torch.arange(start=self.ft_denoising_steps - 1, end=-1, step=-1, device=self.device)
+        return t_single[denoising_inds]
+
+    def get_logprobs(self, cond, chains, get_ent=False, use_base_policy=False):
+        """chains (B, ft+1, Ta, Da) -> log-probs (B*ft, Ta, Da), rows env-major / denoise-minor."""
+        if get_ent:
+            raise NotImplementedError("entropy of the chain is constant for fixed eta; the reference never requests it here")
+        B, ft = chains.shape[0], self.ft_denoising_steps
+        actor = self.actor if use_base_policy else self.actor_ft
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in actor.parameters())
+        if not needs_grad:
+            logp = self.engine().chain_logprobs(cond["state"], chains, use_base_policy=use_base_policy)
+            return logp.view(B * ft, self.horizon_steps, self.action_dim)
+        # differentiable variant (BC regulariser inside the loss, reference diffusion_ppo.py:105-126)
+        state = cond["state"].unsqueeze(1).repeat(1, ft, *(1,) * (cond["state"].ndim - 1)).flatten(0, 1)
+        dinds = torch.arange(ft, device=chains.device).repeat(B)
+        prev = chains[:, :-1].reshape(B * ft, self.horizon_steps, self.action_dim)
+        nxt = chains[:, 1:].reshape(B * ft, self.horizon_steps, self.action_dim)
+        return self.get_logprobs_subsample({"state": state}, prev, nxt, dinds, use_base_policy=use_base_policy)
+
+    def get_logprobs_subsample(self, cond, chains_prev, chains_next, denoising_inds, get_ent=False, use_base_policy=False):
+        """One (prev, next) pair per row with its denoising index -> (B, Ta, Da) [, eta (B, 1, 1)]."""
+        eng = self.engine()
+        actor = self.actor if use_base_policy else self.actor_ft
+        eps = actor(chains_prev, self._ft_timesteps(denoising_inds), cond=cond)
+        logp = _LogProbRows.apply(eps, eng, chains_prev, chains_next, denoising_inds)
+        if get_ent:
+            if self.use_ddim:
+                etas = self.eta(cond).unsqueeze(1)
+            else:
+                etas = torch.ones_like(logp)
+            return logp, etas
+        return logp

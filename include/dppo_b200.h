@@ -1,0 +1,182 @@
+/*
+ * dppo_b200 — C ABI of the B200-native DPPO hot path (libdppo_b200.so).
+ *
+ * The reference (enyen/dppo) has no FFI: its seam is the Python class named by Hydra `_target_`
+ * (dppo/agent/finetune/train_agent.py:84) and the duck-typed method calls of
+ * TrainPPODiffusionAgent.run (dppo/agent/finetune/train_ppo_diffusion_agent.py:47-483).  This header is the
+ * C boundary a replacement for those methods binds; every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every data pointer is a CUDA device pointer owned by the caller (contiguous, fp32 row-major unless stated);
+ *     pointers inside the *_desc structs are HOST pointers, read during the call only;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no call synchronises the device;
+ *   - return value 0 = success, < 0 = error code below; dppo_last_error() returns a thread-local message;
+ *   - a context is not thread-safe (the reference agent is single-threaded per process); the library allocates
+ *     device memory only inside dppo_ctx_create / dppo_pack_* (CUDA-graph friendly afterwards).
+ */
+#ifndef DPPO_B200_H_
+#define DPPO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPPO_OK 0
+#define DPPO_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define DPPO_ERR_CUDA (-2)        /* CUDA runtime error (message holds cudaGetErrorString) */
+#define DPPO_ERR_UNSUPPORTED (-3) /* feature outside the hot path (e.g. learned eta) */
+#define DPPO_ERR_STATE (-4)       /* call order violated (e.g. weights not packed) */
+
+#define DPPO_ACT_RELU 0
+#define DPPO_ACT_MISH 1
+
+#define DPPO_NET_ACTOR 0    /* frozen base policy  (state_dict keys actor.*)    */
+#define DPPO_NET_ACTOR_FT 1 /* fine-tuned policy   (state_dict keys actor_ft.*) */
+
+#define DPPO_PRECISION_SPLIT3 0 /* 3 x bf16 split MMAs (hi/lo operands), meets the fp32 1e-3 tolerance */
+#define DPPO_PRECISION_BF16 1   /* single-pass bf16 MMAs, fast mode */
+
+typedef struct dppo_ctx dppo_ctx;
+
+/* DiffusionMLP geometry.  reference dppo/model/diffusion/mlp_diffusion.py:174-216, dppo/model/common/mlp.py:84-154 */
+typedef struct dppo_mlp_desc {
+  int32_t cond_dim;      /* To * Do, flattened observation */
+  int32_t action_dim;    /* Da */
+  int32_t horizon_steps; /* Ta */
+  int32_t time_dim;      /* sinusoidal embedding width d; time MLP is Lin(d,2d) Mish Lin(2d,d) */
+  int32_t hidden_dim;    /* H of the residual trunk (multiple of 128) */
+  int32_t n_blocks;      /* number of two-layer pre-activation residual blocks */
+  int32_t activation;    /* DPPO_ACT_* of the trunk (time / cond MLPs are Mish resp. trunk activation) */
+  int32_t use_layernorm; /* LayerNorm(eps=1e-6) before each activation inside the blocks */
+  int32_t cond_hidden;   /* cond_mlp_dims[0], 0 = no cond_mlp */
+  int32_t cond_out;      /* cond_mlp_dims[1] */
+} dppo_mlp_desc;
+
+/* Schedule tables exactly as the reference builds them (fp32 tensors from the float64 cosine schedule).
+ * reference dppo/model/diffusion/diffusion.py:98-148 (DDPM), :155-196 (DDIM, already flipped: index 0 = noisiest) */
+typedef struct dppo_sched_desc {
+  int32_t denoising_steps;    /* K */
+  int32_t ft_denoising_steps; /* ft */
+  int32_t use_ddim;
+  int32_t ddim_steps; /* S when use_ddim */
+  float eta;          /* the value EtaFixed returns (dppo/model/diffusion/eta.py:33-40); learned eta unsupported */
+  float denoised_clip_value;     /* < 0: none */
+  float randn_clip_value;
+  float final_action_clip_value; /* < 0: none */
+  float eps_clip_value;          /* < 0: none (DDIM only) */
+  float min_logprob_denoising_std;
+  const float* sqrt_recip_alphas_cumprod;   /* [K] host */
+  const float* sqrt_recipm1_alphas_cumprod; /* [K] host */
+  const float* ddpm_mu_coef1;               /* [K] host */
+  const float* ddpm_mu_coef2;               /* [K] host */
+  const float* ddpm_logvar_clipped;         /* [K] host */
+  const int32_t* ddim_t;                    /* [S] host or NULL */
+  const float* ddim_alphas;                 /* [S] host or NULL */
+  const float* ddim_alphas_prev;            /* [S] host or NULL */
+  const float* ddim_sqrt_one_minus_alphas;  /* [S] host or NULL */
+} dppo_sched_desc;
+
+/* PPO hyper-parameters of one loss call.  reference dppo/model/diffusion/diffusion_ppo.py:25-36,57-199 */
+typedef struct dppo_loss_hp {
+  int32_t ft_denoising_steps;
+  int32_t horizon_steps;  /* Ta */
+  int32_t action_dim;     /* Da */
+  int32_t reward_horizon; /* rows h < reward_horizon enter the mean */
+  int32_t norm_adv;
+  float gamma_denoising;
+  float clip_ploss_coef, clip_ploss_coef_base, clip_ploss_coef_rate;
+  float clip_vloss_coef; /* < 0: unclipped value loss */
+  float adv_clip_lo;     /* bounds applied AFTER normalisation; the caller passes quantile values, or */
+  float adv_clip_hi;     /* -inf / +inf to let the kernel use min / max (quantiles 0 / 1 = no-op)    */
+} dppo_loss_hp;
+
+const char* dppo_last_error(void);
+int dppo_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+/* Replaces the constructor-time table building of DiffusionModel.__init__ (diffusion.py:98-196). */
+int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const dppo_sched_desc* sched, int precision, int device);
+int dppo_ctx_destroy(dppo_ctx* ctx);
+
+/* Repack one network's fp32 parameters into the kernel layout (swizzled bf16 hi/lo weight tiles in streaming order,
+ * per-timestep layer-0 bias table that folds the time-embedding MLP).  Call whenever the parameters change
+ * (after every optimiser step for actor_ft; after VPGDiffusion.step(), diffusion_vpg.py:123-127).
+ * `params` is a HOST array of DEVICE pointers in state_dict order of DiffusionMLP:
+ *   time_embedding.1.{weight,bias}, time_embedding.3.{weight,bias},
+ *   [cond_mlp.moduleList.0.linear_1.{weight,bias}, cond_mlp.moduleList.1.linear_1.{weight,bias}],
+ *   mlp_mean.layers.0.{weight,bias},
+ *   per block b: l1.{weight,bias}, l2.{weight,bias}, [norm1.{weight,bias}, norm2.{weight,bias}],
+ *   mlp_mean.layers.{n_blocks+1}.{weight,bias}                                                              */
+int dppo_pack_mlp(dppo_ctx* ctx, int which, const float* const* params, int n_params, void* stream);
+
+/* ---- rollout: K-step denoising chain ------------------------------------------------------------------------- */
+/* Replaces VPGDiffusion.forward + p_mean_var (diffusion_vpg.py:139-315) and DiffusionMLP.forward
+ * (mlp_diffusion.py:218-250) for all envs and all S steps in ONE persistent kernel launch.
+ *   state  [E, cond_dim]                       traj  [E, Ta*Da]
+ *   noise  [(S+1), E, Ta*Da] or NULL           chain [E, ft+1, Ta*Da] or NULL
+ * noise slot 0 is x_T, slot i+1 the draw of step i BEFORE the +-randn_clip clamp (what torch.randn / randn_like
+ * return at diffusion_vpg.py:258,294).  With noise == NULL the kernel draws Philox4x32-10 normals from
+ * (seed, offset).  env_offset shifts the Philox counter for env-sharded multi-GPU runs.                          */
+int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, const float* noise, uint64_t seed,
+                      uint64_t offset, int64_t env_offset, int deterministic, int use_base_policy,
+                      float min_sampling_denoising_std, float* traj, float* chain, void* stream);
+
+/* Replaces VPGDiffusion.get_logprobs (diffusion_vpg.py:319-396): log-density of every fine-tuned transition of
+ * stored chains, network evaluation included.
+ *   state [Bc, cond_dim], chains [Bc, ft+1, Ta*Da]  ->  logp [Bc*ft, Ta*Da]  (row = env-major, denoise-minor)   */
+int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const float* chains, int n_rows, int use_base_policy,
+                        float* logp, void* stream);
+
+/* ---- update: elementwise halves of get_logprobs_subsample + PPODiffusion.loss -------------------------------- */
+/* Gaussian log-density given the network output (diffusion_vpg.py:165-224,453-458), per-row denoising index.
+ *   eps, x_prev, x_next, logp: [B, Ta*Da]; denoising_inds [B] int64                                              */
+int dppo_logprob_rows(dppo_ctx* ctx, const float* eps, const float* x_prev, const float* x_next,
+                      const int64_t* denoising_inds, int n_rows, float* logp, float* dlogp_deps /* or NULL */,
+                      void* stream);
+
+/* Fused minibatch gather + log-prob + clipped PPO loss, forward AND closed-form backward in one pass
+ * (train_ppo_diffusion_agent.py:316-327 gathers; diffusion_vpg.py:398-461; diffusion_ppo.py:57-199).
+ *   rollout buffers (all N = n_steps*n_envs rows): chains [N, ft+1, D], old_logprobs [N, ft, D],
+ *     returns [N], old_values [N], advantages [N]
+ *   minibatch: inds_all [global_rows] int64 flat indices into (N, ft) of the WHOLE minibatch (b = idx / ft,
+ *     d = idx % ft; advantage statistics are minibatch-global); this rank owns rows
+ *     [row_begin, row_begin + n_rows) of it; eps [n_rows, D] = actor_ft output for (chains[b,d], t_d, obs[b]);
+ *     vpred [n_rows] = critic(obs[b]); global_rows = divisor of every mean
+ *   outputs: grad_eps [n_rows, D] = d pg_loss / d eps, grad_vpred [n_rows] = d v_loss / d vpred,
+ *     scalars[8] (sums over this rank's rows, ALREADY divided by global_rows, so a sum over ranks is the mean):
+ *       0 pg_loss, 1 v_loss, 2 approx_kl, 3 clipfrac, 4 ratio, 5 reserved, 6 adv mean, 7 adv std
+ *   workspace: >= 128 bytes of device scratch, 8-byte aligned.                                                   */
+int dppo_ppo_loss_fwd_bwd(dppo_ctx* ctx, const float* chains, const float* old_logprobs, const float* returns,
+                          const float* old_values, const float* advantages, const int64_t* inds_all, int row_begin,
+                          const float* eps, const float* vpred, int n_rows, int global_rows, const dppo_loss_hp* hp,
+                          float* grad_eps, float* grad_vpred, float* scalars, void* workspace, void* stream);
+
+/* Same loss with the inputs ALREADY gathered per minibatch row, i.e. the argument list of PPODiffusion.loss
+ * (diffusion_ppo.py:57-69): x_prev / x_next / old_logprobs [B, D], returns / old_values / advantages [B],
+ * denoising_inds [B] int64.  Single-process semantics: every mean is over these B rows.                          */
+int dppo_ppo_loss_rows(dppo_ctx* ctx, const float* x_prev, const float* x_next, const float* old_logprobs,
+                       const float* returns, const float* old_values, const float* advantages,
+                       const int64_t* denoising_inds, const float* eps, const float* vpred, int n_rows,
+                       const dppo_loss_hp* hp, float* grad_eps, float* grad_vpred, float* scalars, void* workspace,
+                       void* stream);
+
+/* ---- GAE ------------------------------------------------------------------------------------------------------ */
+/* Reverse scan of train_ppo_diffusion_agent.py:255-279, one thread per env, float64 like the reference's numpy.
+ *   reward, terminated, values: [n_steps, n_envs] float64; next_value [n_envs] float64 (critic of the post-rollout
+ *   observation); outputs advantages, returns [n_steps, n_envs] float64.                                        */
+int dppo_gae_f64(const double* reward, const double* terminated, const double* values, const double* next_value,
+                 int n_steps, int n_envs, double gamma, double gae_lambda, double reward_scale_const,
+                 double* advantages, double* returns, void* stream);
+
+/* ---- bring-up ------------------------------------------------------------------------------------------------- */
+/* Single-CTA tcgen05 GEMM that validates the shared-memory / instruction descriptor encodings on hardware:
+ * c[128,N] = a[128,K] * b[N,K]^T in bf16 with fp32 accumulation.  scratch >= K/64 * 16 KiB.                      */
+int dppo_selftest_umma(const float* a, const float* b, float* c, void* scratch, int N, int K, uint64_t desc_hi,
+                       uint32_t idesc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPPO_B200_H_ */
