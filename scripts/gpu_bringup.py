@@ -34,7 +34,7 @@ import numpy as np, torch
 from tests.helpers import *
 from tests.test_gpu_parity import rel_err
 import time
-for case in CASES:
+for case in __CASES__:
     spec = GOLDEN_CASES[case]; w = get_workload(spec['workload'])
     model = build_model(w, 'cuda:0', our_classes()); gold = load_golden(case)
     inp = make_inputs(w, spec['n_envs'], spec['mb_rows'])
@@ -45,14 +45,15 @@ for case in CASES:
     print(case, 'chains maxrel', e.max(), 'frac>1e-3', (e > 1e-3).mean(), 'first call s', round(time.time() - t0, 3))
     for s in range(e.shape[1]):
         print('   slot', s, 'maxrel', e[:, s].max())
-    lp = model.get_logprobs({'state': inp['state'].cuda()}, torch.from_numpy(gold['chains']).cuda())
+    with torch.no_grad():
+        lp = model.get_logprobs({'state': inp['state'].cuda()}, torch.from_numpy(gold['chains']).cuda())
     torch.cuda.synchronize()
     e2 = rel_err(lp.cpu().numpy(), gold['logprobs'])
     print(case, 'logprobs maxrel', e2.max(), 'frac>1e-3', (e2 > 1e-3).mean())
 """,
 }
-STAGES["chain_all"] = STAGES["chain_hopper"].replace("CASES", "['walker2d', 'transport_k20', 'transport', 'furniture', 'furniture_ddpm100']")
-STAGES["chain_hopper"] = STAGES["chain_hopper"].replace("CASES", "['hopper']")
+STAGES["chain_all"] = STAGES["chain_hopper"].replace("__CASES__", "['walker2d', 'transport_k20', 'transport', 'furniture', 'furniture_ddpm100']")
+STAGES["chain_hopper"] = STAGES["chain_hopper"].replace("__CASES__", "['hopper']")
 STAGES["loss"] = """
 import pytest, sys
 sys.exit(pytest.main(['-x', '-q', 'tests/test_gpu_parity.py', '-k', 'loss']))
