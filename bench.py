@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""
+bench.py — DPPO hot-path benchmark (contract: see the repo's task statement; design notes in DESIGN.md §Measurement).
+
+One "step" = one rollout decision for every environment of the workload: the S-step denoising chain
+(VPGDiffusion.forward with return_chain=True) over E synthetic observations.  Metric = policy env-steps/s
+= E * act_steps / t_step, the reference's own step accounting (train_ppo_diffusion_agent.py:151).
+
+  value      chain kernel with inputs resident in HBM (CUDA events around each step, L2 flushed between steps)
+  e2e        the same through the reference-shaped call model(cond=...) with pinned HOST observations copied in and
+             trajectories + chains copied back every step (what the agent does at train_ppo_diffusion_agent.py:107-122)
+  update     PPO-update samples/s: fused gather+log-prob+loss kernel, autograd backward, optimiser steps (secondary)
+  roofline   tensor-core roofline of the chain kernel from the algorithmic FLOPs S * F_net per decision
+  cpu_baseline / --impl reference   the CPU oracle port of the reference path on this box's host cores
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from dppo_b200.workloads import chain_evals, get_workload  # noqa: E402
+
+METRIC = "policy env-steps/sec (K-step denoise)"
+UNIT = "env-steps/s"
+
+
+def net_flops_per_sample(w):
+    """Forward FLOPs of one denoiser evaluation (2 * MACs of every Linear), SURVEY.md §8 F_net."""
+    a = w["actor"]
+    D, cond = w["horizon_steps"] * w["action_dim"], w["obs_dim"] * w["cond_steps"]
+    td, dims = a["time_dim"], a["mlp_dims"]
+    macs = td * 2 * td + 2 * td * td
+    c_out = cond
+    if a.get("cond_mlp_dims"):
+        c0, c1 = a["cond_mlp_dims"]
+        macs += cond * c0 + c0 * c1
+        c_out = c1
+    H = dims[0]
+    macs += (D + td + c_out) * H + (len(dims) - 1) * H * H + H * D
+    return 2 * macs
+
+
+def workload_name(w, E):
+    kind = f"DDIM-{w['ddim_steps']}" if w["use_ddim"] else f"DDPM K={w['denoising_steps']}"
+    return (f"{w['yaml'].split('/')[2]} ft_ppo_diffusion_mlp, {E} synthetic envs, obs {w['obs_dim']}, act {w['action_dim']}, "
+            f"Tp=Ta={w['horizon_steps']}, {kind}, ft={w['ft_denoising_steps']}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_chain_seconds(w, E, reps, warmup, threads):
+    """Oracle port of VPGDiffusion.forward on the host cores (both networks on fine-tuned steps, like the reference)."""
+    from oracle import dppo_oracle as O
+    from tests.helpers import build_model, make_inputs, oracle_cfgs, oracle_params, our_classes
+
+    torch.set_num_threads(threads)
+    model = build_model(w, "cpu", our_classes())
+    nc, dc = oracle_cfgs(w)
+    p = oracle_params(model)
+    inp = make_inputs(w, E, 8)
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        O.sample_chain(p, nc, dc, inp["state"], inp["noise"], faithful_cost=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, w, E, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times = cpu_chain_seconds(w, E, args.steps, args.warmup, cores)
+    t = sum(times) / len(times)
+    value = E * w["act_steps"] / t
+    sample = f"{args.steps} full chains over all {E} envs (oracle port of the reference path, torch CPU fp32, {cores} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(w, E)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args, w, E, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from tests.helpers import build_model, our_classes
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(w, str(dev), our_classes())
+    model.engine_precision = args.precision
+    eng = model.engine()
+    S, ft, D, Do = chain_evals(w), w["ft_denoising_steps"], w["horizon_steps"] * w["action_dim"], w["obs_dim"] * w["cond_steps"]
+    rng = np.random.default_rng(1000 + rank)
+    n_bufs = 4
+    states = [torch.from_numpy(rng.uniform(-1, 1, (E, w["cond_steps"], w["obs_dim"])).astype(np.float32)).to(dev) for _ in range(n_bufs)]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    min_std = float(model.get_min_sampling_denoising_std())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def kernel_step(i):
+        return eng.sample(states[i % n_bufs], noise=None, seed=42, offset=i + 1, env_offset=rank * E, min_sampling_std=min_std)
+
+    # ---- value: kernel-resident throughput
+    for i in range(args.warmup):
+        flush.zero_()
+        kernel_step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        ev[i][0].record()
+        kernel_step(i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+
+    # ---- e2e: pinned host obs in, trajectories + chains out, through the reference-shaped call
+    host_obs = [torch.from_numpy(rng.uniform(-1, 1, (E, w["cond_steps"], w["obs_dim"])).astype(np.float32)).pin_memory() for _ in range(n_bufs)]
+    host_traj = torch.empty((E, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
+    host_chain = torch.empty((E, ft + 1, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        obs = host_obs[i % n_bufs].to(dev, non_blocking=True)
+        out = model(cond={"state": obs}, deterministic=False, return_chain=True)
+        host_traj.copy_(out.trajectories, non_blocking=True)
+        host_chain.copy_(out.chains, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the agent consumes the actions on the host every step
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+
+    # ---- update (secondary): one PPO minibatch = fused loss kernel + autograd backward + both optimiser steps
+    upd = bench_update(args, w, model, dev, E, rank, world) if args.update else None
+
+    t = torch.tensor([total_ms, e2e_s, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, wall = t.tolist()
+    if rank == 0:
+        act = w["act_steps"]
+        value = world * E * act * args.steps / (total_ms * 1e-3)
+        e2e_value = world * E * act * args.steps / e2e_s
+        fnet = net_flops_per_sample(w)
+        flops_launch = float(S) * fnet * E
+        k_ms = total_ms / args.steps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        achieved = flops_launch / (k_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3" if args.precision == "split3" else "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(w, E), "envs_per_gpu": E, "precision": args.precision,
+                       "l2": "flushed between timed steps (512 MiB memset outside the event pairs)",
+                       "weights": "random init seed 42, actor_ft perturbed 1e-2", "noise": "in-kernel Philox4x32-10"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
+                    "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": args.steps,
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "chain_mlp_kernel",
+                         "note": ("algorithmic FLOPs S*F_net*E (1x); split3 issues 3 bf16 MMAs per logical MMA so frac <= 1/3; "
+                                  + ("peak = MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "peak = fallback 1.59 PF"))},
+            "wall_s_timed_region": wall,
+            "update": upd,
+        }
+        if args.cpu_baseline:
+            cores = os.cpu_count() or 1
+            reps = max(3, min(10, int(15.0 / max(0.05, 0.16e-3 * E))))
+            times = cpu_chain_seconds(w, E, reps, 1, cores)
+            tc = sum(times) / len(times)
+            line["cpu_baseline"] = {"value": E * act / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{reps} full chains over {E} envs, oracle port, torch CPU fp32, {cores} threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_update(args, w, model, dev, E, rank, world):
+    """PPO-update samples/s on synthetic rollout buffers produced by the sampler itself."""
+    import torch.distributed as dist
+
+    ft, Ta, Da = w["ft_denoising_steps"], w["horizon_steps"], w["action_dim"]
+    n_steps = max(1, min(w["train"]["n_steps"], (1 << 21) // max(1, E * ft)))
+    N = n_steps * E
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    obs_k = torch.rand((N, w["cond_steps"], w["obs_dim"]), device=dev, generator=g) * 2 - 1
+    chains_k = torch.empty((N, ft + 1, Ta, Da), device=dev)
+    with torch.no_grad():
+        for s in range(n_steps):
+            chains_k[s * E:(s + 1) * E] = model(cond={"state": obs_k[s * E:(s + 1) * E]}).chains
+        logprobs_k = torch.empty((N, ft, Ta, Da), device=dev)
+        chunk = 32768
+        for s in range(0, N, chunk):
+            logprobs_k[s:s + chunk] = model.get_logprobs({"state": obs_k[s:s + chunk]}, chains_k[s:s + chunk]).view(-1, ft, Ta, Da)
+        values_k = model.critic({"state": obs_k}).view(-1)
+    adv_k = torch.randn(N, device=dev, generator=g)
+    ret_k = adv_k + values_k
+    bs = min(w["train"]["batch_size"], N * ft)
+    per_rank = bs // world
+    opt_a = torch.optim.AdamW(model.actor_ft.parameters(), lr=w["train"]["actor_lr"])
+    opt_c = torch.optim.AdamW(model.critic.parameters(), lr=w["train"]["critic_lr"])
+    params = [p for p in list(model.actor_ft.parameters()) + list(model.critic.parameters()) if p.requires_grad]
+
+    def minibatch(k):
+        inds = torch.randperm(N * ft, device=dev)[:bs]
+        if world > 1:
+            dist.broadcast(inds, 0)
+        res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=rank * per_rank,
+                                  row_count=per_rank, reward_horizon=w["act_steps"])
+        loss = res[0] + w["train"]["vf_coef"] * res[2]
+        opt_a.zero_grad(set_to_none=False)
+        opt_c.zero_grad(set_to_none=False)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+                o += p.numel()
+        opt_a.step()
+        opt_c.step()
+
+    for k in range(3):
+        minibatch(k)
+    torch.cuda.synchronize(dev)
+    reps = 10
+    t0 = time.perf_counter()
+    for k in range(reps):
+        minibatch(k)
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
+            "minibatch_rows": per_rank * world, "buffer_rows": N * ft,
+            "path": "fused gather+log-prob+loss fwd/bwd kernel; network GEMMs via torch autograd (cuBLAS); AdamW torch"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="walker2d")
+    ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default: the workload's n_envs)")
+    ap.add_argument("--precision", default="split3", choices=["split3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-update", dest="update", action="store_false", help="skip the secondary PPO-update measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    w = get_workload(args.workload)
+    E = args.envs or w["n_envs"]
+    if args.impl == "reference":
+        run_reference(args, w, E, rank, world)
+    else:
+        run_b200(args, w, E, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -213,3 +213,10 @@ extern "C" int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const floa
   return sample_chain_impl(ctx, state, n_rows, nullptr, 0, 0, 0, 0, use_base_policy, ctx->min_logprob_std, nullptr,
                            nullptr, chains, logp, static_cast<cudaStream_t>(stream));
 }
+
+// bring-up hook (not in the public header): the chain kernel writes 8 cycle counters per CTA into `buf`
+extern "C" int dppo_debug_set_prof(dppo_ctx* ctx, unsigned long long* buf) {
+  if (!ctx) return DPPO_ERR_INVALID;
+  ctx->d_prof = buf;
+  return DPPO_OK;
+}

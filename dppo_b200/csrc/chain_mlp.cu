@@ -50,6 +50,7 @@ struct ChainArgs {
   float* logp;
   uint64_t seed, offset;
   int64_t env_offset;
+  unsigned long long* prof;  // optional [grid][16] cycle counters (bring-up / profiling), nullptr in production
 };
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
@@ -144,84 +145,115 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
 
   if (warp == 0) {
     // ======================================================================================= weight-tile producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      int cur_net = -1;
-      for (int step = a.first_step; step < a.S; ++step) {
-        const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
-        for (int part = 0; part < 2; ++part) {
-          const uint8_t* src;
-          uint32_t n;
-          if (part == 0) {
-            if (!(a.CH && net != cur_net)) continue;
-            src = a.tiles[net], n = a.n_cond_tiles;
-          } else {
-            src = a.tiles[net] + a.off_step_tiles, n = a.n_step_tiles;
-          }
-          for (uint32_t i = 0; i < n; ++i) {
-            mbar_wait(&s.empty[stage], phase ^ 1);
+    // (whole warp runs the loop so control flow stays uniform; one elected lane issues the copies)
+    uint32_t stage = 0, phase = 0;
+    int cur_net = -1;
+    long long p_wait = 0;
+    const long long p_t0 = clock64();
+    for (int step = a.first_step; step < a.S; ++step) {
+      const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
+      for (int part = 0; part < 2; ++part) {
+        const uint8_t* src;
+        uint32_t n;
+        if (part == 0) {
+          if (!(a.CH && net != cur_net)) continue;
+          src = a.tiles[net], n = a.n_cond_tiles;
+        } else {
+          src = a.tiles[net] + a.off_step_tiles, n = a.n_step_tiles;
+        }
+        for (uint32_t i = 0; i < n; ++i) {
+          const long long tw = clock64();
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          p_wait += clock64() - tw;
+          if (elect_one()) {
             mbar_arrive_expect_tx(&s.full[stage], kTile);
             bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
-            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           }
+          __syncwarp();
+          if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
         }
-        cur_net = net;
       }
+      cur_net = net;
     }
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = p_wait, a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0;
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, NE);
-      uint32_t stage = 0, phase = 0, xr_phase = 0;
-      auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc) {
-        mbar_wait(s.x_ready, xr_phase);
-        xr_phase ^= 1;
-        tc_fence_after();
-        const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-        for (int mt = 0; mt < MTl; ++mt) {
-          const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
-          for (int kc = 0; kc < KCl; ++kc) {
-            const uint32_t boff = uint32_t(kc) * NE * 128;
-            mbar_wait(&s.full[stage], phase);
-            tc_fence_after();
-            uint32_t wa = smem_u32(s.ring + size_t(stage) * kTile);
+    // Whole warp runs the loop (uniform control flow => descriptor arithmetic stays in uniform registers); one elected
+    // lane issues tcgen05.mma / tcgen05.commit.
+    const uint32_t idesc = umma_idesc_bf16(128, NE);
+    uint32_t stage = 0, phase = 0, xr_phase = 0;
+    long long m_wait_x = 0, m_wait_full = 0;
+    const long long m_t0 = clock64();
+    const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
+    auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc) {
+      long long tw = clock64();
+      mbar_wait(s.x_ready, xr_phase);
+      m_wait_x += clock64() - tw;
+      xr_phase ^= 1;
+      tc_fence_after();
+      const uint32_t bh = umma_desc_lo(smem_u32(b_hi)), bl = umma_desc_lo(smem_u32(b_lo));
+      for (int mt = 0; mt < MTl; ++mt) {
+        const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
+        for (int kc = 0; kc < KCl; ++kc) {
+          const uint32_t boff = uint32_t(kc) * (NE * 128 / 16);
+          tw = clock64();
+          mbar_wait(&s.full[stage], phase);
+          m_wait_full += clock64() - tw;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t wa = ring_lo + stage * (kTile / 16);
+            if (acc || kc > 0) {
+              umma_bf16_lo(d, wa, bh + boff, idesc, true);
+            } else {
+              umma_bf16_lo(d, wa, bh + boff, idesc, false);
+            }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d, umma_desc(wa + k * 32), umma_desc(bh + boff + k * 32), idesc, (acc || kc > 0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + boff + 2 * k, idesc, true);
             if (split) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc(wa + k * 32), umma_desc(bl + boff + k * 32), idesc, 1u);
+              for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bl + boff + 2 * k, idesc, true);
             }
             umma_commit(&s.empty[stage]);
-            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
-            if (split) {
-              mbar_wait(&s.full[stage], phase);
-              tc_fence_after();
-              wa = smem_u32(s.ring + size_t(stage) * kTile);
+          }
+          __syncwarp();
+          if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+          if (split) {
+            tw = clock64();
+            mbar_wait(&s.full[stage], phase);
+            m_wait_full += clock64() - tw;
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t wa = ring_lo + stage * (kTile / 16);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc(wa + k * 32), umma_desc(bh + boff + k * 32), idesc, 1u);
+              for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + boff + 2 * k, idesc, true);
               umma_commit(&s.empty[stage]);
-              if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
             }
+            __syncwarp();
+            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           }
         }
-        umma_commit(s.layer_done);
-      };
-      int cur_net = -1;
-      for (int step = a.first_step; step < a.S; ++step) {
-        const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
-        if (a.CH && net != cur_net) {
-          run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false);
-          run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false);
-        }
-        cur_net = net;
-        run_layer(s.x0_hi, s.x0_lo, a.MT, a.KC0, col_h, false);
-        for (int b = 0; b < a.nb; ++b) {
-          run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_y, false);
-          run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_h, true);
-        }
-        run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false);
       }
+      if (elect_one()) umma_commit(s.layer_done);
+      __syncwarp();
+    };
+    int cur_net = -1;
+    for (int step = a.first_step; step < a.S; ++step) {
+      const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
+      if (a.CH && net != cur_net) {
+        run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false);
+        run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false);
+      }
+      cur_net = net;
+      run_layer(s.x0_hi, s.x0_lo, a.MT, a.KC0, col_h, false);
+      for (int b = 0; b < a.nb; ++b) {
+        run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_y, false);
+        run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_h, true);
+      }
+      run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false);
+    }
+    if (a.prof && lane == 0) {
+      a.prof[blockIdx.x * 16 + 2] = m_wait_x, a.prof[blockIdx.x * 16 + 3] = m_wait_full;
+      a.prof[blockIdx.x * 16 + 4] = clock64() - m_t0;
     }
   } else {
     // ======================================================================================= epilogue warps
@@ -234,8 +266,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     uint32_t ld_phase = 0;
     float xreg[CPT];
 
+    long long e_wait = 0;
+    const long long e_t0 = clock64();
     auto wait_layer = [&]() {
+      const long long tw = clock64();
       mbar_wait(s.layer_done, ld_phase);
+      e_wait += clock64() - tw;
       ld_phase ^= 1;
       tc_fence_after();
     };
@@ -482,6 +518,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       }
       signal_x();
     }
+    if (a.prof && et == 0) a.prof[blockIdx.x * 16 + 5] = e_wait, a.prof[blockIdx.x * 16 + 6] = clock64() - e_t0;
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 8 + (warp - 2)] = (clock64() - e_t0) - e_wait;
   }
 
   tc_fence_before();
@@ -527,6 +565,7 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   a.eps_clip = ctx->eps_clip;
   a.state = state, a.E = E, a.noise = noise, a.traj = traj, a.chain = chain, a.chains_in = chains_in, a.logp = logp;
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
+  a.prof = ctx->d_prof;
 
   const size_t fixed = smem_fixed_bytes(g);
   const size_t budget = 232448;

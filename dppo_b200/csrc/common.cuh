@@ -28,12 +28,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the warp instead of burning issue slots of its scheduler
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
       : "memory");
   return ok != 0;
 }
@@ -45,13 +46,31 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) {
-      printf("dppo_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
+    if ((++spins & 0xFF) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        printf("dppo_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
+}
+
+// one lane of the (converged) warp gets true; keeps surrounding address arithmetic in the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      :
+      : "memory");
+  return pred != 0;
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
@@ -104,6 +123,21 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint64_t high_
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// same, with the constant high word split off so that stepping K is a single 32-bit add on the low word
+constexpr uint32_t kDescHi32 = uint32_t(kDescSw128KMajor >> 32);
+constexpr uint32_t kDescLoFlags = uint32_t(kDescSw128KMajor & 0xFFFFFFFFull);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return kDescLoFlags | ((smem_addr >> 4) & 0x3FFF); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  const uint64_t a = (uint64_t(kDescHi32) << 32) | a_lo, b = (uint64_t(kDescHi32) << 32) | b_lo;
+  if (accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc) : "memory");
+  }
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread

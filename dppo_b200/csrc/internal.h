@@ -74,7 +74,6 @@ struct dppo_ctx {
   float eta = 1.f, x0_clip = 1.f, randn_clip = 3.f, final_clip = -1.f, eps_clip = -1.f, min_logprob_std = 0.1f;
   std::vector<dppo::StepRow> rows;        // host copy, S rows
   dppo::StepRow* d_rows = nullptr;        // device copy
-  dppo::StepRow* d_rows_call = nullptr;   // per-call scratch (std floors applied), 2 x S rows
   dppo::PackedNet nets[2];
-  float* d_time_scratch = nullptr;
+  unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

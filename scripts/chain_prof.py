@@ -1,0 +1,39 @@
+"""Per-role cycle counters of the chain kernel (bring-up aid).  python scripts/chain_prof.py [workload] [envs] [precision]"""
+import ctypes as C
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from dppo_b200 import _lib
+from dppo_b200.workloads import get_workload
+from tests.helpers import build_model, our_classes
+
+name = sys.argv[1] if len(sys.argv) > 1 else "walker2d"
+w = get_workload(name)
+E = int(sys.argv[2]) if len(sys.argv) > 2 else w["n_envs"]
+prec = sys.argv[3] if len(sys.argv) > 3 else "split3"
+model = build_model(w, "cuda:0", our_classes())
+model.engine_precision = prec
+eng = model.engine()
+grid = (E + 31) // 32
+prof = torch.zeros(grid * 16, dtype=torch.int64, device="cuda")
+lib = _lib.load()
+lib.dppo_debug_set_prof.argtypes = [C.c_void_p, C.c_void_p]
+lib.dppo_debug_set_prof(eng.ctx, C.c_void_p(prof.data_ptr()))
+state = torch.rand(E, 1, w["obs_dim"], device="cuda") * 2 - 1
+for _ in range(3):
+    eng.sample(state)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+eng.sample(state)
+b.record()
+torch.cuda.synchronize()
+p = prof.view(grid, 16).cpu()
+used = p[p[:, 4] > 0]
+names = ["prod_wait_empty", "prod_total", "mma_wait_x", "mma_wait_full", "mma_total", "epi_wait_layer", "epi_total", "-"] + [f"epi_work_warp{i+2}" for i in range(8)]
+print(f"{name} E={E} {prec}: kernel {a.elapsed_time(b):.3f} ms, {len(used)} CTAs")
+for i, n in enumerate(names):
+    col = used[:, i].double()
+    print(f"  {n:16s} mean {col.mean() / 1e3:10.1f} kcyc   max {col.max() / 1e3:10.1f} kcyc")
