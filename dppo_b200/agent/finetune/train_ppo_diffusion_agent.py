@@ -1,0 +1,321 @@
+"""
+DPPO fine-tuning loop, B200-native.
+
+TrainPPODiffusionAgent -> /root/reference/dppo/agent/finetune/train_ppo_diffusion_agent.py:21-483 (+ the constructor
+chain train_ppo_agent.py:16-89, train_agent.py:21-120).  Same config keys, same iteration structure
+(eval / train iterations, rollout of n_steps decisions, old log-probs + values, reward scaling, GAE, update_epochs x
+minibatches with the KL early stop, LR schedules, model.step(), checkpoints with the reference's state_dict keys).
+What changed is where the data lives and what executes the hot path:
+
+  rollout     model(cond) = ONE persistent sm_100a kernel per decision (dppo_sample_chain); chains are written into a
+              device-resident (n_steps, E, ft+1, Ta, Da) fp32 buffer - only the action chunk goes back to the host for
+              the simulator (the reference copies actions AND chains to float64 numpy every step, :117-145).
+  prologue    get_logprobs (dppo_chain_logprobs) and the critic run on the device buffers in chunks of
+              logprob_batch_size; GAE is dppo_gae_f64 (float64, one thread per env) instead of a host numpy loop.
+  update      the minibatch gathers are fused into dppo_ppo_loss_fwd_bwd (indices from the unchanged torch.randperm);
+              one device->host read per minibatch (the reference does 4 .item()s + Bmb element reads).
+  multi-GPU   envs are sharded over ranks, rollout buffers all-gathered once per iteration, every minibatch is split
+              into contiguous per-rank slices and gradients + diagnostics are summed by ONE all-reduce of a flat buffer
+              (dppo_b200/distributed.py); W ranks reproduce the single-process update.
+
+There is no CPU fallback: the model's methods raise without a CUDA device.
+"""
+
+import logging
+import math
+import os
+import pickle
+import random
+import time
+
+import numpy as np
+import torch
+
+from dppo_b200 import distributed as D
+from dppo_b200 import engine as E_
+from dppo_b200.util.config import instantiate
+from dppo_b200.util.reward_scaling import RunningRewardScaler
+
+log = logging.getLogger(__name__)
+
+
+def cosine_warmup_lr(step, first_cycle_steps, max_lr, min_lr, warmup_steps):
+    """Learning rate after `step` scheduler steps: linear warm-up from min_lr, then cosine to min_lr, restarting every
+    first_cycle_steps (what util/scheduler.py's CosineAnnealingWarmupRestarts yields with cycle_mult = gamma = 1;
+    before the first scheduler step the optimiser sits at min_lr)."""
+    if step < 0:
+        return min_lr
+    s = step % first_cycle_steps
+    if s < warmup_steps:
+        return (max_lr - min_lr) * s / warmup_steps + min_lr
+    return min_lr + (max_lr - min_lr) * (1 + math.cos(math.pi * (s - warmup_steps) / (first_cycle_steps - warmup_steps))) / 2
+
+
+class TrainPPODiffusionAgent:
+    def __init__(self, cfg, venv=None):
+        self.cfg = cfg
+        self.device = cfg.device
+        self.seed = cfg.get("seed", 42)
+        random.seed(self.seed)
+        np.random.seed(self.seed)
+        torch.manual_seed(self.seed)
+        self.rank, self.world = D.world()
+
+        # env shard of this rank (reference: one process owns all envs, train_agent.py:43-66)
+        self.n_envs_global = cfg.env.n_envs
+        self.env_begin, self.env_end = D.env_shard(self.n_envs_global, self.rank, self.world)
+        self.n_envs = self.env_end - self.env_begin
+        self.n_cond_step, self.obs_dim, self.action_dim = cfg.cond_steps, cfg.obs_dim, cfg.action_dim
+        self.act_steps, self.horizon_steps = cfg.act_steps, cfg.horizon_steps
+        self.max_episode_steps = cfg.env.max_episode_steps
+        self.reset_at_iteration = cfg.env.get("reset_at_iteration", True)
+        if venv is None:
+            from dppo_b200.env.synthetic import SyntheticVecEnv
+
+            venv = SyntheticVecEnv(self.n_envs, self.obs_dim, self.action_dim, self.n_cond_step, self.act_steps,
+                                   self.max_episode_steps, seed=self.seed, env_offset=self.env_begin)
+        self.venv = venv
+        self.best_reward_threshold_for_success = cfg.env.get("best_reward_threshold_for_success", 0)
+
+        self.batch_size = cfg.train.batch_size
+        self.model = instantiate(cfg.model)
+        self.itr = 0
+        self.n_train_itr, self.val_freq = cfg.train.n_train_itr, cfg.train.val_freq
+        self.force_train = cfg.train.get("force_train", False)
+        self.n_steps = cfg.train.n_steps
+        self.max_grad_norm = cfg.train.get("max_grad_norm", None)
+        self.logdir = cfg.logdir
+        self.checkpoint_dir = os.path.join(self.logdir, "checkpoint")
+        self.result_path = os.path.join(self.logdir, "result.pkl")
+        if self.rank == 0:
+            os.makedirs(self.checkpoint_dir, exist_ok=True)
+        self.log_freq = cfg.train.get("log_freq", 1)
+        self.save_model_freq = cfg.train.save_model_freq
+
+        # PPO hyper-parameters (train_ppo_agent.py:18-89)
+        self.logprob_batch_size = cfg.train.get("logprob_batch_size", 10000)
+        self.gamma = cfg.train.gamma
+        self.n_critic_warmup_itr = cfg.train.n_critic_warmup_itr
+        self.actor_optimizer = torch.optim.AdamW(self.model.actor_ft.parameters(), lr=cfg.train.actor_lr,
+                                                 weight_decay=cfg.train.actor_weight_decay)
+        self.critic_optimizer = torch.optim.AdamW(self.model.critic.parameters(), lr=cfg.train.critic_lr,
+                                                  weight_decay=cfg.train.critic_weight_decay)
+        self._sched = {"actor": -1, "critic": -1}
+        self._apply_lr()
+        self.gae_lambda = cfg.train.get("gae_lambda", 0.95)
+        self.target_kl = cfg.train.target_kl
+        self.update_epochs = cfg.train.update_epochs
+        self.ent_coef = cfg.train.get("ent_coef", 0)
+        self.vf_coef = cfg.train.get("vf_coef", 0)
+        self.reward_scale_running = cfg.train.reward_scale_running
+        if self.reward_scale_running:
+            self.running_reward_scaler = RunningRewardScaler(self.n_envs)
+        self.reward_scale_const = cfg.train.get("reward_scale_const", 1)
+        self.use_bc_loss = cfg.train.get("use_bc_loss", False)
+        self.bc_loss_coeff = cfg.train.get("bc_loss_coeff", 0)
+        self.reward_horizon = cfg.get("reward_horizon", self.act_steps)
+        if self.model.learn_eta:
+            raise NotImplementedError("learned eta is outside the hot path (no YAML enables it)")
+
+        # gradients of both networks + 8 diagnostics in ONE flat buffer -> one all-reduce per minibatch
+        self.grads = D.FlatGradBuffer(list(self.model.actor_ft.parameters()) + list(self.model.critic.parameters()))
+        self.timings = {}
+
+    # ------------------------------------------------------------------ schedules
+    def _apply_lr(self):
+        t = self.cfg.train
+        for name, opt, lr, sc in (("actor", self.actor_optimizer, t.actor_lr, t.actor_lr_scheduler),
+                                  ("critic", self.critic_optimizer, t.critic_lr, t.critic_lr_scheduler)):
+            v = cosine_warmup_lr(self._sched[name], sc.first_cycle_steps, lr, sc.min_lr, sc.warmup_steps)
+            for g in opt.param_groups:
+                g["lr"] = v
+
+    # ------------------------------------------------------------------ checkpoints (train_agent.py:125-145)
+    def save_model(self):
+        if self.rank != 0:
+            return
+        path = os.path.join(self.checkpoint_dir, f"state_{self.itr}.pt")
+        torch.save({"itr": self.itr, "model": self.model.state_dict()}, path)
+        log.info("Saved model to %s", path)
+
+    def load(self, itr):
+        data = torch.load(os.path.join(self.checkpoint_dir, f"state_{itr}.pt"), weights_only=True)
+        self.itr = data["itr"]
+        self.model.load_state_dict(data["model"])
+
+    def reset_env_all(self, options_venv=None):
+        obs = self.venv.reset_arg(options_list=options_venv or [{} for _ in range(self.n_envs)])
+        if isinstance(obs, list):
+            obs = {k: np.stack([o[k] for o in obs]) for k in obs[0]}
+        return obs
+
+    # ------------------------------------------------------------------ the pieces of one iteration
+    def rollout(self, prev_obs_venv, eval_mode, firsts_trajs):
+        """n_steps decisions for this rank's envs.  Returns device buffers + host reward / terminated arrays."""
+        dev, n, E = self.device, self.n_steps, self.n_envs
+        ft = self.model.ft_denoising_steps
+        obs_buf = torch.empty((n, E, self.n_cond_step, self.obs_dim), dtype=torch.float32, device=dev)
+        chains_buf = torch.empty((n, E, ft + 1, self.horizon_steps, self.action_dim), dtype=torch.float32, device=dev)
+        reward_trajs, terminated_trajs = np.zeros((n, E)), np.zeros((n, E))
+        pinned_obs = torch.empty((E, self.n_cond_step, self.obs_dim), dtype=torch.float32).pin_memory()
+        pinned_act = torch.empty((E, self.horizon_steps, self.action_dim), dtype=torch.float32).pin_memory()
+        env_steps = 0
+        for step in range(n):
+            pinned_obs.copy_(torch.from_numpy(np.ascontiguousarray(prev_obs_venv["state"], dtype=np.float32)))
+            obs_buf[step].copy_(pinned_obs, non_blocking=True)
+            samples = self.model(cond={"state": obs_buf[step]}, deterministic=eval_mode, return_chain=True,
+                                 env_offset=self.env_begin)
+            chains_buf[step].copy_(samples.chains)
+            pinned_act.copy_(samples.trajectories, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the simulator needs the action chunk on the host
+            action_venv = pinned_act.numpy()[:, : self.act_steps]
+            obs_venv, reward_venv, terminated_venv, truncated_venv, _ = self.venv.step(action_venv)
+            done_venv = terminated_venv | truncated_venv
+            reward_trajs[step], terminated_trajs[step] = reward_venv, terminated_venv
+            firsts_trajs[step + 1] = done_venv
+            prev_obs_venv = obs_venv
+            env_steps += E * self.act_steps if not eval_mode else 0
+        return obs_buf, chains_buf, reward_trajs, terminated_trajs, prev_obs_venv, done_venv, env_steps
+
+    @torch.no_grad()
+    def prologue(self, obs_buf, chains_buf, reward_trajs, terminated_trajs, firsts_trajs, last_obs):
+        """Old log-probs, values, reward scaling and GAE (reference :197-279) on this rank's envs."""
+        n, E = self.n_steps, self.n_envs
+        ft = self.model.ft_denoising_steps
+        obs_k = obs_buf.view(n * E, self.n_cond_step, self.obs_dim)
+        chains_k = chains_buf.view(n * E, ft + 1, self.horizon_steps, self.action_dim)
+        values = torch.empty(n * E, dtype=torch.float32, device=self.device)
+        logprobs = torch.empty((n * E, ft, self.horizon_steps, self.action_dim), dtype=torch.float32, device=self.device)
+        for s in range(0, n * E, self.logprob_batch_size):
+            e = min(n * E, s + self.logprob_batch_size)
+            values[s:e] = self.model.critic({"state": obs_k[s:e]}).view(-1)
+            logprobs[s:e] = self.model.get_logprobs({"state": obs_k[s:e]}, chains_k[s:e]).view(e - s, ft, self.horizon_steps,
+                                                                                             self.action_dim)
+        if self.reward_scale_running:
+            reward_trajs = self.running_reward_scaler(reward=reward_trajs.T, first=firsts_trajs[:-1].T).T
+        next_value = self.model.critic({"state": torch.from_numpy(np.ascontiguousarray(last_obs["state"], dtype=np.float32))
+                                        .to(self.device)}).view(-1)
+        f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)  # noqa: E731
+        adv, ret = E_.gae(f64(reward_trajs), f64(terminated_trajs), values.view(n, E).double(), next_value.double(),
+                          self.gamma, self.gae_lambda, self.reward_scale_const)
+        return values.view(n, E), logprobs.view(n, E, ft, self.horizon_steps, self.action_dim), adv.float(), ret.float()
+
+    def update(self, obs_buf, chains_buf, logprobs, values, adv, ret):
+        """update_epochs x minibatches over the GLOBAL buffers (reference :305-383)."""
+        Eg, n = self.n_envs_global, self.n_steps
+        ft = self.model.ft_denoising_steps
+        # every rank gets the reference's (step, env)-ordered *_k arrays
+        obs_k = D.gather_env_dim(obs_buf, Eg).view(n * Eg, self.n_cond_step, self.obs_dim)
+        chains_k = D.gather_env_dim(chains_buf, Eg).view(n * Eg, ft + 1, self.horizon_steps, self.action_dim)
+        logprobs_k = D.gather_env_dim(logprobs, Eg).view(n * Eg, ft, self.horizon_steps, self.action_dim)
+        values_k = D.gather_env_dim(values, Eg).reshape(-1)
+        adv_k = D.gather_env_dim(adv, Eg).reshape(-1)
+        ret_k = D.gather_env_dim(ret, Eg).reshape(-1)
+        total_steps = n * Eg * ft
+        num_batch = max(1, total_steps // self.batch_size)  # the tail rows of each permutation are skipped, as in the reference
+        clipfracs, stats, flag_break = [], None, False
+        for update_epoch in range(self.update_epochs):
+            inds_k = D.broadcast_permutation(total_steps, self.device)
+            for batch in range(num_batch):
+                inds_b = inds_k[batch * self.batch_size:(batch + 1) * self.batch_size]
+                lo, hi = D.minibatch_slice(inds_b.numel(), self.rank, self.world)
+                self.grads.zero()
+                res = self.model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
+                                               row_count=hi - lo, use_bc_loss=self.use_bc_loss,
+                                               reward_horizon=self.reward_horizon, scalars_out=self.grads.scalars)
+                pg_loss, entropy_loss, v_loss, bc_loss = res[0], res[1], res[2], res[6]
+                loss = pg_loss + entropy_loss * self.ent_coef + v_loss * self.vf_coef + bc_loss * self.bc_loss_coeff
+                loss.backward()
+                self.grads.allreduce()  # gradients + [pg, v, kl, clipfrac, ratio] partial means, one collective
+                s = self.grads.scalars.tolist()  # the one device->host read of the minibatch
+                stats = dict(pg_loss=s[0], v_loss=s[1], approx_kl=s[2], clipfrac=s[3], ratio=s[4], bc_loss=float(bc_loss),
+                             eta=res[7], loss=s[0] + float(entropy_loss) * self.ent_coef + s[1] * self.vf_coef
+                             + float(bc_loss) * self.bc_loss_coeff)
+                clipfracs.append(s[3])
+                if self.itr >= self.n_critic_warmup_itr:
+                    if self.max_grad_norm is not None:
+                        torch.nn.utils.clip_grad_norm_(self.model.actor_ft.parameters(), self.max_grad_norm)
+                    self.actor_optimizer.step()
+                self.critic_optimizer.step()
+                if self.target_kl is not None and s[2] > self.target_kl:
+                    flag_break = True
+                    break
+            if flag_break:
+                break
+        y_pred, y_true = values_k.cpu().numpy(), ret_k.cpu().numpy()
+        var_y = np.var(y_true)
+        stats["explained_var"] = np.nan if var_y == 0 else 1 - np.var(y_true - y_pred) / var_y
+        stats["clipfrac"] = float(np.mean(clipfracs))
+        stats["minibatches"] = len(clipfracs)
+        return stats
+
+    # ------------------------------------------------------------------ main loop (reference :47-483)
+    def run(self):
+        run_results, cnt_train_step = [], 0
+        done_venv = np.zeros((1, self.n_envs))
+        prev_obs_venv = None
+        t_start = time.perf_counter()
+        while self.itr < self.n_train_itr:
+            eval_mode = self.itr % self.val_freq == 0 and not self.force_train
+            self.model.eval() if eval_mode else self.model.train()
+            firsts_trajs = np.zeros((self.n_steps + 1, self.n_envs))
+            # the reference resets when reset_at_iteration, in eval mode, or right after an eval iteration; its
+            # `last_itr_eval` is overwritten before use (:66), so "eval_mode" covers both; a run that never resets
+            # needs an initial reset, which the reference leaves unbound
+            if self.reset_at_iteration or eval_mode or prev_obs_venv is None:
+                prev_obs_venv = self.reset_env_all()
+                firsts_trajs[0] = 1
+            else:
+                firsts_trajs[0] = done_venv
+            t0 = time.perf_counter()
+            obs_buf, chains_buf, reward_trajs, terminated_trajs, prev_obs_venv, done_venv, env_steps = self.rollout(
+                prev_obs_venv, eval_mode, firsts_trajs)
+            torch.cuda.synchronize()
+            t_roll = time.perf_counter() - t0
+            cnt_train_step += env_steps * (self.n_envs_global // max(1, self.n_envs)) if self.world > 1 else env_steps
+
+            # episode statistics: episodes that start and finish inside the iteration (:153-193)
+            ep_rewards = []
+            for e in range(self.n_envs):
+                marks = np.where(firsts_trajs[:, e] == 1)[0]
+                for a, b in zip(marks[:-1], marks[1:]):
+                    if b - a > 1:
+                        ep_rewards.append(reward_trajs[a:b, e])
+            avg_episode_reward = float(np.mean([r.sum() for r in ep_rewards])) if ep_rewards else 0.0
+            avg_best_reward = float(np.mean([r.max() / self.act_steps for r in ep_rewards])) if ep_rewards else 0.0
+            success_rate = float(np.mean([r.max() / self.act_steps >= self.best_reward_threshold_for_success
+                                          for r in ep_rewards])) if ep_rewards else 0.0
+
+            stats, t_pro, t_upd = None, 0.0, 0.0
+            if not eval_mode:
+                t0 = time.perf_counter()
+                values, logprobs, adv, ret = self.prologue(obs_buf, chains_buf, reward_trajs, terminated_trajs, firsts_trajs,
+                                                           prev_obs_venv)
+                torch.cuda.synchronize()
+                t_pro = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                stats = self.update(obs_buf, chains_buf, logprobs, values, adv, ret)
+                torch.cuda.synchronize()
+                t_upd = time.perf_counter() - t0
+
+            if self.itr >= self.n_critic_warmup_itr:
+                self._sched["actor"] += 1
+            self._sched["critic"] += 1
+            self._apply_lr()
+            self.model.step()
+            if self.itr % self.save_model_freq == 0 or self.itr == self.n_train_itr - 1:
+                self.save_model()
+            rec = {"itr": self.itr, "step": cnt_train_step, "time": time.perf_counter() - t_start,
+                   "t_rollout": t_roll, "t_prologue": t_pro, "t_update": t_upd}
+            if eval_mode:
+                rec.update(eval_success_rate=success_rate, eval_episode_reward=avg_episode_reward,
+                           eval_best_reward=avg_best_reward)
+            else:
+                rec.update(train_episode_reward=avg_episode_reward, **stats)
+            run_results.append(rec)
+            if self.rank == 0 and self.itr % self.log_freq == 0:
+                log.info("%s", rec)
+                with open(self.result_path, "wb") as f:
+                    pickle.dump(run_results, f)
+            self.itr += 1
+        return run_results

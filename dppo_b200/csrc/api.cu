@@ -89,7 +89,7 @@ static int build_geometry(dppo_ctx* c) {
   if (g.act != DPPO_ACT_RELU && g.act != DPPO_ACT_MISH) return set_error("activation %d unsupported", g.act), DPPO_ERR_INVALID;
   g.MT = g.H / 128;
   g.KCH = g.H / 64;
-  g.NE = g.H <= 512 ? 64 : 32;
+  if (2 * g.D > g.H) return set_error("Ta*Da = %d needs hidden_dim >= %d", g.D, 2 * g.D), DPPO_ERR_INVALID;
   g.KC0 = ceil_div(g.D + g.Dc, 64);
   if (g.KC0 > g.KCH) return set_error("layer-0 width %d exceeds hidden_dim", g.D + g.Dc), DPPO_ERR_INVALID;
   g.KCc = g.CH ? ceil_div(g.Dc_in, 64) : 0;

@@ -16,6 +16,8 @@
 // posterior-mean / noise-injection / chain-store step after the output layer).
 //
 // Precision: SPLIT3 issues x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (three bf16 MMAs, fp32 accumulate), BF16 issues one.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -111,8 +113,8 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   return s;
 }
 
-static size_t smem_fixed_bytes(const MlpGeom& g) {
-  const size_t xb = size_t(g.NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * g.NE * 128 * g.nsplit;
+static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
+  const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
   return xb + x0b + 16 * kMaxStages + 32 + kEpiWarps * 2 * 32 * 4 + 1024 /* alignment slack */;
 }
 
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint32_t ld_phase = 0;
     float xreg[CPT];
+    const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
 
     long long e_wait = 0;
     const long long e_t0 = clock64();
@@ -377,24 +380,28 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       } else {
         stage_cond_input();
       }
-      // x_T (sampling) or the first stored chain entry (evaluation)
-      if (fl < a.D) {
+      // x_T (sampling) or the first stored chain entry (evaluation).  Flat element mapping: thread `et` owns elements
+      // i = et + j*256 of the tile's NE x D sample block for the whole chain (x stays in registers between steps), so
+      // every global access below is contiguous across the 256 epilogue threads.
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          const int env = env0 + col0 + c;
-          float x = 0.f;
+      for (int j = 0; j < CPT; ++j) {
+        const int i = et + j * kEpiThreads;
+        float x = 0.f;
+        if (i < nxe) {
+          const int e = i / a.D, f = i - e * a.D;
+          const int env = env0 + e;
           if (env < a.E) {
             if (a.eval_mode)
-              x = a.chains_in[(size_t(env) * (a.ft + 1)) * a.D + fl];
+              x = a.chains_in[(size_t(env) * (a.ft + 1)) * a.D + f];
             else if (a.noise)
-              x = a.noise[size_t(env) * a.D + fl];
+              x = a.noise[size_t(env) * a.D + f];
             else
-              x = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + fl, 0u);
-            if (!a.eval_mode && a.chain && a.ft == a.S) a.chain[(size_t(env) * (a.ft + 1)) * a.D + fl] = x;
+              x = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, 0u);
+            if (!a.eval_mode && a.chain && a.ft == a.S) a.chain[(size_t(env) * (a.ft + 1)) * a.D + f] = x;
           }
-          xreg[c] = x;
-          store_operand<NE>(s.x0_hi, s.x0_lo, col0 + c, fl, x, split);
+          store_operand<NE>(s.x0_hi, s.x0_lo, e, f, x, split);
         }
+        xreg[j] = x;
       }
       signal_x();
     }
@@ -449,29 +456,42 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         signal_x();
       }
 
-      // output layer + posterior
+      // output layer + posterior.  The accumulator holds eps as [feature lane][env column]; the warps whose lane
+      // quarter holds valid features move it (+ bias) to a [env][feature] fp32 tile in shared memory (aliasing X, which
+      // the completed output-layer MMAs no longer read), then ALL epilogue threads run the posterior on the flat mapping.
       wait_layer();
       {
-        float v[CPT];
-        tmem_ld(tmem + lane_addr + col_y + col0, v);
-        if (fl < a.D) {
-          const float bo = side[a.off_bout + fl];
-          const bool last = step == a.S - 1;
-          const int d_eval = step - a.first_step;
-          float stdv, f2 = row.f2, f3 = row.f3;
-          if (a.eval_mode) {
-            stdv = fmaxf(row.std_train, a.min_std);
-          } else if (a.deterministic) {
-            f2 = row.f2_det, f3 = row.f3_det;
-            stdv = a.use_ddim ? 0.f : (row.t == 0 ? 0.f : fmaxf(row.std_train, 1e-3f));
-          } else {
-            stdv = fmaxf(row.std_train, a.min_std);
-          }
+        float* s_eps = reinterpret_cast<float*>(s.x_hi);
+        if (q * 32 < a.D) {
+          float v[CPT];
+          tmem_ld(tmem + lane_addr + col_y + col0, v);
+          if (fl < a.D) {
+            const float bo = side[a.off_bout + fl];
 #pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            const int env = env0 + col0 + c;
-            float eps = v[c] + bo;
-            const float x = xreg[c];
+            for (int c = 0; c < CPT; ++c) s_eps[(col0 + c) * a.D + fl] = v[c] + bo;
+          }
+        }
+        named_bar_sync(1, kEpiThreads);
+        const bool last = step == a.S - 1;
+        const int d_eval = step - a.first_step;
+        float stdv, f2 = row.f2, f3 = row.f3;
+        if (a.eval_mode) {
+          stdv = fmaxf(row.std_train, a.min_std);
+        } else if (a.deterministic) {
+          f2 = row.f2_det, f3 = row.f3_det;
+          stdv = a.use_ddim ? 0.f : (row.t == 0 ? 0.f : fmaxf(row.std_train, 1e-3f));
+        } else {
+          stdv = fmaxf(row.std_train, a.min_std);
+        }
+        const float inv_2var = 1.f / (2.f * (stdv * stdv)), log_std = logf(stdv);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int i = et + j * kEpiThreads;
+          if (i < nxe) {
+            const int e = i / a.D, f = i - e * a.D;
+            const int env = env0 + e;
+            float eps = s_eps[i];
+            const float x = xreg[j];
             float x0, mu;
             if (!a.use_ddim) {
               x0 = row.f0 * x - row.f1 * eps;
@@ -489,31 +509,33 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             float xn = 0.f;
             if (env < a.E) {
               if (a.eval_mode) {
-                xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + fl];
+                xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + f];
                 const float diff = xn - mu;
-                const float lp = -(diff * diff) / (2.f * (stdv * stdv)) - logf(stdv) - 0.91893853320467274f;
-                a.logp[(size_t(env) * a.ft + d_eval) * a.D + fl] = lp;
+                a.logp[(size_t(env) * a.ft + d_eval) * a.D + f] = -(diff * diff) * inv_2var - log_std - 0.91893853320467274f;
               } else {
                 float z;
                 if (a.noise)
-                  z = a.noise[(size_t(step + 1) * a.E + env) * a.D + fl];
+                  z = a.noise[(size_t(step + 1) * a.E + env) * a.D + f];
                 else
-                  z = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + fl, uint32_t(step + 1));
+                  z = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, uint32_t(step + 1));
                 z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
                 xn = mu + stdv * z;
                 if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
-                if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + fl] = xn;
-                if (last) a.traj[size_t(env) * a.D + fl] = xn;
+                if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
+                if (last) a.traj[size_t(env) * a.D + f] = xn;
               }
             }
-            xreg[c] = xn;
-            store_operand<NE>(s.x0_hi, s.x0_lo, col0 + c, fl, xn, split);
+            xreg[j] = xn;
+            store_operand<NE>(s.x0_hi, s.x0_lo, e, f, xn, split);
           }
         }
         // the next step switches network and has a cond_mlp: its input must be staged before the hand-off
         if (a.CH && step + 1 < a.S) {
           const int nnet = (a.rows[step + 1].ft && !a.use_base) ? 1 : 0;
-          if (nnet != net) stage_cond_input();
+          if (nnet != net) {
+            named_bar_sync(1, kEpiThreads);  // s_eps aliases X: every thread must be done reading it
+            stage_cond_input();
+          }
         }
       }
       signal_x();
@@ -529,6 +551,23 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
 }
 
 // ============================================================================================== host launch
+// Environments per CTA tile (= N of every MMA).  An MMA of this kernel is bound by the shared-memory read of its
+// 128 x 16 weight operand, so its cost barely depends on N: the fastest launch is the smallest tile that still fits the
+// tiles of the call into ONE wave of CTAs (one CTA per SM).  DPPO_B200_TILE_ENVS overrides (bring-up / tuning).
+static int pick_tile_envs(const dppo_ctx* ctx, int E) {
+  const int cap = ctx->g.H <= 512 ? 64 : 32;  // X operand (NE x H bf16 hi + lo) must leave room for the weight ring
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DPPO_B200_TILE_ENVS");
+    forced = e ? atoi(e) : 0;
+  }
+  if ((forced == 16 || forced == 32 || forced == 64) && forced <= cap) return forced;
+  const int tiles[3] = {16, 32, 64};
+  for (int ne : tiles)
+    if (ne <= cap && (E + ne - 1) / ne <= ctx->sm_count) return ne;
+  return cap;
+}
+
 template <int NE, int ACT, bool LN>
 static int launch(const ChainArgs& a, size_t smem_bytes, cudaStream_t st) {
   auto kfn = chain_mlp_kernel<NE, ACT, LN>;
@@ -567,7 +606,8 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
   a.prof = ctx->d_prof;
 
-  const size_t fixed = smem_fixed_bytes(g);
+  const int NE = pick_tile_envs(ctx, E);
+  const size_t fixed = smem_fixed_bytes(g, NE);
   const size_t budget = 232448;
   if (fixed + 2 * kTile > budget) return set_error("chain kernel: geometry needs %zu B of shared memory", fixed), DPPO_ERR_INVALID;
   int nstage = int((budget - fixed) / kTile);
@@ -577,8 +617,11 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
 
 #define DPPO_LAUNCH(NE_, ACT_)                                             \
   (g.ln ? launch<NE_, ACT_, true>(a, smem_bytes, st) : launch<NE_, ACT_, false>(a, smem_bytes, st))
-  if (g.NE == 64) return g.act == DPPO_ACT_RELU ? DPPO_LAUNCH(64, DPPO_ACT_RELU) : DPPO_LAUNCH(64, DPPO_ACT_MISH);
-  return g.act == DPPO_ACT_RELU ? DPPO_LAUNCH(32, DPPO_ACT_RELU) : DPPO_LAUNCH(32, DPPO_ACT_MISH);
+#define DPPO_LAUNCH_ACT(NE_) (g.act == DPPO_ACT_RELU ? DPPO_LAUNCH(NE_, DPPO_ACT_RELU) : DPPO_LAUNCH(NE_, DPPO_ACT_MISH))
+  if (NE == 64) return DPPO_LAUNCH_ACT(64);
+  if (NE == 32) return DPPO_LAUNCH_ACT(32);
+  return DPPO_LAUNCH_ACT(16);
+#undef DPPO_LAUNCH_ACT
 #undef DPPO_LAUNCH
 }
 

@@ -35,7 +35,6 @@ struct StepRow {
 // Geometry of the packed MLP (same for actor and actor_ft).
 struct MlpGeom {
   int D, Dc_in, Dc, td, H, nb, act, ln, CH, CO;  // Dc_in = cond_dim, Dc = features entering layer 0 (cond_dim or cond_out)
-  int NE;        // envs per CTA tile
   int MT, KCH;   // H/128, H/64
   int KC0;       // 64-wide K chunks of layer 0 ([x | cond])
   int KCc, MTc;  // cond_mlp layer 0: K chunks of cond_dim, M tiles of CH

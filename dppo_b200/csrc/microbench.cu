@@ -1,0 +1,173 @@
+// Micro-benchmarks behind two bring-up entry points (not on the product path, not in the public header):
+//   dppo_debug_mma_rate     cycles per tcgen05.mma (M=128, K=16, bf16, both operands in shared memory) as a function of
+//                           N, issued the way the chain kernel issues them (uniform warp loop, one elected lane)
+//   dppo_debug_stream_rate  bytes/cycle/SM a grid of CTAs gets when every CTA streams the SAME region of global memory
+//                           (L2 resident) into a shared-memory ring with 16 KiB bulk copies - optionally as thread-block
+//                           clusters in which each CTA fetches 1/C of every tile and multicasts it to its peers
+// Both tell the chain kernel which resource bounds it (DESIGN.md "Chain kernel roofline").
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace dppo {
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int n_b, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (192 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    // A: 8 tiles of 128 x 64 (16 KiB each) at [0, 128 KiB); B: n_b operands of N x 64 at 128 KiB (n_b * N <= 512 rows)
+    const uint32_t a0 = umma_desc_lo(smem_u32(smem)), b0 = umma_desc_lo(smem_u32(smem + 128 * 1024));
+    const uint32_t n_acc = 512 / N >= 4 ? 4 : 512 / N;
+    uint32_t at = 0, acc = 0, bt = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; i += 4) {
+      if (elect_one()) {
+        const uint32_t d = tmem + acc * N;
+        const uint32_t aa = a0 + at * (16384 / 16), bb = b0 + bt * (uint32_t(N) * 128 / 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lo(d, aa + 2 * k, bb + 2 * k, idesc, true);
+      }
+      __syncwarp();
+      if (++at == 8) at = 0;
+      if (++acc == n_acc) acc = 0;
+      if (++bt == uint32_t(n_b)) bt = 0;
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------- streaming
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> shared memory of every CTA in `mask` (same CTA-relative offsets), completing on each one's barrier
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at the same CTA-relative offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
+constexpr int kSbStages = 8;
+constexpr uint32_t kSbTile = 16384;
+
+__global__ void __launch_bounds__(64, 1) stream_rate_kernel(const uint8_t* __restrict__ region, int region_tiles,
+                                                            int n_tiles, int csz, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[kSbStages], empty[kSbStages];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = csz > 1 ? cluster_ctarank() : 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSbStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], csz);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (csz > 1) cluster_sync_all();
+  const long long t0 = clock64();
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    const uint32_t slice = kSbTile / csz;
+    for (int i = 0; i < n_tiles; ++i) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[stage], kSbTile);
+        const uint8_t* src = region + size_t(i % region_tiles) * kSbTile;
+        if (csz == 1)
+          bulk_g2s(ring + size_t(stage) * kSbTile, src, kSbTile, &full[stage]);
+        else
+          bulk_g2s_multicast(ring + size_t(stage) * kSbTile + rank * slice, src + rank * slice, slice, &full[stage],
+                             uint16_t((1u << csz) - 1));
+      }
+      __syncwarp();
+      if (++stage == kSbStages) stage = 0, phase ^= 1;
+    }
+  } else {
+    uint32_t stage = 0, phase = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+      mbar_wait(&full[stage], phase);
+      if (elect_one()) {
+        if (csz == 1) {
+          mbar_arrive(&empty[stage]);
+        } else {
+          for (int r = 0; r < csz; ++r) mbar_arrive_remote(&empty[stage], uint32_t(r));
+        }
+      }
+      __syncwarp();
+      if (++stage == kSbStages) stage = 0, phase ^= 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+  if (csz > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
+}
+
+}  // namespace dppo
+
+extern "C" int dppo_debug_mma_rate(int N, int n_mma, int n_b, unsigned long long* out, void* stream) {
+  using namespace dppo;
+  if (N < 16 || N > 256 || N % 16 || n_b < 1 || n_b * N > 512) return -1;
+  const int smem = 193 * 1024 + 1024;
+  if (cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
+  mma_rate_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, n_b, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int dppo_debug_stream_rate(const void* region, int region_tiles, int n_tiles, int grid, int cluster,
+                                      unsigned long long* out, void* stream) {
+  using namespace dppo;
+  if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return -1;
+  if (grid % cluster) return -1;
+  const int smem = kSbStages * kSbTile + 1024;
+  if (cudaFuncSetAttribute(stream_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(64), cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, stream_rate_kernel, static_cast<const uint8_t*>(region), region_tiles, n_tiles,
+                                     cluster, out);
+  return e == cudaSuccess ? 0 : -3;
+}

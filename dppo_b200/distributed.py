@@ -1,0 +1,104 @@
+"""
+Data-parallel plumbing of the DPPO hot path: one process per GPU, torch.distributed (NCCL on the B200 box, gloo in the
+CPU tests).  The reference is single-process; this module is the only distributed component and it is
+built so that W ranks reproduce the single-process arithmetic:
+
+  rollout   envs are independent -> rank r owns the contiguous env range `env_shard(E, r, W)`; no collective while
+            sampling.  Uneven shards are allowed (E = 50 over 4 ranks -> 13, 13, 12, 12).
+  gather    once per iteration the rank-local rollout buffers (n_steps, E_r, ...) are all-gathered into the reference's
+            (n_steps, E, ...) arrays (`gather_env_dim`), so the flat row index (step * E + env) * ft + d of
+            train_ppo_diffusion_agent.py:316-320 is unchanged.
+  update    rank 0 draws torch.randperm exactly like the reference (:311) and broadcasts it; rank r evaluates the
+            contiguous slice `minibatch_slice(Bmb, r, W)` of every minibatch, divides by the GLOBAL row count, and
+            `allreduce_flat` sums gradients and loss scalars in one collective.  The union of the slices is the
+            reference minibatch bit-exactly; a remainder goes to the last rank.
+"""
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def env_shard(n_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[begin, end) of the envs rank `rank` owns: the first n_envs % W ranks get one extra env."""
+    base, extra = divmod(n_envs, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def minibatch_slice(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[begin, end) of the rows of one minibatch rank `rank` evaluates; the remainder goes to the last rank."""
+    per = n_rows // world_size
+    begin = rank * per
+    return begin, (n_rows if rank == world_size - 1 else begin + per)
+
+
+def gather_env_dim(local: torch.Tensor, n_envs: int, env_dim: int = 1) -> torch.Tensor:
+    """
+    All-gather rank-local buffers along their env dimension into the full array every rank then holds.
+    `local` has size env_shard(...) along `env_dim`; shards are padded to the largest shard for the collective only.
+    """
+    rank, W = world()
+    if W == 1:
+        return local
+    sizes = [env_shard(n_envs, r, W) for r in range(W)]
+    widest = max(e - b for b, e in sizes)
+    moved = local.movedim(env_dim, 0).contiguous()
+    if moved.shape[0] < widest:
+        pad = torch.zeros((widest - moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+        moved = torch.cat([moved, pad], 0)
+    parts: List[torch.Tensor] = [torch.empty_like(moved) for _ in range(W)]
+    dist.all_gather(parts, moved)
+    full = torch.cat([p[: e - b] for p, (b, e) in zip(parts, sizes)], 0)
+    return full.movedim(0, env_dim).contiguous()
+
+
+def broadcast_permutation(n: int, device, generator=None) -> torch.Tensor:
+    """torch.randperm(n) drawn on rank 0 (the reference's call, train_ppo_diffusion_agent.py:311) and broadcast."""
+    rank, W = world()
+    if rank == 0:
+        perm = torch.randperm(n, device=device, generator=generator)
+    else:
+        perm = torch.empty(n, dtype=torch.int64, device=device)
+    if W > 1:
+        dist.broadcast(perm, 0)
+    return perm
+
+
+class FlatGradBuffer:
+    """
+    One flat fp32 buffer aliasing the .grad of every trainable parameter, followed by `n_scalars` slots for loss
+    diagnostics, so that one all-reduce per minibatch carries gradients and scalars.
+    Backward writes straight into the views - there is no pack / unpack copy.
+    """
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], n_scalars: int = 8):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n + n_scalars, dtype=torch.float32, device=dev)
+        self.n_grad, self.n_scalars = n, n_scalars
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    @property
+    def scalars(self) -> torch.Tensor:
+        return self.flat[self.n_grad:]
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self):
+        _, W = world()
+        if W > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)

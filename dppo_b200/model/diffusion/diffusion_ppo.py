@@ -71,11 +71,15 @@ class PPODiffusion(VPGDiffusion):
         bc = self.get_logprobs(obs, samples.chains, get_ent=False, use_base_policy=False)
         return -bc.clamp(min=-5, max=2).mean(dim=(-1, -2)).view(-1).mean()
 
-    def _finish(self, eps, vpred, grad_eps, grad_v, scalars, obs, use_bc_loss):
+    def _finish(self, eps, vpred, grad_eps, grad_v, scalars, obs, use_bc_loss, scalars_out=None):
         pg_loss, v_loss = _FusedLoss.apply(eps, vpred, grad_eps, grad_v, scalars)
         bc_loss = self._bc_loss(obs) if use_bc_loss else 0
         eta_mean = float(self.eta.value()) if self.use_ddim and hasattr(self, "eta") else 1.0
         entropy_loss = torch.full((), -eta_mean, device=eps.device)
+        if scalars_out is not None:
+            # multi-rank caller: the partial means stay on the device and ride the gradient all-reduce
+            scalars_out.copy_(scalars)
+            return pg_loss, entropy_loss, v_loss, scalars[3], scalars[2], scalars[4], bc_loss, eta_mean
         host = scalars.tolist()  # the one device->host read of the call (the reference does four .item()s)
         return pg_loss, entropy_loss, v_loss, host[3], host[2], host[4], bc_loss, eta_mean
 
@@ -94,12 +98,14 @@ class PPODiffusion(VPGDiffusion):
 
     # ------------------------------------------------------------------ fused-gather variant (B200 agent)
     def loss_gathered(self, obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k, inds_all, row_begin=0,
-                      row_count=None, use_bc_loss=False, reward_horizon=4):
+                      row_count=None, use_bc_loss=False, reward_horizon=4, scalars_out=None):
         """
         Rollout buffers stay in place: obs_k (N, To, Do), chains_k (N, ft+1, Ta, Da), logprobs_k (N, ft, Ta, Da),
         returns_k / values_k / advantages_k (N,), inds_all = the minibatch's flat indices into (N, ft)
         (reference train_ppo_diffusion_agent.py:316-327).  This rank evaluates rows [row_begin, row_begin+row_count)
         and divides by len(inds_all), so summing ranks' losses / gradients gives the single-process result.
+        `scalars_out` (8 floats, device): the kernel's partial means are copied there and NOT read back to the host
+        (the caller all-reduces them together with the gradients); elements 3-5 of the return are then device scalars.
         """
         eng = self.engine()
         ft = self.ft_denoising_steps
@@ -113,4 +119,4 @@ class PPODiffusion(VPGDiffusion):
         hp = eng.make_hp(self, reward_horizon, lo, hi)
         grad_eps, grad_v, scalars = eng.loss_gathered(hp, chains_k, logprobs_k, returns_k, values_k, advantages_k,
                                                       inds_all, row_begin, eps.detach(), vpred.detach())
-        return self._finish(eps, vpred, grad_eps, grad_v, scalars, obs, use_bc_loss)
+        return self._finish(eps, vpred, grad_eps, grad_v, scalars, obs, use_bc_loss, scalars_out)

@@ -122,11 +122,12 @@ class VPGDiffusion(DiffusionModel):
 
     # ------------------------------------------------------------------ sampling (reference :227-315)
     @torch.no_grad()
-    def forward(self, cond, deterministic=False, return_chain=True, use_base_policy=False, noise=None):
+    def forward(self, cond, deterministic=False, return_chain=True, use_base_policy=False, noise=None, env_offset=0):
         """
         cond["state"]: (B, To, Do).  Returns Sample(trajectories (B, Ta, Da), chains (B, ft+1, Ta, Da)).
         `noise` (S+1, B, Ta, Da) injects the draws the reference takes from torch.randn / randn_like (parity tests);
-        without it the kernel draws Philox normals seeded from torch's generator.
+        without it the kernel draws Philox normals seeded from torch's generator.  `env_offset` = global index of
+        row 0 (env-sharded ranks then draw what one process would draw for the same envs).
         """
         eng = self.engine()
         state = cond["state"]
@@ -137,7 +138,7 @@ class VPGDiffusion(DiffusionModel):
             self._rng_offset += 1
             offset = self._rng_offset
         traj, chain = eng.sample(
-            state.to(self.device), noise=noise, seed=seed, offset=offset, deterministic=deterministic,
+            state.to(self.device), noise=noise, seed=seed, offset=offset, env_offset=env_offset, deterministic=deterministic,
             use_base_policy=use_base_policy, min_sampling_std=float(self.get_min_sampling_denoising_std()),
             return_chain=return_chain,
         )
