@@ -220,3 +220,11 @@ extern "C" int dppo_debug_set_prof(dppo_ctx* ctx, unsigned long long* buf) {
   ctx->d_prof = buf;
   return DPPO_OK;
 }
+
+// bring-up / tuning hook (not in the public header): force the chain kernel's tile size (16/32/64 envs) and cluster
+// size (1/2/4/8 CTAs sharing a tile); 0 = let the cost model choose
+extern "C" int dppo_debug_set_shape(dppo_ctx* ctx, int tile_envs, int cluster) {
+  if (!ctx) return DPPO_ERR_INVALID;
+  ctx->force_ne = tile_envs, ctx->force_c = cluster;
+  return DPPO_OK;
+}

@@ -11,6 +11,14 @@
 // Accumulators live in TMEM: region h (residual stream, MT*NE columns) and region y (block hidden / output layer).
 // The residual add is free: the second Linear of a block accumulates straight onto h in TMEM.
 //
+// Feature-split clusters: the kernel is bound by how fast ONE SM can pull weight tiles out of L2 (~35 B/cycle/SM measured,
+// profiles/r1a_microbench.txt), and a CTA that owns all features of its environments must pull the whole network every
+// step.  A cluster of C CTAs therefore shares one tile of NE environments: CTA r computes the M-tiles
+// [r*MT/C, (r+1)*MT/C) of every hidden layer (streaming only 1/C of the weights), writes its activations into its own
+// copy of X and pushes that column block into the peers' copies with one bulk shared::cta -> shared::cluster copy per
+// peer and operand half (the copy completes on the peer's x_full mbarrier).  The tiny output layer, the posterior step
+// and the layer-0 operand are computed redundantly by every CTA, so nothing else crosses CTAs.
+//
 // Warp roles (320 threads): warp 0 = weight-tile producer, warp 1 = MMA issuer (+ TMEM allocator),
 // warps 2..9 = epilogue (TMEM -> registers -> bias / LayerNorm / activation -> bf16 split -> shared memory, and the
 // posterior-mean / noise-injection / chain-store step after the output layer).
@@ -32,6 +40,7 @@ constexpr int kMaxStages = 12;
 struct ChainArgs {
   // geometry
   int D, Dc_in, Dc, H, nb, act, ln, CH, CO, MT, KCH, KC0, KCc, MTc, nsplit, nstage;
+  int C;  // CTAs per cluster (feature split), divides MT
   uint32_t off_tb, off_blk, blk_stride, off_bout, off_bc0, off_bc1;
   const uint8_t* tiles[2];
   const float* side[2];
@@ -89,7 +98,7 @@ __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, int row,
 
 struct Smem {
   uint8_t *x_hi, *x_lo, *x0_hi, *x0_lo, *ring;
-  uint64_t *full, *empty, *layer_done, *x_ready;
+  uint64_t *full, *empty, *layer_done, *x_full, *can_send;
   uint32_t* tmem_slot;
   float* ln_part;  // [kEpiWarps][2][32]
 };
@@ -107,7 +116,8 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
-  s.x_ready = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.can_send = reinterpret_cast<uint64_t*>(p), p += 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
   s.ln_part = reinterpret_cast<float*>(p);
   return s;
@@ -115,7 +125,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
 
 static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
   const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
-  return xb + x0b + 16 * kMaxStages + 32 + kEpiWarps * 2 * 32 * 4 + 1024 /* alignment slack */;
+  return xb + x0b + 16 * kMaxStages + 48 + kEpiWarps * 2 * 32 * 4 + 1024 /* alignment slack */;
 }
 
 // ============================================================================================== the kernel
@@ -127,7 +137,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
   const Smem s = carve<NE>(smem, a);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = a.nsplit == 2;
-  const int env0 = blockIdx.x * NE;
+  const int C = a.C;
+  const uint32_t rank = C > 1 ? cluster_ctarank() : 0u;
+  const int env0 = (blockIdx.x / C) * NE;
+  const int MTo = a.MT / C;          // M-tiles of every hidden layer this CTA computes
+  const int mt0 = int(rank) * MTo;   // first one
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.nstage; ++i) {
@@ -135,15 +149,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       mbar_init(&s.empty[i], 1);
     }
     mbar_init(s.layer_done, 1);
-    mbar_init(s.x_ready, kEpiThreads);
+    mbar_init(s.x_full, 1);
+    mbar_init(s.can_send, C > 1 ? C - 1 : 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (C > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   const uint32_t tmem = *s.tmem_slot;
-  const uint32_t col_h = 0, col_y = uint32_t(a.MT) * NE;
+  const uint32_t col_h = 0, col_y = uint32_t(MTo) * NE;
 
   if (warp == 0) {
     // ======================================================================================= weight-tile producer
@@ -152,18 +168,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     int cur_net = -1;
     long long p_wait = 0;
     const long long p_t0 = clock64();
-    for (int step = a.first_step; step < a.S; ++step) {
-      const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
-      for (int part = 0; part < 2; ++part) {
-        const uint8_t* src;
-        uint32_t n;
-        if (part == 0) {
-          if (!(a.CH && net != cur_net)) continue;
-          src = a.tiles[net], n = a.n_cond_tiles;
-        } else {
-          src = a.tiles[net] + a.off_step_tiles, n = a.n_step_tiles;
-        }
-        for (uint32_t i = 0; i < n; ++i) {
+    // tiles of M-tiles [m_begin, m_end) of one Linear whose tile group starts at `base` (layout: m-tile major, k-chunk minor,
+    // hi tile then lo tile)
+    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl) {
+      for (int mt = m_begin; mt < m_end; ++mt) {
+        const uint8_t* src = base + size_t(mt) * KCl * a.nsplit * kTile;
+        const int n = KCl * a.nsplit;
+        for (int i = 0; i < n; ++i) {
           const long long tw = clock64();
           mbar_wait(&s.empty[stage], phase ^ 1);
           p_wait += clock64() - tw;
@@ -175,7 +186,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
         }
       }
+    };
+    const size_t lin0 = size_t(a.MT) * a.KC0 * a.nsplit * kTile, linh = size_t(a.MT) * a.KCH * a.nsplit * kTile;
+    for (int step = a.first_step; step < a.S; ++step) {
+      const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
+      if (a.CH && net != cur_net) {
+        stream(a.tiles[net], 0, a.MTc, a.KCc);
+        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64);
+      }
       cur_net = net;
+      const uint8_t* base = a.tiles[net] + a.off_step_tiles;
+      stream(base, mt0, mt0 + MTo, a.KC0);
+      base += lin0;
+      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH);
+      stream(base, 0, 1, a.KCH);
     }
     if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = p_wait, a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0;
   } else if (warp == 1) {
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
     auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc) {
       long long tw = clock64();
-      mbar_wait(s.x_ready, xr_phase);
+      mbar_wait(s.x_full, xr_phase);
       m_wait_x += clock64() - tw;
       xr_phase ^= 1;
       tc_fence_after();
@@ -246,10 +270,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false);
       }
       cur_net = net;
-      run_layer(s.x0_hi, s.x0_lo, a.MT, a.KC0, col_h, false);
+      run_layer(s.x0_hi, s.x0_lo, MTo, a.KC0, col_h, false);
       for (int b = 0; b < a.nb; ++b) {
-        run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_y, false);
-        run_layer(s.x_hi, s.x_lo, a.MT, a.KCH, col_h, true);
+        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_y, false);
+        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_h, true);
       }
       run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false);
     }
@@ -269,20 +293,50 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     float xreg[CPT];
     const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
 
-    long long e_wait = 0;
+    long long e_wait = 0, e_hand = 0;
     const long long e_t0 = clock64();
-    auto wait_layer = [&]() {
+    uint32_t cs_phase = 0;
+    // `handshake`: this epilogue overwrites parts of X (its column block, or the s_eps alias), so (a) the peers must have
+    // consumed the block pushed earlier and (b) they must be done reading their copy before a new block is pushed
+    auto wait_layer = [&](bool exchange) {
       const long long tw = clock64();
       mbar_wait(s.layer_done, ld_phase);
       e_wait += clock64() - tw;
       ld_phase ^= 1;
       tc_fence_after();
+      if (exchange && C > 1) {
+        // this CTA's MMAs no longer read its copy of X: the peers may overwrite their column blocks in it ...
+        if (et == 0)
+          for (uint32_t p = 0; p < uint32_t(C); ++p)
+            if (p != rank) mbar_arrive_remote(s.can_send, p);
+        // ... and once every peer says the same, (a) the block this CTA pushed after the previous layer has been
+        // consumed, so its source may be overwritten, and (b) the new block may be pushed into the peers' copies
+        const long long th = clock64();
+        mbar_wait_cluster(s.can_send, cs_phase);
+        e_hand += clock64() - th;
+        cs_phase ^= 1;
+      }
     };
-    auto signal_x = [&]() {
+    // hand the operand written by this epilogue over to the MMA warp (and, for an exchange layer, to the peers)
+    const uint32_t blk_chunks = 2u * uint32_t(MTo), blk_bytes = blk_chunks * NE * 128u;  // this CTA's column block of X
+    const uint32_t blk_off = uint32_t(mt0) * 2u * NE * 128u;
+    auto signal_x = [&](bool exchange) {
       tmem_wait_st();
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(s.x_ready);
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+        if (exchange && C > 1) {
+          mbar_arrive_expect_tx(s.x_full, uint32_t(C - 1) * blk_bytes * uint32_t(a.nsplit));
+          for (uint32_t p = 0; p < uint32_t(C); ++p) {
+            if (p == rank) continue;
+            bulk_s2peer(s.x_hi + blk_off, s.x_hi + blk_off, blk_bytes, s.x_full, p);
+            if (split) bulk_s2peer(s.x_lo + blk_off, s.x_lo + blk_off, blk_bytes, s.x_full, p);
+          }
+        } else {
+          mbar_arrive(s.x_full);
+        }
+      }
     };
     // raw observation -> X (input of the cond_mlp), zero padded to the 64-wide chunks it occupies
     auto stage_cond_input = [&]() {
@@ -294,8 +348,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         store_operand<NE>(s.x_hi, s.x_lo, e, k, v, split);
       }
     };
-    // generic hidden-layer epilogue: v = acc + bias; [store back]; [LayerNorm]; activation; -> X
-    auto epi_hidden = [&](uint32_t region, int MTl, const float* bias, bool store_back, bool identity,
+    // generic hidden-layer epilogue: v = acc + bias_a (+ bias_b); [LayerNorm]; activation; -> X
+    // `mt_first`: global index of the layer's first M-tile held in `region` (feature = (mt_first + mt) * 128 + lane).
+    // The accumulator is [feature lane][env column]; X wants [env row][feature] with 2-byte elements.  Neighbouring
+    // lanes swap one value per column pair (even lane keeps column c, odd lane column c + 1), so that every thread owns
+    // TWO consecutive features of one env row: one packed bf16x2 convert and one 4-byte store per operand half.
+    const uint32_t odd = lane & 1;
+    auto epi_hidden = [&](uint32_t region, int mt_first, int MTl, const float* bias_a, const float* bias_b, bool identity,
                           const float* ln_g, const float* ln_b) {
       float mean[LN ? CPT : 1], rstd[LN ? CPT : 1];
       if (LN && ln_g != nullptr) {
@@ -305,7 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         for (int mt = 0; mt < MTl; ++mt) {
           float v[CPT];
           tmem_ld(tmem + lane_addr + region + uint32_t(mt) * NE + col0, v);
-          const float b = bias[mt * 128 + fl];
+          const int f = (mt_first + mt) * 128 + fl;
+          const float b = bias_a[f] + (bias_b ? bias_b[f] : 0.f);
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
             const float x = v[c] + b;
@@ -342,21 +402,30 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       }
       for (int mt = 0; mt < MTl; ++mt) {
         float v[CPT];
-        const uint32_t taddr = tmem + lane_addr + region + uint32_t(mt) * NE + col0;
-        tmem_ld(taddr, v);
-        const int f = mt * 128 + fl;
-        const float b = bias[f];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) v[c] += b;
-        if (store_back) tmem_st(taddr, v);
+        tmem_ld(tmem + lane_addr + region + uint32_t(mt) * NE + col0, v);
+        const int f = (mt_first + mt) * 128 + fl;
+        const float b = bias_a[f] + (bias_b ? bias_b[f] : 0.f);
         float g = 1.f, be = 0.f;
         if (LN && ln_g != nullptr) g = ln_g[f], be = ln_b[f];
+        const uint32_t kp = uint32_t(f) & ~1u;  // first feature of the pair this thread stores
+        const uint32_t j16 = (kp & 63u) >> 3;
+        const uint32_t base = (kp >> 6) * (NE * 128u) + ((kp & 7u) << 1) + (uint32_t(col0) + odd) * 128u;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          float x = v[c];
-          if (LN && ln_g != nullptr) x = (x - mean[LN ? c : 0]) * rstd[LN ? c : 0] * g + be;
-          if (!identity) x = activate<ACT>(x);
-          store_operand<NE>(s.x_hi, s.x_lo, col0 + c, f, x, split);
+        for (int c = 0; c < CPT; c += 2) {
+          float x0 = v[c] + b, x1 = v[c + 1] + b;
+          if (LN && ln_g != nullptr) {
+            x0 = (x0 - mean[LN ? c : 0]) * rstd[LN ? c : 0] * g + be;
+            x1 = (x1 - mean[LN ? c + 1 : 0]) * rstd[LN ? c + 1 : 0] * g + be;
+          }
+          if (!identity) x0 = activate<ACT>(x0), x1 = activate<ACT>(x1);
+          const float recv = __shfl_xor_sync(0xffffffffu, odd ? x0 : x1, 1);
+          const float fa = odd ? recv : x0, fb = odd ? x1 : recv;  // features kp, kp + 1 of env row col0 + c + odd
+          const uint32_t off = base + uint32_t(c) * 128u + ((j16 ^ ((uint32_t(c) + odd) & 7u)) << 4);
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(fa, fb);
+          *reinterpret_cast<__nv_bfloat162*>(s.x_hi + off) = h2;
+          if (split)
+            *reinterpret_cast<__nv_bfloat162*>(s.x_lo + off) =
+                __floats2bfloat162_rn(fa - __low2float(h2), fb - __high2float(h2));
         }
       }
     };
@@ -382,8 +451,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       }
       // x_T (sampling) or the first stored chain entry (evaluation).  Flat element mapping: thread `et` owns elements
       // i = et + j*256 of the tile's NE x D sample block for the whole chain (x stays in registers between steps), so
-      // every global access below is contiguous across the 256 epilogue threads.
-#pragma unroll
+      // every global access below is contiguous across the 256 epilogue threads.  The loops over j are deliberately NOT
+      // unrolled (xreg sits in L1-resident local memory): a handful of elements per thread, but a large body.
+#pragma unroll 1
       for (int j = 0; j < CPT; ++j) {
         const int i = et + j * kEpiThreads;
         float x = 0.f;
@@ -397,13 +467,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
               x = a.noise[size_t(env) * a.D + f];
             else
               x = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, 0u);
-            if (!a.eval_mode && a.chain && a.ft == a.S) a.chain[(size_t(env) * (a.ft + 1)) * a.D + f] = x;
+            if (!a.eval_mode && a.chain && a.ft == a.S && rank == 0) a.chain[(size_t(env) * (a.ft + 1)) * a.D + f] = x;
           }
           store_operand<NE>(s.x0_hi, s.x0_lo, e, f, x, split);
         }
         xreg[j] = x;
       }
-      signal_x();
+      signal_x(false);
     }
 
     // ------------------------------------------------------------------------------------ step loop
@@ -412,13 +482,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       const StepRow row = a.rows[step];
       const int net = (row.ft && !a.use_base) ? 1 : 0;
       const float* side = a.side[net];
-      if (a.CH && net != cur_net) {
-        // cond_mlp: Linear -> act -> Linear, output becomes the conditioning columns of the layer-0 operand
-        wait_layer();
-        epi_hidden(col_y, a.MTc, side + a.off_bc0, false, false, nullptr, nullptr);
-        signal_x();
-        wait_layer();
-        {
+      // Hidden layers through ONE instance of the epilogue code (instruction-cache footprint):
+      //   L = -2  cond_mlp hidden   (only when the network changes; computed redundantly by every CTA of a cluster)
+      //   L = -1  cond_mlp output   -> conditioning columns of the layer-0 operand
+      //   L =  0  layer 0           h  = W0 [x | cond] + TB[t]             (TB folds bias + time embedding)
+      //   L odd   l1 of block b     y  = W1 act(norm1(h)) + b1
+      //   L even  l2 of block b     h += W2 act(norm2(y)) + b2             (h's biases are never stored back into TMEM:
+      //                                                                      its epilogue adds TB[t] + prefix sum of b2)
+      const float* tb = side + a.off_tb + size_t(row.t) * a.H;
+      const int n_hidden = 1 + 2 * a.nb;
+      for (int L = (a.CH && net != cur_net) ? -2 : 0; L < n_hidden; ++L) {
+        if (L == -1) {
+          wait_layer(false);
           float v[CPT];
           tmem_ld(tmem + lane_addr + col_y + col0, v);
           if (fl < a.CO) {
@@ -426,40 +501,41 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
 #pragma unroll
             for (int c = 0; c < CPT; ++c) store_operand<NE>(s.x0_hi, s.x0_lo, col0 + c, a.D + fl, v[c] + b, split);
           }
+          signal_x(false);
+          continue;
         }
-        signal_x();
+        const int b = L > 0 ? (L - 1) >> 1 : 0;
+        const float* blk = side + a.off_blk + size_t(b) * a.blk_stride;
+        uint32_t region = col_h;
+        int mt_first = mt0, MTl = MTo;
+        const float *ba = tb, *bb = nullptr, *lg = nullptr, *lb = nullptr;
+        bool identity = false;
+        if (L == -2) {
+          region = col_y, mt_first = 0, MTl = a.MTc, ba = side + a.off_bc0;
+        } else if (L == 0) {
+          if (a.ln) lg = blk + 2 * a.H, lb = blk + 3 * a.H;
+        } else if (L & 1) {
+          region = col_y, ba = blk;
+          if (a.ln) lg = blk + 4 * a.H, lb = blk + 5 * a.H;
+        } else {
+          ba = blk + a.H, bb = tb;  // slot 1 of a block holds the PREFIX SUM of the l2 biases (pack.cu)
+          if (b + 1 < a.nb) {
+            if (a.ln) lg = blk + a.blk_stride + 2 * a.H, lb = blk + a.blk_stride + 3 * a.H;
+          } else {
+            identity = true;  // no activation between the last block and the output layer
+          }
+        }
+        wait_layer(L >= 0);
+        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb);
+        signal_x(L >= 0);
       }
       cur_net = net;
-
-      // layer 0: h = W0 [x | cond] + TB[t]   (TB folds bias + time embedding)
-      wait_layer();
-      {
-        const float* blk0 = side + a.off_blk;
-        epi_hidden(col_h, a.MT, side + a.off_tb + size_t(row.t) * a.H, true, false, a.ln ? blk0 + 2 * a.H : nullptr,
-                   a.ln ? blk0 + 3 * a.H : nullptr);
-      }
-      signal_x();
-      for (int b = 0; b < a.nb; ++b) {
-        const float* blk = side + a.off_blk + size_t(b) * a.blk_stride;
-        // l1: y = W1 act(norm1(h)) + b1
-        wait_layer();
-        epi_hidden(col_y, a.MT, blk, false, false, a.ln ? blk + 4 * a.H : nullptr, a.ln ? blk + 5 * a.H : nullptr);
-        signal_x();
-        // l2: h += W2 act(norm2(y)) + b2
-        wait_layer();
-        if (b + 1 < a.nb) {
-          const float* nxt = blk + a.blk_stride;
-          epi_hidden(col_h, a.MT, blk + a.H, true, false, a.ln ? nxt + 2 * a.H : nullptr, a.ln ? nxt + 3 * a.H : nullptr);
-        } else {
-          epi_hidden(col_h, a.MT, blk + a.H, false, true, nullptr, nullptr);
-        }
-        signal_x();
-      }
 
       // output layer + posterior.  The accumulator holds eps as [feature lane][env column]; the warps whose lane
       // quarter holds valid features move it (+ bias) to a [env][feature] fp32 tile in shared memory (aliasing X, which
       // the completed output-layer MMAs no longer read), then ALL epilogue threads run the posterior on the flat mapping.
-      wait_layer();
+      // Every CTA of a cluster does this redundantly (same inputs, same noise); rank 0 alone writes to global memory.
+      wait_layer(true);
       {
         float* s_eps = reinterpret_cast<float*>(s.x_hi);
         if (q * 32 < a.D) {
@@ -484,10 +560,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           stdv = fmaxf(row.std_train, a.min_std);
         }
         const float inv_2var = 1.f / (2.f * (stdv * stdv)), log_std = logf(stdv);
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < CPT; ++j) {
           const int i = et + j * kEpiThreads;
-          if (i < nxe) {
+          if (i >= nxe) break;
+          {
             const int e = i / a.D, f = i - e * a.D;
             const int env = env0 + e;
             float eps = s_eps[i];
@@ -511,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
               if (a.eval_mode) {
                 xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + f];
                 const float diff = xn - mu;
-                a.logp[(size_t(env) * a.ft + d_eval) * a.D + f] = -(diff * diff) * inv_2var - log_std - 0.91893853320467274f;
+                if (rank == 0) a.logp[(size_t(env) * a.ft + d_eval) * a.D + f] = -(diff * diff) * inv_2var - log_std - 0.91893853320467274f;
               } else {
                 float z;
                 if (a.noise)
@@ -521,8 +598,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
                 z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
                 xn = mu + stdv * z;
                 if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
-                if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
-                if (last) a.traj[size_t(env) * a.D + f] = xn;
+                if (rank == 0) {
+                  if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
+                  if (last) a.traj[size_t(env) * a.D + f] = xn;
+                }
               }
             }
             xreg[j] = xn;
@@ -538,34 +617,64 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         }
       }
-      signal_x();
+      signal_x(false);
     }
-    if (a.prof && et == 0) a.prof[blockIdx.x * 16 + 5] = e_wait, a.prof[blockIdx.x * 16 + 6] = clock64() - e_t0;
-    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 8 + (warp - 2)] = (clock64() - e_t0) - e_wait;
+    if (a.prof && et == 0) a.prof[blockIdx.x * 16 + 5] = e_wait, a.prof[blockIdx.x * 16 + 6] = clock64() - e_t0, a.prof[blockIdx.x * 16 + 7] = e_hand;
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 8 + (warp - 2)] = (clock64() - e_t0) - e_wait - e_hand;
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (C > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal it or copy into it
 }
 
 // ============================================================================================== host launch
-// Environments per CTA tile (= N of every MMA).  An MMA of this kernel is bound by the shared-memory read of its
-// 128 x 16 weight operand, so its cost barely depends on N: the fastest launch is the smallest tile that still fits the
-// tiles of the call into ONE wave of CTAs (one CTA per SM).  DPPO_B200_TILE_ENVS overrides (bring-up / tuning).
-static int pick_tile_envs(const dppo_ctx* ctx, int E) {
-  const int cap = ctx->g.H <= 512 ? 64 : 32;  // X operand (NE x H bf16 hi + lo) must leave room for the weight ring
-  static int forced = -1;
-  if (forced < 0) {
+// Launch shape: NE environments per tile (= N of every MMA) and C CTAs per cluster sharing one tile (feature split).
+// Cost model per CTA and denoising step, from the micro-benchmarks in profiles/ (cycles):
+//   ingest   weight tiles this CTA streams x 16 KiB / 34.7 B/cycle          (L2 -> shared memory, per-SM limit)
+//   mma      MMAs x max(NE/2, 32 + NE/4)                                    (tensor floor vs. shared-memory operand read)
+//   epi      activation elements per epilogue thread x ~30 cycles
+//   exch     bytes pushed to the peers / ~25 B/cycle
+// and the launch needs ceil(tiles / co-resident clusters) waves.  DPPO_B200_TILE_ENVS / DPPO_B200_CLUSTER override.
+struct LaunchShape {
+  int NE, C;
+};
+static LaunchShape pick_shape(const dppo_ctx* ctx, int E) {
+  const MlpGeom& g = ctx->g;
+  const int cap = g.H <= 512 ? 64 : 32;  // X operand (NE x H bf16 hi + lo) must leave room for the weight ring
+  static int env_ne = -1, env_c = -1;
+  if (env_ne < 0) {
     const char* e = getenv("DPPO_B200_TILE_ENVS");
-    forced = e ? atoi(e) : 0;
+    env_ne = e ? atoi(e) : 0;
+    e = getenv("DPPO_B200_CLUSTER");
+    env_c = e ? atoi(e) : 0;
   }
-  if ((forced == 16 || forced == 32 || forced == 64) && forced <= cap) return forced;
-  const int tiles[3] = {16, 32, 64};
-  for (int ne : tiles)
-    if (ne <= cap && (E + ne - 1) / ne <= ctx->sm_count) return ne;
-  return cap;
+  const int forced_ne = ctx->force_ne ? ctx->force_ne : env_ne, forced_c = ctx->force_c ? ctx->force_c : env_c;
+  const int max_clusters[4] = {ctx->sm_count, ctx->sm_count / 2, (ctx->sm_count - 16) / 4, 16};  // C = 1, 2, 4, 8
+  LaunchShape best{cap, 1};
+  double best_t = 1e30;
+  for (int ci = 0; ci < 4; ++ci) {
+    const int C = 1 << ci;
+    if (g.MT % C || (g.ln && C > 1)) continue;  // LayerNorm statistics span all features: not split yet
+    if (forced_c > 0 && C != forced_c) continue;
+    for (int NE = 16; NE <= cap; NE *= 2) {
+      if (forced_ne > 0 && NE != forced_ne) continue;
+      const int tiles = (E + NE - 1) / NE;
+      const int waves = (tiles + max_clusters[ci] - 1) / max_clusters[ci];
+      const double pairs = double(g.MT / C) * (g.KC0 + 2.0 * g.nb * g.KCH) + g.KCH;  // (hi, lo) tile pairs per step
+      const double ingest = pairs * g.nsplit * 16384.0 / 34.7;
+      const double per_mma = NE / 2.0 > 32.0 + NE / 4.0 ? NE / 2.0 : 32.0 + NE / 4.0;
+      const double mma = pairs * 4.0 * (g.nsplit == 2 ? 3.0 : 1.0) * per_mma;
+      const double layers = 1.0 + 2.0 * g.nb;
+      const double epi = layers * (double(NE) * g.H / C / 256.0) * 30.0 + 2000.0;
+      const double exch = C > 1 ? layers * (C - 1) * (2.0 * g.MT / C * NE * 128.0 * g.nsplit) / 25.0 + layers * 1500.0 : 0.0;
+      const double t = waves * ((ingest > mma ? ingest : mma) + epi + exch);
+      if (t < best_t) best_t = t, best = LaunchShape{NE, C};
+    }
+  }
+  return best;
 }
 
 template <int NE, int ACT, bool LN>
@@ -577,9 +686,14 @@ static int launch(const ChainArgs& a, size_t smem_bytes, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(chain_mlp_kernel)");
     configured = true;
   }
-  const int grid = (a.E + NE - 1) / NE;
-  kfn<<<grid, kThreads, smem_bytes, st>>>(a);
-  cudaError_t e = cudaGetLastError();
+  const int tiles = (a.E + NE - 1) / NE;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(tiles * a.C)), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(a.C), attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, a);
   if (e != cudaSuccess) return cuda_fail(e, "chain_mlp_kernel launch");
   return DPPO_OK;
 }
@@ -606,7 +720,9 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
   a.prof = ctx->d_prof;
 
-  const int NE = pick_tile_envs(ctx, E);
+  const LaunchShape shape = pick_shape(ctx, E);
+  const int NE = shape.NE;
+  a.C = shape.C;
   const size_t fixed = smem_fixed_bytes(g, NE);
   const size_t budget = 232448;
   if (fixed + 2 * kTile > budget) return set_error("chain kernel: geometry needs %zu B of shared memory", fixed), DPPO_ERR_INVALID;

@@ -74,5 +74,6 @@ struct dppo_ctx {
   std::vector<dppo::StepRow> rows;        // host copy, S rows
   dppo::StepRow* d_rows = nullptr;        // device copy
   dppo::PackedNet nets[2];
+  int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

@@ -5,8 +5,6 @@
 //                           (L2 resident) into a shared-memory ring with 16 KiB bulk copies - optionally as thread-block
 //                           clusters in which each CTA fetches 1/C of every tile and multicasts it to its peers
 // Both tell the chain kernel which resource bounds it (DESIGN.md "Chain kernel roofline").
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 
 namespace dppo {
@@ -58,33 +56,6 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int 
 }
 
 // ---------------------------------------------------------------------------------------------------- streaming
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// bulk copy global -> shared memory of every CTA in `mask` (same CTA-relative offsets), completing on each one's barrier
-__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
-                                                   uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-// arrive on the barrier at the same CTA-relative offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-      "r"(rank)
-      : "memory");
-}
-
 constexpr int kSbStages = 8;
 constexpr uint32_t kSbTile = 16384;
 

@@ -99,6 +99,12 @@ static int launch_pack_linear(const float* W, int out_f, int in_f, int skip_at, 
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// dst = src + prev (prev may be null): running sum of the l2 biases over the residual blocks
+__global__ void add_vec_kernel(const float* __restrict__ src, const float* __restrict__ prev, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] + (prev ? prev[i] : 0.f);
+}
+
 static void copy_pad(const float* src, int n, float* dst, int n_pad, cudaStream_t st) {
   copy_pad_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src, n, dst, n_pad);
 }
@@ -145,7 +151,8 @@ int pack_mlp_impl(dppo_ctx* ctx, int which, const float* const* p, int n_params,
     if (launch_pack_linear(w2, g.H, g.H, 0, 0, g.MT, g.KCH, g.nsplit, cur, st)) goto fail;
     cur += (size_t)g.MT * g.KCH * tile_group;
     copy_pad(b1, g.H, side, g.H, st);
-    copy_pad(b2, g.H, side + g.H, g.H, st);
+    // the residual stream's biases are added by the epilogue, not stored back into TMEM: slot 1 = b2_0 + ... + b2_b
+    add_vec_kernel<<<(g.H + 255) / 256, 256, 0, st>>>(b2, b > 0 ? side - g.blk_stride + g.H : nullptr, g.H, side + g.H);
     if (g.ln) {
       for (int q = 0; q < 4; ++q) copy_pad(p[i++], g.H, side + (size_t)(2 + q) * g.H, g.H, st);  // g1 be1 g2 be2
     }

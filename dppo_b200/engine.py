@@ -115,6 +115,11 @@ class ChainEngine:
         except Exception:
             pass
 
+    def set_launch_shape(self, tile_envs=0, cluster=0):
+        """Tuning / test hook: force the chain kernel's tile size and cluster size (0 = cost model)."""
+        self.lib.dppo_debug_set_shape.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _lib.check(self.lib.dppo_debug_set_shape(self.ctx, int(tile_envs), int(cluster)), "dppo_debug_set_shape")
+
     # ------------------------------------------------------------------ weights
     def sync_weights(self, which, net):
         ps = _mlp_param_list(net)

@@ -13,10 +13,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "walker2d"
 w = get_workload(name)
 E = int(sys.argv[2]) if len(sys.argv) > 2 else w["n_envs"]
 prec = sys.argv[3] if len(sys.argv) > 3 else "split3"
+ne = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+cl = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 model = build_model(w, "cuda:0", our_classes())
 model.engine_precision = prec
 eng = model.engine()
-grid = (E + 31) // 32
+eng.set_launch_shape(ne, cl)
+grid = ((E + 15) // 16) * 8
 prof = torch.zeros(grid * 16, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 lib.dppo_debug_set_prof.argtypes = [C.c_void_p, C.c_void_p]
@@ -32,8 +35,8 @@ b.record()
 torch.cuda.synchronize()
 p = prof.view(grid, 16).cpu()
 used = p[p[:, 4] > 0]
-names = ["prod_wait_empty", "prod_total", "mma_wait_x", "mma_wait_full", "mma_total", "epi_wait_layer", "epi_total", "-"] + [f"epi_work_warp{i+2}" for i in range(8)]
-print(f"{name} E={E} {prec}: kernel {a.elapsed_time(b):.3f} ms, {len(used)} CTAs")
+names = ["prod_wait_empty", "prod_total", "mma_wait_x", "mma_wait_full", "mma_total", "epi_wait_layer", "epi_total", "epi_handshake"] + [f"epi_work_warp{i+2}" for i in range(8)]
+print(f"{name} E={E} {prec} NE={ne} C={cl}: kernel {a.elapsed_time(b):.3f} ms, {len(used)} CTAs")
 for i, n in enumerate(names):
     col = used[:, i].double()
     print(f"  {n:16s} mean {col.mean() / 1e3:10.1f} kcyc   max {col.max() / 1e3:10.1f} kcyc")

@@ -171,3 +171,21 @@ def test_bf16_fast_mode_within_its_tolerance_report():
     e = rel_err(out.chains.cpu().numpy(), gold["chains"])
     assert np.isfinite(e).all()
     assert float((e > 5e-3).mean()) < 0.05, f"bf16 fast mode: max {e.max():.3e}, {(e > 5e-3).mean():.3%} over 5e-3"
+
+
+@pytest.mark.parametrize("case,tile_envs,cluster", [
+    ("hopper", 16, 1), ("hopper", 32, 2), ("hopper", 16, 4), ("hopper", 64, 4), ("walker2d", 64, 2), ("walker2d", 32, 4),
+    ("transport_k20", 32, 2), ("transport_k20", 16, 8), ("transport", 32, 4),
+])
+def test_chain_and_logprobs_every_launch_shape(case, tile_envs, cluster):
+    """Feature-split clusters (C CTAs share one env tile) and every tile size give the same chains / log-probs."""
+    w, model, gold, inp = _setup(case)
+    model.engine().set_launch_shape(tile_envs, cluster)
+    state, noise = inp["state"].cuda(), inp["noise"].cuda()
+    out = model(cond={"state": state}, deterministic=False, return_chain=True, noise=noise)
+    torch.cuda.synchronize()
+    assert_close(out.chains.cpu().numpy(), gold["chains"], 1e-3, f"{case} chains NE={tile_envs} C={cluster}", max_frac=2e-3)
+    assert_close(out.trajectories.cpu().numpy(), gold["traj"], 1e-3, f"{case} traj NE={tile_envs} C={cluster}", max_frac=2e-3)
+    with torch.no_grad():
+        lp = model.get_logprobs({"state": state}, torch.from_numpy(gold["chains"]).cuda())
+    assert_close(lp.cpu().numpy(), gold["logprobs"], 1e-3, f"{case} log-probs NE={tile_envs} C={cluster}", max_frac=2e-3)
