@@ -98,9 +98,10 @@ __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, int row,
 
 struct Smem {
   uint8_t *x_hi, *x_lo, *x0_hi, *x0_lo, *ring;
-  uint64_t *full, *empty, *layer_done, *x_full, *can_send;
+  uint64_t *full, *empty, *layer_done, *x_full, *can_send, *ln_bar;
   uint32_t* tmem_slot;
-  float* ln_part;  // [kEpiWarps][2][32]
+  float* ln_part;  // [kEpiWarps][2][32] per-warp partial sums
+  float* ln_x;     // [8 ranks][64 envs][2] per-CTA partial sums of a cluster (LayerNorm over features split across CTAs)
 };
 
 template <int NE>
@@ -118,14 +119,16 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
   s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
   s.can_send = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.ln_bar = reinterpret_cast<uint64_t*>(p), p += 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
-  s.ln_part = reinterpret_cast<float*>(p);
+  s.ln_part = reinterpret_cast<float*>(p), p += kEpiWarps * 2 * 32 * 4;
+  s.ln_x = reinterpret_cast<float*>(p);
   return s;
 }
 
 static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
   const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
-  return xb + x0b + 16 * kMaxStages + 48 + kEpiWarps * 2 * 32 * 4 + 1024 /* alignment slack */;
+  return xb + x0b + 16 * kMaxStages + 64 + kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 + 1024 /* alignment slack */;
 }
 
 // ============================================================================================== the kernel
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     mbar_init(s.layer_done, 1);
     mbar_init(s.x_full, 1);
     mbar_init(s.can_send, C > 1 ? C - 1 : 1);
+    mbar_init(s.ln_bar, C * NE);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_slot, 512);
@@ -354,8 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // lanes swap one value per column pair (even lane keeps column c, odd lane column c + 1), so that every thread owns
     // TWO consecutive features of one env row: one packed bf16x2 convert and one 4-byte store per operand half.
     const uint32_t odd = lane & 1;
+    uint32_t ln_phase = 0;
+    // `whole_row`: this CTA holds every feature of the layer (cond_mlp), otherwise they are split over the cluster
     auto epi_hidden = [&](uint32_t region, int mt_first, int MTl, const float* bias_a, const float* bias_b, bool identity,
-                          const float* ln_g, const float* ln_b) {
+                          const float* ln_g, const float* ln_b, bool whole_row) {
       float mean[LN ? CPT : 1], rstd[LN ? CPT : 1];
       if (LN && ln_g != nullptr) {
         float s1[CPT], s2[CPT];
@@ -386,18 +392,52 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           for (int c = 0; c < CPT; ++c) mine[c] = s1[c], mine[32 + c] = s2[c];
         }
         named_bar_sync(1, kEpiThreads);
-        const float inv_n = 1.f / float(MTl * 128);
+        if (whole_row || C == 1) {
+          const float inv_n = 1.f / float(MTl * 128);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          float t1 = 0.f, t2 = 0.f;
+          for (int c = 0; c < CPT; ++c) {
+            float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const float* part = s.ln_part + (half * 4 + w) * 64;
-            t1 += part[c], t2 += part[32 + c];
+            for (int w = 0; w < 4; ++w) {
+              const float* part = s.ln_part + (half * 4 + w) * 64;
+              t1 += part[c], t2 += part[32 + c];
+            }
+            const float m = t1 * inv_n;
+            const float var = fmaxf(t2 * inv_n - m * m, 0.f);
+            mean[LN ? c : 0] = m, rstd[LN ? c : 0] = rsqrtf(var + 1e-6f);
           }
-          const float m = t1 * inv_n;
-          const float var = fmaxf(t2 * inv_n - m * m, 0.f);
-          mean[LN ? c : 0] = m, rstd[LN ? c : 0] = rsqrtf(var + 1e-6f);
+        } else {
+          // the row's features are split over the C CTAs of the cluster: thread e < NE publishes this CTA's partial sums of
+          // env e to every CTA (remote stores, then a releasing arrive on that CTA's ln_bar); everybody then adds C partials
+          if (et < NE) {
+            const int h_ = et / CPT, c_ = et % CPT;
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float* part = s.ln_part + (h_ * 4 + w) * 64;
+              t1 += part[c_], t2 += part[32 + c_];
+            }
+            float* slot = s.ln_x + (rank * 64 + et) * 2;
+            for (uint32_t p = 0; p < uint32_t(C); ++p) {
+              st_remote_f32(slot, p, t1);
+              st_remote_f32(slot + 1, p, t2);
+              mbar_arrive_remote(s.ln_bar, p);
+            }
+          }
+          mbar_wait_cluster(s.ln_bar, ln_phase);
+          ln_phase ^= 1;
+          const float inv_n = 1.f / float(MTl * 128 * C);
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int r = 0; r < C; ++r) {
+              const float* slot = s.ln_x + (r * 64 + col0 + c) * 2;
+              t1 += slot[0], t2 += slot[1];
+            }
+            const float m = t1 * inv_n;
+            const float var = fmaxf(t2 * inv_n - m * m, 0.f);
+            mean[LN ? c : 0] = m, rstd[LN ? c : 0] = rsqrtf(var + 1e-6f);
+          }
         }
       }
       for (int mt = 0; mt < MTl; ++mt) {
@@ -526,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         }
         wait_layer(L >= 0);
-        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb);
+        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0);
         signal_x(L >= 0);
       }
       cur_net = net;
@@ -657,7 +697,7 @@ static LaunchShape pick_shape(const dppo_ctx* ctx, int E) {
   double best_t = 1e30;
   for (int ci = 0; ci < 4; ++ci) {
     const int C = 1 << ci;
-    if (g.MT % C || (g.ln && C > 1)) continue;  // LayerNorm statistics span all features: not split yet
+    if (g.MT % C) continue;
     if (forced_c > 0 && C != forced_c) continue;
     for (int NE = 16; NE <= cap; NE *= 2) {
       if (forced_ne > 0 && NE != forced_ne) continue;

@@ -104,6 +104,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), rank)) : "memory");
 }
+// store one float into CTA `rank`'s shared memory at the CTA-relative address of `local`
+__device__ __forceinline__ void st_remote_f32(float* local, uint32_t rank, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_u32(smem_u32(local), rank)), "f"(v) : "memory");
+}
 // acquire at cluster scope: pairs with mbar_arrive_remote of a peer CTA
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

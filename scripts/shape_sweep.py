@@ -19,7 +19,7 @@ for ne in (16, 32, 64):
     if ne == 64 and MT > 4:
         continue
     for c in (1, 2, 4, 8):
-        if MT % c or (c > 1 and w["actor"].get("use_layernorm")):
+        if MT % c:
             continue
         eng.set_launch_shape(ne, c)
         try:

@@ -176,6 +176,7 @@ def test_bf16_fast_mode_within_its_tolerance_report():
 @pytest.mark.parametrize("case,tile_envs,cluster", [
     ("hopper", 16, 1), ("hopper", 32, 2), ("hopper", 16, 4), ("hopper", 64, 4), ("walker2d", 64, 2), ("walker2d", 32, 4),
     ("transport_k20", 32, 2), ("transport_k20", 16, 8), ("transport", 32, 4),
+    ("furniture", 16, 8), ("furniture", 32, 2), ("furniture_ddpm100", 16, 4),
 ])
 def test_chain_and_logprobs_every_launch_shape(case, tile_envs, cluster):
     """Feature-split clusters (C CTAs share one env tile) and every tile size give the same chains / log-probs."""
