@@ -220,6 +220,11 @@ def run_b200(args, w, E, rank, world, local_rank):
             pass
         peak = float(peaks.get("bf16_tflops", 1590.0))
         achieved = flops_launch / (k_ms * 1e-3) / 1e12
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the latest `ncu --set full` capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{E}")
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -232,9 +237,12 @@ def run_b200(args, w, E, rank, world, local_rank):
             "gpu_launches": args.steps,
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "chain_mlp_kernel",
+                         "traffic": traffic, "kernel": "chain_mlp_kernel",
                          "note": ("algorithmic FLOPs S*F_net*E (1x); split3 issues 3 bf16 MMAs per logical MMA so frac <= 1/3; "
-                                  + ("peak = MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "peak = fallback 1.59 PF"))},
+                                  "the kernel is bound by the per-SM L2->shared weight ingest (34.7 B/cycle/SM measured), "
+                                  "see DESIGN.md section 3; traffic = ncu dram bytes per launch (bytes); "
+                                  + ("peak = MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone), of measured"
+                                     if peaks else "peak = fallback 1.59 PF, of fallback"))},
             "wall_s_timed_region": wall,
             "update": upd,
         }
@@ -270,31 +278,26 @@ def bench_update(args, w, model, dev, E, rank, world):
         values_k = model.critic({"state": obs_k}).view(-1)
     adv_k = torch.randn(N, device=dev, generator=g)
     ret_k = adv_k + values_k
+    from dppo_b200 import distributed as D
+
     bs = min(w["train"]["batch_size"], N * ft)
-    per_rank = bs // world
     opt_a = torch.optim.AdamW(model.actor_ft.parameters(), lr=w["train"]["actor_lr"])
     opt_c = torch.optim.AdamW(model.critic.parameters(), lr=w["train"]["critic_lr"])
-    params = [p for p in list(model.actor_ft.parameters()) + list(model.critic.parameters()) if p.requires_grad]
+    grads = D.FlatGradBuffer(list(model.actor_ft.parameters()) + list(model.critic.parameters()))
+    lo, hi = D.minibatch_slice(bs, rank, world)
+    per_rank = bs // world
 
     def minibatch(k):
-        inds = torch.randperm(N * ft, device=dev)[:bs]
-        if world > 1:
-            dist.broadcast(inds, 0)
-        res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=rank * per_rank,
-                                  row_count=per_rank, reward_horizon=w["act_steps"])
-        loss = res[0] + w["train"]["vf_coef"] * res[2]
-        opt_a.zero_grad(set_to_none=False)
-        opt_c.zero_grad(set_to_none=False)
-        loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            o = 0
-            for p in params:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p))
-                o += p.numel()
+        inds = D.broadcast_permutation(N * ft, dev)[:bs]
+        grads.zero()
+        res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo,
+                                  row_count=hi - lo, reward_horizon=w["act_steps"], scalars_out=grads.scalars)
+        (res[0] + w["train"]["vf_coef"] * res[2]).backward()
+        grads.allreduce()  # gradients of both networks + loss diagnostics: one NCCL all-reduce
+        kl = grads.scalars.tolist()[2]  # the agent's early-stop test: one device->host read per minibatch
         opt_a.step()
         opt_c.step()
+        return kl
 
     for k in range(3):
         minibatch(k)
@@ -309,7 +312,8 @@ def bench_update(args, w, model, dev, E, rank, world):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
             "minibatch_rows": per_rank * world, "buffer_rows": N * ft,
-            "path": "fused gather+log-prob+loss fwd/bwd kernel; network GEMMs via torch autograd (cuBLAS); AdamW torch"}
+            "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
+                     "network GEMMs via torch autograd (cuBLAS fp32); AdamW torch")}
 
 
 def main():

@@ -91,3 +91,46 @@ def get_workload(name: str) -> dict:
 def chain_evals(w: dict) -> int:
     """Number of network evaluations per sampled action chunk (S in SURVEY.md §8)."""
     return w["ddim_steps"] if w["use_ddim"] else w["denoising_steps"]
+
+
+def make_agent_cfg(w: dict, device: str, logdir: str, n_envs: int = None, n_steps: int = None, n_train_itr: int = 2,
+                   batch_size: int = None, update_epochs: int = None, seed: int = 42, precision: str = None):
+    """
+    Config tree for dppo_b200.agent.finetune.train_ppo_diffusion_agent.TrainPPODiffusionAgent with the keys of the
+    reference YAML cited in `w["yaml"]` (model node = Hydra-style `_target_` dicts).  Only DiffusionMLP actors.
+    """
+    from dppo_b200.util.config import Cfg
+
+    a = dict(w["actor"])
+    if a.pop("kind") != "mlp":
+        raise NotImplementedError("agent configs are built for DiffusionMLP actors")
+    t = w["train"]
+    cond_dim = w["obs_dim"] * w["cond_steps"]
+    E = n_envs or w["n_envs"]
+    model = {
+        "_target_": "dppo_b200.model.diffusion.diffusion_ppo.PPODiffusion",
+        "actor": dict({"_target_": "dppo_b200.model.diffusion.mlp_diffusion.DiffusionMLP", "action_dim": w["action_dim"],
+                       "horizon_steps": w["horizon_steps"], "cond_dim": cond_dim}, **a),
+        "critic": dict({"_target_": "dppo_b200.model.common.critic.CriticObs", "cond_dim": cond_dim}, **w["critic"]),
+        "ft_denoising_steps": w["ft_denoising_steps"], "horizon_steps": w["horizon_steps"], "obs_dim": w["obs_dim"],
+        "action_dim": w["action_dim"], "denoising_steps": w["denoising_steps"], "device": device,
+        "use_ddim": w["use_ddim"], "ddim_steps": w["ddim_steps"], "network_path": None, "learn_eta": False,
+        "engine_precision": precision, **w["ppo"],
+    }
+    if w.get("eta"):
+        model["eta"] = dict({"_target_": "dppo_b200.model.diffusion.eta.EtaFixed"}, **w["eta"])
+    sched = dict(first_cycle_steps=1000, warmup_steps=10, min_lr=t["actor_lr"])
+    return Cfg(
+        device=device, seed=seed, logdir=logdir, obs_dim=w["obs_dim"], action_dim=w["action_dim"], cond_steps=w["cond_steps"],
+        act_steps=w["act_steps"], horizon_steps=w["horizon_steps"],
+        env=dict(n_envs=E, name="synthetic", max_episode_steps=t["max_episode_steps"], reset_at_iteration=False,
+                 best_reward_threshold_for_success=3),
+        train=dict(n_train_itr=n_train_itr, val_freq=10 ** 9, force_train=True, n_steps=n_steps or t["n_steps"],
+                   gamma=t["gamma"], gae_lambda=t["gae_lambda"], n_critic_warmup_itr=t["n_critic_warmup_itr"],
+                   actor_lr=t["actor_lr"], critic_lr=t["critic_lr"], actor_weight_decay=0, critic_weight_decay=0,
+                   actor_lr_scheduler=sched, critic_lr_scheduler=dict(sched, min_lr=t["critic_lr"]),
+                   batch_size=batch_size or t["batch_size"], update_epochs=update_epochs or t["update_epochs"],
+                   vf_coef=t["vf_coef"], target_kl=t["target_kl"], reward_scale_running=True, reward_scale_const=1.0,
+                   save_model_freq=10 ** 9, logprob_batch_size=max(E, (10000 // E) * E)),
+        model=model,
+    )

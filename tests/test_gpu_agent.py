@@ -1,0 +1,85 @@
+"""The B200 agent loop end to end on cuda:0 (tiny Hopper-shaped run) and its pieces against the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from dppo_b200.workloads import get_workload, make_agent_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _agent(tmp_path, **kw):
+    from dppo_b200.agent.finetune.train_ppo_diffusion_agent import TrainPPODiffusionAgent
+
+    w = get_workload("hopper")
+    cfg = make_agent_cfg(w, "cuda:0", str(tmp_path), **kw)
+    return w, TrainPPODiffusionAgent(cfg)
+
+
+def test_prologue_matches_oracle_gae_and_model_calls(tmp_path):
+    from oracle import dppo_oracle as O
+
+    w, ag = _agent(tmp_path, n_envs=8, n_steps=6, batch_size=64, update_epochs=1)
+    firsts = np.zeros((ag.n_steps + 1, ag.n_envs))
+    firsts[0] = 1
+    obs0 = ag.reset_env_all()
+    ag.model.train()
+    obs_buf, chains_buf, rew, term, last_obs, done, _ = ag.rollout(obs0, False, firsts)
+    rew0 = rew.copy()
+    values, logprobs, adv, ret = ag.prologue(obs_buf, chains_buf, rew, term, firsts, last_obs)
+    # values / log-probs are the model's own calls on the flattened (step, env) rows
+    obs_k = obs_buf.view(-1, 1, w["obs_dim"])
+    with torch.no_grad():
+        v_ref = ag.model.critic({"state": obs_k}).view(ag.n_steps, ag.n_envs)
+        lp_ref = ag.model.get_logprobs({"state": obs_k}, chains_buf.view(-1, *chains_buf.shape[2:]))
+    assert torch.equal(values, v_ref) and torch.equal(logprobs.view_as(lp_ref), lp_ref)
+    # GAE (float64 kernel) against the oracle's restatement of the reference's numpy loop, with the same scaled rewards
+    scaler = O.RunningRewardScaler(ag.n_envs)
+    rew_s = scaler(rew0.T, firsts[:-1].T).T
+    with torch.no_grad():
+        nxt = ag.model.critic({"state": torch.from_numpy(last_obs["state"]).cuda()}).view(-1).double().cpu().numpy()
+    adv_o, ret_o = O.gae(rew_s, term, values.double().cpu().numpy(), nxt, ag.gamma, ag.gae_lambda, 1.0)
+    np.testing.assert_allclose(adv.cpu().numpy(), adv_o, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ret.cpu().numpy(), ret_o, rtol=1e-6, atol=1e-6)
+
+
+def test_run_two_iterations_updates_and_checkpoints(tmp_path):
+    w, ag = _agent(tmp_path, n_envs=8, n_steps=8, batch_size=128, update_epochs=2, n_train_itr=2)
+    before = {k: v.clone() for k, v in ag.model.actor_ft.state_dict().items()}
+    base = {k: v.clone() for k, v in ag.model.actor.state_dict().items()}
+    res = ag.run()
+    assert len(res) == 2 and all(np.isfinite(r["pg_loss"]) and np.isfinite(r["v_loss"]) for r in res)
+    assert res[-1]["step"] == 2 * 8 * 8 * w["act_steps"] and res[-1]["minibatches"] >= 1
+    assert any(not torch.equal(before[k], v) for k, v in ag.model.actor_ft.state_dict().items())
+    assert all(torch.equal(base[k], v) for k, v in ag.model.actor.state_dict().items())  # frozen base policy
+    ckpt = torch.load(tmp_path / "checkpoint" / "state_1.pt", weights_only=True)
+    keys = set(k.split(".")[0] for k in ckpt["model"])
+    assert ckpt["itr"] == 1 and {"network", "actor", "actor_ft", "critic"} <= keys
+
+
+def test_update_equals_plain_autograd_minibatch(tmp_path):
+    """One minibatch through the flat-gradient path == model.loss (reference signature) + autograd on the same rows."""
+    w, ag = _agent(tmp_path, n_envs=8, n_steps=6, batch_size=96, update_epochs=1)
+    firsts = np.zeros((ag.n_steps + 1, ag.n_envs))
+    obs_buf, chains_buf, rew, term, last_obs, _, _ = ag.rollout(ag.reset_env_all(), False, firsts)
+    values, logprobs, adv, ret = ag.prologue(obs_buf, chains_buf, rew, term, firsts, last_obs)
+    m, ft = ag.model, ag.model.ft_denoising_steps
+    N = ag.n_steps * ag.n_envs
+    obs_k, chains_k = obs_buf.view(N, 1, -1), chains_buf.view(N, ft + 1, *chains_buf.shape[3:])
+    lp_k = logprobs.view(N, ft, *logprobs.shape[3:])
+    inds = torch.randperm(N * ft, device="cuda")[:96]
+    ag.grads.zero()
+    r1 = m.loss_gathered(obs_k, chains_k, lp_k, ret.reshape(-1), values.reshape(-1), adv.reshape(-1), inds,
+                         reward_horizon=ag.reward_horizon, scalars_out=ag.grads.scalars)
+    (r1[0] + 0.5 * r1[2]).backward()
+    g_flat = ag.grads.flat[: ag.grads.n_grad].clone()
+    for p in ag.grads.params:
+        p.grad = None
+    b, d = inds // ft, inds % ft
+    r0 = m.loss({"state": obs_k[b]}, chains_k[b, d], chains_k[b, d + 1], d, ret.reshape(-1)[b], values.reshape(-1)[b],
+                adv.reshape(-1)[b], lp_k[b, d], reward_horizon=ag.reward_horizon)
+    (r0[0] + 0.5 * r0[2]).backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in ag.grads.params])
+    assert float((g_flat - g_ref).abs().max()) <= 1e-5 * max(1.0, float(g_ref.abs().max()))
+    assert abs(float(ag.grads.scalars[0]) - float(r0[0])) <= 1e-6 * max(1.0, abs(float(r0[0])))
