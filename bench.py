@@ -58,7 +58,7 @@ def workload_name(w, E):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -159,12 +159,12 @@ def run_b200(args, w, E, rank, world, local_rank):
         return eng.sample(states[i % n_bufs], noise=None, seed=42, offset=i + 1, env_offset=rank * E, min_sampling_std=min_std)
 
     # ---- value: kernel-resident throughput
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for i in range(args.warmup):
         flush.zero_()
         kernel_step(i)
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -197,7 +197,18 @@ def run_b200(args, w, E, rank, world, local_rank):
         e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the timed regions are tens of milliseconds, nvidia-smi samples every 100 ms: keep issuing the SAME launches (untimed)
+    # until the sampler has seen the device under this load for at least a second
+    t_load = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_load < 1.2:
+        kernel_step(i)
+        i += 1
+        if i % 16 == 0:
+            torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
     clk = clocks.stop()
+    clk["window"] = "warm-up + timed steps + e2e steps + 1.2 s of the same launches (untimed continuation)"
 
     # ---- update (secondary): one PPO minibatch = fused loss kernel + autograd backward + both optimiser steps
     upd = bench_update(args, w, model, dev, E, rank, world) if args.update else None
