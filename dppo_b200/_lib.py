@@ -17,7 +17,8 @@ PRECISIONS = {"split3": PRECISION_SPLIT3, "bf16": PRECISION_BF16}
 
 # every symbol include/dppo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "dppo_last_error", "dppo_version", "dppo_ctx_create", "dppo_ctx_destroy", "dppo_pack_mlp", "dppo_sample_chain",
+    "dppo_last_error", "dppo_version", "dppo_ctx_create", "dppo_ctx_destroy", "dppo_pack_mlp", "dppo_ctx_create_unet",
+    "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain",
     "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64",
     "dppo_selftest_umma",
 ]
@@ -27,6 +28,32 @@ class MlpDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "cond_dim", "action_dim", "horizon_steps", "time_dim", "hidden_dim", "n_blocks", "activation",
         "use_layernorm", "cond_hidden", "cond_out")]
+
+
+UNET_MAX_LEVELS = 4
+
+
+class UnetDesc(C.Structure):
+    _fields_ = [
+        ("cond_dim", C.c_int32), ("action_dim", C.c_int32), ("horizon_steps", C.c_int32), ("time_dim", C.c_int32),
+        ("dim", C.c_int32), ("n_levels", C.c_int32), ("dim_mults", C.c_int32 * UNET_MAX_LEVELS),
+        ("kernel_size", C.c_int32), ("n_groups", C.c_int32), ("activation", C.c_int32),
+        ("cond_predict_scale", C.c_int32), ("larger_encoder", C.c_int32), ("groupnorm_eps", C.c_float),
+    ]
+
+
+class UGemm(C.Structure):
+    """csrc/unet_plan.h UGemm (host-only inspection of the lowered Unet program)."""
+    _fields_ = [("tile_off", C.c_uint32), ("mt", C.c_uint16), ("kc", C.c_uint16), ("src_chunk", C.c_uint16 * 2),
+                ("src_n", C.c_uint16 * 2), ("acc_tile", C.c_uint16), ("pad", C.c_uint16)]
+
+
+class ULayer(C.Structure):
+    """csrc/unet_plan.h ULayer."""
+    _fields_ = [("n_gemm", C.c_int32), ("g", UGemm * 2)] + [(n, C.c_int32) for n in (
+        "kind", "acc_tile", "mt", "nf", "bias_off", "bias_tstride", "gn_size", "gamma_off", "beta_off")] + [
+        ("gn_eps", C.c_float)] + [(n, C.c_int32) for n in (
+            "act", "film", "film_c", "film_tshift", "res", "res_acc_tile", "res_bias_off", "res_chunk", "dst_chunk")]
 
 
 class SchedDesc(C.Structure):
@@ -74,6 +101,19 @@ def load(build_if_missing=True):
     lib.dppo_ctx_create.argtypes = [C.POINTER(vp), C.POINTER(MlpDesc), C.POINTER(SchedDesc), i32, i32]
     lib.dppo_ctx_destroy.argtypes = [vp]
     lib.dppo_pack_mlp.argtypes = [vp, i32, C.POINTER(vp), i32, vp]
+    lib.dppo_ctx_create_unet.argtypes = [C.POINTER(vp), C.POINTER(UnetDesc), C.POINTER(SchedDesc), i32, i32]
+    lib.dppo_pack_unet.argtypes = [vp, i32, C.POINTER(vp), i32, vp]
+    lib.dppo_unet_param_count.argtypes = [C.POINTER(UnetDesc)]
+    # host-only inspection of the lowered Unet program (tests; not part of the public header)
+    lib.dppo_unet_plan_create.argtypes = [C.POINTER(UnetDesc), i32, i32, C.POINTER(vp)]
+    lib.dppo_unet_plan_destroy.argtypes = [vp]
+    lib.dppo_unet_plan_info.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.dppo_unet_plan_layers.argtypes = [vp, vp]
+    lib.dppo_unet_plan_dense.argtypes = [vp, i32, C.POINTER(vp), vp]
+    lib.dppo_unet_plan_side.argtypes = [vp, C.POINTER(vp), vp]
+    for name in ("dppo_unet_plan_create", "dppo_unet_plan_destroy", "dppo_unet_plan_info", "dppo_unet_plan_layers",
+                 "dppo_unet_plan_dense", "dppo_unet_plan_side"):
+        getattr(lib, name).restype = i32
     lib.dppo_sample_chain.argtypes = [vp, vp, i32, vp, u64, u64, i64, i32, i32, f32, vp, vp, vp]
     lib.dppo_chain_logprobs.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.dppo_logprob_rows.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "internal.h"
+#include "unet_plan.h"
 
 namespace dppo {
 
@@ -26,6 +27,11 @@ int pack_mlp_impl(dppo_ctx* ctx, int which, const float* const* p, int n_params,
 int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
                       int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
                       const float* chains_in, float* logp, cudaStream_t st);
+
+int pack_unet_impl(dppo_ctx* ctx, int which, const float* const* p, int n_params, cudaStream_t st);
+int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
+                           int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
+                           const float* chains_in, float* logp, cudaStream_t st);
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -117,18 +123,20 @@ static int build_geometry(dppo_ctx* c) {
 using namespace dppo;
 
 extern "C" const char* dppo_last_error(void) { return g_err; }
-extern "C" int dppo_version(void) { return 100; }
+extern "C" int dppo_version(void) { return 101; }
 
-extern "C" int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const dppo_sched_desc* s, int precision,
-                               int device) {
-  if (!out || !actor || !s) return set_error("dppo_ctx_create: null argument"), DPPO_ERR_INVALID;
+// schedule + geometry + device allocations shared by the two denoiser kinds
+static int ctx_create_common(dppo_ctx** out, const dppo_mlp_desc* mlp, const dppo_unet_desc* unet, const dppo_sched_desc* s,
+                             int precision, int device) {
+  if (!out || (!mlp && !unet) || !s) return set_error("dppo_ctx_create: null argument"), DPPO_ERR_INVALID;
   if (precision != DPPO_PRECISION_SPLIT3 && precision != DPPO_PRECISION_BF16)
     return set_error("dppo_ctx_create: unknown precision %d", precision), DPPO_ERR_INVALID;
   DPPO_CUDA(cudaSetDevice(device));
   dppo_ctx* c = new dppo_ctx();
   c->device = device;
   c->precision = precision;
-  c->net = *actor;
+  c->kind = unet ? 1 : 0;
+  if (mlp) c->net = *mlp;
   c->K = s->denoising_steps;
   c->ft = s->ft_denoising_steps;
   c->use_ddim = s->use_ddim;
@@ -148,6 +156,9 @@ extern "C" int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const
              (s->use_ddim && (!s->ddim_t || !s->ddim_alphas || !s->ddim_alphas_prev || !s->ddim_sqrt_one_minus_alphas))) {
     set_error("dppo_ctx_create: missing schedule table");
     rc = DPPO_ERR_INVALID;
+  } else if (unet) {
+    c->unet = new UnetPlan();
+    rc = unet_build_plan(*unet, c->K, precision, c->unet);
   } else {
     rc = build_geometry(c);
   }
@@ -158,9 +169,24 @@ extern "C" int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const
       c->sm_count = dev_sms;
     cudaError_t e = cudaMalloc(&c->d_rows, sizeof(StepRow) * c->S);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_rows, c->rows.data(), sizeof(StepRow) * c->S, cudaMemcpyHostToDevice);
+    const size_t blob = unet ? c->unet->n_tiles * 16384 : c->g.blob_bytes;
+    const size_t n_side = unet ? c->unet->n_side : c->g.n_side;
     for (int w = 0; w < 2 && e == cudaSuccess; ++w) {
-      e = cudaMalloc(&c->nets[w].tiles, c->g.blob_bytes);
-      if (e == cudaSuccess) e = cudaMalloc(&c->nets[w].side, c->g.n_side * sizeof(float));
+      e = cudaMalloc(&c->nets[w].tiles, blob);
+      if (e == cudaSuccess) e = cudaMalloc(&c->nets[w].side, n_side * sizeof(float));
+      if (e == cudaSuccess && unet) e = cudaMalloc(&c->d_unet_params[w], sizeof(float*) * c->unet->n_params);
+    }
+    if (e == cudaSuccess && unet) {
+      const UnetPlan& P = *c->unet;
+      auto upload = [&](auto** dst, const auto& vec) {
+        using T = typename std::remove_reference<decltype(vec)>::type::value_type;
+        cudaError_t r = cudaMalloc(reinterpret_cast<void**>(dst), sizeof(T) * vec.size());
+        if (r == cudaSuccess) r = cudaMemcpy(*dst, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice);
+        return r;
+      };
+      e = upload(&c->d_unet_jobs, P.jobs);
+      if (e == cudaSuccess) e = upload(&c->d_unet_side_jobs, P.side_jobs);
+      if (e == cudaSuccess) e = upload(&c->d_unet_layers, P.layers);
     }
     if (e != cudaSuccess) rc = cuda_fail(e, "dppo_ctx_create allocation");
   }
@@ -172,13 +198,37 @@ extern "C" int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const
   return DPPO_OK;
 }
 
+extern "C" int dppo_ctx_create(dppo_ctx** out, const dppo_mlp_desc* actor, const dppo_sched_desc* s, int precision,
+                               int device) {
+  if (!actor) return set_error("dppo_ctx_create: null argument"), DPPO_ERR_INVALID;
+  return ctx_create_common(out, actor, nullptr, s, precision, device);
+}
+
+extern "C" int dppo_ctx_create_unet(dppo_ctx** out, const dppo_unet_desc* actor, const dppo_sched_desc* s, int precision,
+                                    int device) {
+  if (!actor) return set_error("dppo_ctx_create_unet: null argument"), DPPO_ERR_INVALID;
+  return ctx_create_common(out, nullptr, actor, s, precision, device);
+}
+
+extern "C" int dppo_unet_param_count(const dppo_unet_desc* actor) {
+  if (!actor) return set_error("dppo_unet_param_count: null argument"), DPPO_ERR_INVALID;
+  UnetPlan P;
+  const int rc = unet_build_plan(*actor, 1, DPPO_PRECISION_SPLIT3, &P);
+  return rc == DPPO_OK ? P.n_params : rc;
+}
+
 extern "C" int dppo_ctx_destroy(dppo_ctx* c) {
   if (!c) return DPPO_OK;
   cudaFree(c->d_rows);
   for (int w = 0; w < 2; ++w) {
     cudaFree(c->nets[w].tiles);
     cudaFree(c->nets[w].side);
+    cudaFree(c->d_unet_params[w]);
   }
+  cudaFree(c->d_unet_jobs);
+  cudaFree(c->d_unet_side_jobs);
+  cudaFree(c->d_unet_layers);
+  delete c->unet;
   delete c;
   return DPPO_OK;
 }
@@ -188,7 +238,17 @@ extern "C" int dppo_pack_mlp(dppo_ctx* ctx, int which, const float* const* param
   if (which != DPPO_NET_ACTOR && which != DPPO_NET_ACTOR_FT) return set_error("dppo_pack_mlp: which=%d", which), DPPO_ERR_INVALID;
   for (int i = 0; i < n_params; ++i)
     if (!params[i]) return set_error("dppo_pack_mlp: parameter %d is null", i), DPPO_ERR_INVALID;
+  if (ctx->kind != 0) return set_error("dppo_pack_mlp: the context was created for a Unet1D denoiser"), DPPO_ERR_STATE;
   return pack_mlp_impl(ctx, which, params, n_params, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dppo_pack_unet(dppo_ctx* ctx, int which, const float* const* params, int n_params, void* stream) {
+  if (!ctx || !params) return set_error("dppo_pack_unet: null argument"), DPPO_ERR_INVALID;
+  if (which != DPPO_NET_ACTOR && which != DPPO_NET_ACTOR_FT) return set_error("dppo_pack_unet: which=%d", which), DPPO_ERR_INVALID;
+  if (ctx->kind != 1) return set_error("dppo_pack_unet: the context was created for a DiffusionMLP denoiser"), DPPO_ERR_STATE;
+  for (int i = 0; i < n_params; ++i)
+    if (!params[i]) return set_error("dppo_pack_unet: parameter %d is null", i), DPPO_ERR_INVALID;
+  return pack_unet_impl(ctx, which, params, n_params, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, const float* noise, uint64_t seed,
@@ -198,9 +258,10 @@ extern "C" int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, 
   if (n_envs < 0) return set_error("dppo_sample_chain: n_envs=%d", n_envs), DPPO_ERR_INVALID;
   if (n_envs == 0) return DPPO_OK;
   if (!ctx->nets[0].packed || (!use_base_policy && !ctx->nets[1].packed))
-    return set_error("dppo_sample_chain: weights not packed (call dppo_pack_mlp for actor and actor_ft)"), DPPO_ERR_STATE;
-  return sample_chain_impl(ctx, state, n_envs, noise, seed, offset, env_offset, deterministic, use_base_policy, min_std,
-                           traj, chain, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    return set_error("dppo_sample_chain: weights not packed (call dppo_pack_mlp / dppo_pack_unet for actor and actor_ft)"), DPPO_ERR_STATE;
+  return (ctx->kind == 1 ? sample_chain_unet_impl : sample_chain_impl)(
+      ctx, state, n_envs, noise, seed, offset, env_offset, deterministic, use_base_policy, min_std, traj, chain, nullptr,
+      nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const float* chains, int n_rows,
@@ -210,8 +271,9 @@ extern "C" int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const floa
   if (n_rows == 0 || ctx->ft == 0) return DPPO_OK;
   if (!ctx->nets[use_base_policy ? 0 : 1].packed)
     return set_error("dppo_chain_logprobs: weights not packed"), DPPO_ERR_STATE;
-  return sample_chain_impl(ctx, state, n_rows, nullptr, 0, 0, 0, 0, use_base_policy, ctx->min_logprob_std, nullptr,
-                           nullptr, chains, logp, static_cast<cudaStream_t>(stream));
+  return (ctx->kind == 1 ? sample_chain_unet_impl : sample_chain_impl)(
+      ctx, state, n_rows, nullptr, 0, 0, 0, 0, use_base_policy, ctx->min_logprob_std, nullptr, nullptr, chains, logp,
+      static_cast<cudaStream_t>(stream));
 }
 
 // bring-up hook (not in the public header): the chain kernel writes 8 cycle counters per CTA into `buf`

@@ -1,0 +1,548 @@
+// Persistent denoise-chain kernel for the Unet1D denoiser (sm_100a: tcgen05.mma + TMEM + bulk TMA copies).
+//
+// Replaces, for one tile of NE environments per CTA and ALL S denoising steps in one launch:
+//   VPGDiffusion.forward / p_mean_var / get_logprobs   reference dppo/model/diffusion/diffusion_vpg.py:139-396
+//   Unet1D.forward + ResidualBlock1D                    reference dppo/model/diffusion/unet.py:27-118,267-327
+//   Conv1dBlock / Downsample1d / Upsample1d             reference dppo/model/diffusion/modules.py:30-95
+//
+// The network arrives as a program of dense layers (unet_plan.h): every conv over the short action horizon was
+// lowered at pack time to the banded block-Toeplitz matrix it is.  Per layer: 1-2 swap-AB GEMMs (weights = MMA A
+// operand streamed from L2 through a ring of 16 KiB pre-swizzled tiles, activations of the NE environments = B operand
+// resident in shared memory as bf16 hi [+ lo]) accumulate into TMEM, then the epilogue warps apply bias, GroupNorm
+// (a group is a run of <= 32 consecutive features = TMEM lanes of one warp: shuffle reductions, no shared memory),
+// activation, FiLM (scale / bias per channel from this block's conditioning encoder, kept in a small fp32 buffer) and
+// the residual, and write the next operand.  Same warp roles and barrier protocol as chain_mlp.cu.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "internal.h"
+#include "unet_plan.h"
+
+namespace dppo {
+
+namespace {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr uint32_t kTile = 16384;
+constexpr int kMaxStages = 10;
+
+struct UArgs {
+  int D, Da, Ta, Dc, nsplit, nstage;
+  int n_layers;
+  const ULayer* layers;
+  uint32_t n_step_tiles;
+  const uint8_t* tiles[2];
+  const float* side[2];
+  int chunk_x, chunk_state, chunk_state_act, KS, total_chunks, film_dim;
+  // schedule
+  const StepRow* rows;
+  int S, ft, first_step, eval_mode, use_ddim;
+  int deterministic, use_base;
+  float min_std, x0_clip, randn_clip, final_clip, eps_clip;
+  // io
+  const float* state;
+  int E;
+  const float* noise;
+  float* traj;
+  float* chain;
+  const float* chains_in;
+  float* logp;
+  uint64_t seed, offset;
+  int64_t env_offset;
+};
+
+// Philox4x32-10 keyed exactly like chain_mlp.cu (same draws for the same (seed, offset, element, slot))
+__device__ __forceinline__ float philox_normal_u(uint64_t seed, uint64_t offset, uint64_t elem, uint32_t slot) {
+  uint32_t c0 = uint32_t(elem), c1 = uint32_t(elem >> 32), c2 = slot, c3 = uint32_t(offset);
+  uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32) ^ uint32_t(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+  const float u1 = (float(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (float(c1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_f(float x) {
+  if (ACT == DPPO_ACT_RELU) return fmaxf(x, 0.f);
+  return mish_f(x);
+}
+
+struct USmem {
+  uint8_t *op_hi, *op_lo, *ring;
+  float *film, *eps;
+  uint64_t *full, *empty, *layer_done, *x_full;
+  uint32_t* tmem_slot;
+};
+
+__host__ __device__ inline size_t usmem_fixed_bytes(int NE, int total_chunks, int nsplit, int film_dim, int D) {
+  const size_t op = size_t(total_chunks) * NE * 128 * nsplit;
+  const size_t film = (size_t(NE) * film_dim * 4 + 127) & ~size_t(127);
+  const size_t eps = (size_t(NE) * D * 4 + 127) & ~size_t(127);
+  return op + film + eps + 16 * kMaxStages + 64 + 1024 /* alignment slack */;
+}
+
+template <int NE>
+__device__ __forceinline__ USmem ucarve(uint8_t* base, const UArgs& a) {
+  USmem s;
+  const size_t opb = size_t(a.total_chunks) * NE * 128;
+  uint8_t* p = base;
+  s.op_hi = p, p += opb;
+  s.op_lo = p, p += (a.nsplit == 2 ? opb : 0);
+  s.ring = p, p += size_t(a.nstage) * kTile;
+  s.film = reinterpret_cast<float*>(p), p += (size_t(NE) * a.film_dim * 4 + 127) & ~size_t(127);
+  s.eps = reinterpret_cast<float*>(p), p += (size_t(NE) * a.D * 4 + 127) & ~size_t(127);
+  s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
+  s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
+  s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+  return s;
+}
+
+// ============================================================================================== the kernel
+template <int NE, int ACT>
+__global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) {
+  constexpr int CPT = NE / 2;  // accumulator columns (environments) per epilogue thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const USmem s = ucarve<NE>(smem, a);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = a.nsplit == 2;
+  const int env0 = blockIdx.x * NE;
+  constexpr uint32_t kChunk = NE * 128u;  // bytes of one 64-feature operand chunk (one half)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.nstage; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.layer_done, 1);
+    mbar_init(s.x_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+
+  if (warp == 0) {
+    // ======================================================================================= weight-tile producer
+    // the per-step tile stream is the whole packed network in program order
+    uint32_t stage = 0, phase = 0;
+    for (int step = a.first_step; step < a.S; ++step) {
+      const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
+      const uint8_t* src = a.tiles[net];
+      for (uint32_t i = 0; i < a.n_step_tiles; ++i) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&s.full[stage], kTile);
+          bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
+        }
+        __syncwarp();
+        if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, NE);
+    uint32_t stage = 0, phase = 0, xr_phase = 0;
+    const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
+    const uint32_t op_hi = umma_desc_lo(smem_u32(s.op_hi)), op_lo = umma_desc_lo(smem_u32(s.op_lo));
+    for (int step = a.first_step; step < a.S; ++step) {
+      for (int li = 0; li < a.n_layers; ++li) {
+        const ULayer* L = a.layers + li;
+        const int n_gemm = L->n_gemm;
+        mbar_wait(s.x_full, xr_phase);
+        xr_phase ^= 1;
+        tc_fence_after();
+        for (int gi = 0; gi < n_gemm; ++gi) {
+          const UGemm G = L->g[gi];
+          for (int mt = 0; mt < int(G.mt); ++mt) {
+            const uint32_t d = tmem + uint32_t(G.acc_tile + mt) * NE;
+            for (int kc = 0; kc < int(G.kc); ++kc) {
+              const uint32_t chunk = kc < int(G.src_n[0]) ? uint32_t(G.src_chunk[0]) + kc
+                                                          : uint32_t(G.src_chunk[1]) + (kc - int(G.src_n[0]));
+              const uint32_t boff = chunk * (kChunk / 16);
+              const uint32_t bh = op_hi + boff, bl = op_lo + boff;
+              mbar_wait(&s.full[stage], phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t wa = ring_lo + stage * (kTile / 16);
+                if (kc > 0) {
+                  umma_bf16_lo(d, wa, bh, idesc, true);
+                } else {
+                  umma_bf16_lo(d, wa, bh, idesc, false);
+                }
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + 2 * k, idesc, true);
+                if (split) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bl + 2 * k, idesc, true);
+                }
+                umma_commit(&s.empty[stage]);
+              }
+              __syncwarp();
+              if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+              if (split) {
+                mbar_wait(&s.full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint32_t wa = ring_lo + stage * (kTile / 16);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + 2 * k, idesc, true);
+                  umma_commit(&s.empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+              }
+            }
+          }
+        }
+        if (elect_one()) umma_commit(s.layer_done);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================================================================================= epilogue warps
+    const int et = threadIdx.x - 64;   // 0..255
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the NE columns
+    const int fl = q * 32 + lane;      // feature (TMEM lane) within an m-tile
+    const int col0 = half * CPT;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t odd = lane & 1;
+    uint32_t ld_phase = 0;
+    float xreg[CPT];
+    const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
+
+    auto wait_layer = [&]() {
+      mbar_wait(s.layer_done, ld_phase);
+      ld_phase ^= 1;
+      tc_fence_after();
+    };
+    auto signal_x = [&]() {
+      tc_fence_before();
+      fence_proxy_async_smem();
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) mbar_arrive(s.x_full);
+    };
+    // operand store of one value (prologue / posterior; the layer epilogues use packed pairs)
+    auto store_op = [&](int chunk0, int row, int k, float v) {
+      const uint32_t off = uint32_t(chunk0) * kChunk + sw128_offset(uint32_t(row), uint32_t(k), NE);
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      *reinterpret_cast<__nv_bfloat16*>(s.op_hi + off) = h;
+      if (split) *reinterpret_cast<__nv_bfloat16*>(s.op_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+    };
+    // flat sample index (t * Da + d, the reference's (Ta, Da) layout) -> channel-major operand feature d * Ta + t
+    auto x_feature = [&](int f) { return (f % a.Da) * a.Ta + f / a.Da; };
+
+    // ------------------------------------------------------------------------------------ prologue
+    {
+      const uint32_t op_bytes = uint32_t(a.total_chunks) * kChunk;
+      for (uint32_t i = et * 16; i < op_bytes; i += kEpiThreads * 16) {
+        *reinterpret_cast<uint4*>(s.op_hi + i) = make_uint4(0, 0, 0, 0);
+        if (split) *reinterpret_cast<uint4*>(s.op_lo + i) = make_uint4(0, 0, 0, 0);
+      }
+      named_bar_sync(1, kEpiThreads);
+      for (int i = et; i < NE * a.Dc; i += kEpiThreads) {
+        const int e = i / a.Dc, k = i % a.Dc;
+        const int env = env0 + e;
+        const float v = env < a.E ? a.state[size_t(env) * a.Dc + k] : 0.f;
+        store_op(a.chunk_state, e, k, v);
+        if (a.chunk_state_act >= 0) store_op(a.chunk_state_act, e, k, act_f<ACT>(v));
+      }
+#pragma unroll 1
+      for (int j = 0; j < CPT; ++j) {
+        const int i = et + j * kEpiThreads;
+        float x = 0.f;
+        if (i < nxe) {
+          const int e = i / a.D, f = i - e * a.D;
+          const int env = env0 + e;
+          if (env < a.E) {
+            if (a.eval_mode)
+              x = a.chains_in[(size_t(env) * (a.ft + 1)) * a.D + f];
+            else if (a.noise)
+              x = a.noise[size_t(env) * a.D + f];
+            else
+              x = philox_normal_u(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, 0u);
+            if (!a.eval_mode && a.chain && a.ft == a.S) a.chain[(size_t(env) * (a.ft + 1)) * a.D + f] = x;
+          }
+          store_op(a.chunk_x, e, x_feature(f), x);
+        }
+        xreg[j] = x;
+      }
+      signal_x();
+    }
+
+    // ------------------------------------------------------------------------------------ step loop
+    for (int step = a.first_step; step < a.S; ++step) {
+      const StepRow row = a.rows[step];
+      const int net = (row.ft && !a.use_base) ? 1 : 0;
+      const float* side = a.side[net];
+      for (int li = 0; li < a.n_layers; ++li) {
+        const ULayer* L = a.layers + li;
+        const int kind = L->kind, acc_tile = L->acc_tile, MTl = L->mt, nf = L->nf;
+        const float* bias = side + L->bias_off + size_t(L->bias_tstride) * row.t;
+        wait_layer();
+        if (kind == U_EPI_OPERAND) {
+          const int gs = L->gn_size, do_act = L->act, film = L->film, film_c = L->film_c, tshift = L->film_tshift;
+          const int res = L->res;
+          const float* gamma = side + L->gamma_off;
+          const float* beta = side + L->beta_off;
+          const float gn_eps = L->gn_eps;
+          const float* res_bias = side + L->res_bias_off;
+          const uint32_t dst_base = uint32_t(L->dst_chunk) * kChunk;
+          const uint32_t res_base = uint32_t(res == U_RES_SLOT ? L->res_chunk : 0) * kChunk;
+          const uint32_t res_tile = uint32_t(L->res_acc_tile);
+          for (int mt = 0; mt < MTl; ++mt) {
+            float v[CPT];
+            tmem_ld(tmem + lane_addr + uint32_t(acc_tile + mt) * NE + col0, v);
+            const int f = mt * 128 + fl;
+            const float b = bias[f];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) v[c] += b;
+            if (gs) {
+              // GroupNorm over gs consecutive features (lanes) of each environment column: mean, then centred variance
+              const float inv = 1.f / float(gs), g = gamma[f], be = beta[f];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) {
+                float sm = v[c];
+                for (int o = gs >> 1; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                const float dlt = v[c] - sm * inv;
+                float sq = dlt * dlt;
+                for (int o = gs >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                v[c] = dlt * rsqrtf(sq * inv + gn_eps) * g + be;
+              }
+            }
+            if (do_act) {
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) v[c] = act_f<ACT>(v[c]);
+            }
+            if (film && f < nf) {
+              const float* fr = s.film + size_t(col0) * a.film_dim + (f >> tshift);
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) {
+                const float* fe = fr + size_t(c) * a.film_dim;
+                v[c] = film == 2 ? fe[0] * v[c] + fe[film_c] : v[c] + fe[0];
+              }
+            }
+            if (res == U_RES_ACC) {
+              float r[CPT];
+              tmem_ld(tmem + lane_addr + (res_tile + uint32_t(mt)) * NE + col0, r);
+              const float rb = res_bias[f];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) v[c] += r[c] + rb;
+            }
+            if (f >= nf) {
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) v[c] = 0.f;
+            }
+            // neighbouring lanes swap one value per column pair: every thread then owns two consecutive features of one
+            // environment row -> one packed bf16x2 convert and one 4-byte store per operand half
+            const uint32_t kp = uint32_t(f) & ~1u;
+            const uint32_t j16 = (kp & 63u) >> 3;
+            const uint32_t rel = (kp >> 6) * kChunk + ((kp & 7u) << 1) + (uint32_t(col0) + odd) * 128u;
+#pragma unroll
+            for (int c = 0; c < CPT; c += 2) {
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[c] : v[c + 1], 1);
+              float fa = odd ? recv : v[c], fb = odd ? v[c + 1] : recv;  // features kp, kp + 1 of env row col0 + c + odd
+              const uint32_t off = rel + uint32_t(c) * 128u + ((j16 ^ ((uint32_t(c) + odd) & 7u)) << 4);
+              if (res == U_RES_SLOT) {
+                const __nv_bfloat162 rh = *reinterpret_cast<const __nv_bfloat162*>(s.op_hi + res_base + off);
+                fa += __low2float(rh), fb += __high2float(rh);
+                if (split) {
+                  const __nv_bfloat162 rl = *reinterpret_cast<const __nv_bfloat162*>(s.op_lo + res_base + off);
+                  fa += __low2float(rl), fb += __high2float(rl);
+                }
+              }
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(fa, fb);
+              *reinterpret_cast<__nv_bfloat162*>(s.op_hi + dst_base + off) = h2;
+              if (split)
+                *reinterpret_cast<__nv_bfloat162*>(s.op_lo + dst_base + off) =
+                    __floats2bfloat162_rn(fa - __low2float(h2), fb - __high2float(h2));
+            }
+          }
+        } else if (kind == U_EPI_FILM) {
+          for (int mt = 0; mt < MTl; ++mt) {
+            float v[CPT];
+            tmem_ld(tmem + lane_addr + uint32_t(acc_tile + mt) * NE + col0, v);
+            const int f = mt * 128 + fl;
+            if (f < nf) {
+              const float b = bias[f];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) s.film[size_t(col0 + c) * a.film_dim + f] = v[c] + b;
+            }
+          }
+        } else {
+          // output layer + posterior (diffusion_vpg.py:165-224, 279-311): eps -> [env][flat element] fp32 tile, then all
+          // epilogue threads run the element-wise update on the flat mapping (coalesced global access)
+          if (q * 32 < a.D) {
+            float v[CPT];
+            tmem_ld(tmem + lane_addr + uint32_t(acc_tile) * NE + col0, v);
+            if (fl < a.D) {
+              const float bo = bias[fl];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) s.eps[(col0 + c) * a.D + fl] = v[c] + bo;
+            }
+          }
+          named_bar_sync(1, kEpiThreads);
+          const bool last = step == a.S - 1;
+          const int d_eval = step - a.first_step;
+          float stdv, f2 = row.f2, f3 = row.f3;
+          if (a.eval_mode) {
+            stdv = fmaxf(row.std_train, a.min_std);
+          } else if (a.deterministic) {
+            f2 = row.f2_det, f3 = row.f3_det;
+            stdv = a.use_ddim ? 0.f : (row.t == 0 ? 0.f : fmaxf(row.std_train, 1e-3f));
+          } else {
+            stdv = fmaxf(row.std_train, a.min_std);
+          }
+          const float inv_2var = 1.f / (2.f * (stdv * stdv)), log_std = logf(stdv);
+#pragma unroll 1
+          for (int j = 0; j < CPT; ++j) {
+            const int i = et + j * kEpiThreads;
+            if (i >= nxe) break;
+            const int e = i / a.D, f = i - e * a.D;
+            const int env = env0 + e;
+            float eps = s.eps[i];
+            const float x = xreg[j];
+            float x0, mu;
+            if (!a.use_ddim) {
+              x0 = row.f0 * x - row.f1 * eps;
+              if (a.x0_clip >= 0.f) x0 = fminf(fmaxf(x0, -a.x0_clip), a.x0_clip);
+              mu = f2 * x0 + f3 * x;
+            } else {
+              x0 = (x - row.f1 * eps) / row.f0;
+              if (a.x0_clip >= 0.f) {
+                x0 = fminf(fmaxf(x0, -a.x0_clip), a.x0_clip);
+                eps = (x - row.f0 * x0) / row.f1;
+              }
+              if (a.eps_clip >= 0.f) eps = fminf(fmaxf(eps, -a.eps_clip), a.eps_clip);
+              mu = f2 * x0 + f3 * eps;
+            }
+            float xn = 0.f;
+            if (env < a.E) {
+              if (a.eval_mode) {
+                xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + f];
+                const float diff = xn - mu;
+                a.logp[(size_t(env) * a.ft + d_eval) * a.D + f] = -(diff * diff) * inv_2var - log_std - 0.91893853320467274f;
+              } else {
+                float z;
+                if (a.noise)
+                  z = a.noise[(size_t(step + 1) * a.E + env) * a.D + f];
+                else
+                  z = philox_normal_u(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, uint32_t(step + 1));
+                z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
+                xn = mu + stdv * z;
+                if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
+                if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
+                if (last) a.traj[size_t(env) * a.D + f] = xn;
+              }
+            }
+            xreg[j] = xn;
+            store_op(a.chunk_x, e, x_feature(f), xn);
+          }
+        }
+        signal_x();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int NE, int ACT>
+int ulaunch(const UArgs& a, size_t smem_bytes, cudaStream_t st) {
+  auto kfn = chain_unet_kernel<NE, ACT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(chain_unet_kernel)");
+    configured = true;
+  }
+  const int tiles = (a.E + NE - 1) / NE;
+  chain_unet_kernel<NE, ACT><<<tiles, kThreads, smem_bytes, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "chain_unet_kernel launch");
+  return DPPO_OK;
+}
+
+}  // namespace
+
+// Tile size: the kernel is bound by the weight ingest of one SM (the whole lowered net, every step, whatever NE is),
+// so the smallest tile that still fits every environment in one wave wins; larger tiles only when E needs them.
+static int pick_unet_tile(const dppo_ctx* ctx, int E, int* nstage_out) {
+  const UnetPlan& P = *ctx->unet;
+  static int env_ne = -1;
+  if (env_ne < 0) {
+    const char* e = getenv("DPPO_B200_TILE_ENVS");
+    env_ne = e ? atoi(e) : 0;
+  }
+  const int forced = ctx->force_ne ? ctx->force_ne : env_ne;
+  const size_t budget = 232448;
+  int best = 0, best_stage = 0;
+  double best_t = 1e30;
+  for (int NE = 16; NE <= 64; NE *= 2) {
+    if (forced > 0 && NE != forced) continue;
+    if (2 * P.MTmax * NE > 512) continue;
+    const size_t fixed = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D);
+    if (fixed + 2 * kTile > budget) continue;
+    int nstage = int((budget - fixed) / kTile);
+    if (nstage > kMaxStages) nstage = kMaxStages;
+    const int tiles = (E + NE - 1) / NE;
+    const int waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
+    const double ingest = double(P.n_tiles) * 16384.0 / (nstage >= 3 ? 34.7 : 20.0);
+    const double epi = double(P.layers.size()) * (double(NE) * P.MTmax * 128 / 256.0 * 37.0 + 1500.0);
+    const double t = waves * (ingest + epi);
+    if (t < best_t) best_t = t, best = NE, best_stage = nstage;
+  }
+  *nstage_out = best_stage;
+  return best;
+}
+
+int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
+                           int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
+                           const float* chains_in, float* logp, cudaStream_t st) {
+  const UnetPlan& P = *ctx->unet;
+  UArgs a{};
+  a.D = P.D, a.Da = P.d.action_dim, a.Ta = P.d.horizon_steps, a.Dc = P.d.cond_dim, a.nsplit = P.nsplit;
+  a.n_layers = int(P.layers.size()), a.layers = ctx->d_unet_layers, a.n_step_tiles = uint32_t(P.n_tiles);
+  for (int w = 0; w < 2; ++w) a.tiles[w] = ctx->nets[w].tiles, a.side[w] = ctx->nets[w].side;
+  a.chunk_x = P.chunk_x, a.chunk_state = P.chunk_state, a.chunk_state_act = P.chunk_state_act, a.KS = P.KS;
+  a.total_chunks = P.total_chunks, a.film_dim = P.film_dim;
+  a.rows = ctx->d_rows, a.S = ctx->S, a.ft = ctx->ft, a.use_ddim = ctx->use_ddim;
+  a.eval_mode = chains_in != nullptr;
+  a.first_step = a.eval_mode ? ctx->S - ctx->ft : 0;
+  a.deterministic = deterministic, a.use_base = use_base;
+  a.min_std = min_std, a.x0_clip = ctx->x0_clip, a.randn_clip = ctx->randn_clip, a.final_clip = ctx->final_clip;
+  a.eps_clip = ctx->eps_clip;
+  a.state = state, a.E = E, a.noise = noise, a.traj = traj, a.chain = chain, a.chains_in = chains_in, a.logp = logp;
+  a.seed = seed, a.offset = offset, a.env_offset = env_offset;
+
+  int nstage = 0;
+  const int NE = pick_unet_tile(ctx, E, &nstage);
+  if (NE == 0) return set_error("unet chain kernel: no tile size fits this geometry in shared memory / TMEM"), DPPO_ERR_UNSUPPORTED;
+  a.nstage = nstage;
+  const size_t smem_bytes = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D) + size_t(nstage) * kTile;
+#define DPPO_ULAUNCH(NE_) \
+  (P.d.activation == DPPO_ACT_RELU ? ulaunch<NE_, DPPO_ACT_RELU>(a, smem_bytes, st) : ulaunch<NE_, DPPO_ACT_MISH>(a, smem_bytes, st))
+  if (NE == 64) return DPPO_ULAUNCH(64);
+  if (NE == 32) return DPPO_ULAUNCH(32);
+  return DPPO_ULAUNCH(16);
+#undef DPPO_ULAUNCH
+}
+
+}  // namespace dppo

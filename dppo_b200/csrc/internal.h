@@ -54,6 +54,11 @@ struct MlpGeom {
   size_t blob_bytes;
 };
 
+struct UnetPlan;
+struct UPackJob;
+struct USideJob;
+struct ULayer;
+
 struct PackedNet {
   uint8_t* tiles = nullptr;  // device
   float* side = nullptr;     // device
@@ -74,6 +79,13 @@ struct dppo_ctx {
   std::vector<dppo::StepRow> rows;        // host copy, S rows
   dppo::StepRow* d_rows = nullptr;        // device copy
   dppo::PackedNet nets[2];
+  // Unet1D denoiser (kind == 1): host plan + its device-side job / layer tables (unet_plan.h)
+  int kind = 0;  // 0 = DiffusionMLP, 1 = Unet1D
+  dppo::UnetPlan* unet = nullptr;
+  dppo::UPackJob* d_unet_jobs = nullptr;
+  dppo::USideJob* d_unet_side_jobs = nullptr;
+  dppo::ULayer* d_unet_layers = nullptr;
+  const float** d_unet_params[2] = {nullptr, nullptr};
   int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

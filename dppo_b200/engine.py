@@ -56,6 +56,74 @@ def mlp_desc_of(net):
     return d
 
 
+def _unet_param_list(net):
+    """Parameters of a Unet1D in the order dppo_pack_unet expects (include/dppo_b200.h): execution order."""
+    ps = [net.time_mlp[1].weight, net.time_mlp[1].bias, net.time_mlp[3].weight, net.time_mlp[3].bias]
+
+    def res(blk):
+        out = []
+        for cb in blk.blocks:
+            out += [cb.block[0].weight, cb.block[0].bias, cb.block[2].weight, cb.block[2].bias]
+        for m in blk.cond_encoder:
+            if isinstance(m, torch.nn.Linear):
+                out += [m.weight, m.bias]
+        if isinstance(blk.residual_conv, torch.nn.Conv1d):
+            out += [blk.residual_conv.weight, blk.residual_conv.bias]
+        return out
+
+    for r1, r2, down in net.down_modules:
+        ps += res(r1) + res(r2)
+        if hasattr(down, "conv"):
+            ps += [down.conv.weight, down.conv.bias]
+    for m in net.mid_modules:
+        ps += res(m)
+    for r1, r2, up in net.up_modules:
+        ps += res(r1) + res(r2)
+        if hasattr(up, "conv"):
+            ps += [up.conv.weight, up.conv.bias]
+    fc = net.final_conv
+    ps += [fc[0].block[0].weight, fc[0].block[0].bias, fc[0].block[2].weight, fc[0].block[2].bias, fc[1].weight, fc[1].bias]
+    return ps
+
+
+def unet_desc_of(net, horizon_steps):
+    """dppo_unet_desc of a dppo_b200.model.diffusion.unet.Unet1D; raises for variants outside the kernel."""
+    if hasattr(net, "cond_mlp"):
+        raise NotImplementedError("unet chain kernel: cond_mlp_dims is not supported (no fine-tuning YAML sets it)")
+    blk = net.mid_modules[0]
+    conv0 = blk.blocks[0].block[0]
+    norm0 = blk.blocks[0].block[2]
+    if not isinstance(norm0, torch.nn.GroupNorm):
+        raise NotImplementedError("unet chain kernel: n_groups must be set (GroupNorm)")
+    act_mod = blk.blocks[0].block[4]
+    act = {"ReLU": _lib.ACT_RELU, "Mish": _lib.ACT_MISH}.get(type(act_mod).__name__)
+    if act is None:
+        raise NotImplementedError(f"unet chain kernel: activation {type(act_mod).__name__}")
+    d = _lib.UnetDesc()
+    first = net.down_modules[0][0]
+    d.action_dim = first.blocks[0].block[0].in_channels
+    d.horizon_steps = horizon_steps
+    d.time_dim = net.time_dim
+    n_lin = [m for m in blk.cond_encoder if isinstance(m, torch.nn.Linear)]
+    d.larger_encoder = int(len(n_lin) == 3)
+    d.cond_dim = n_lin[0].in_features - net.time_dim
+    widths = [lvl[0].out_channels for lvl in net.down_modules]
+    if len(widths) > _lib.UNET_MAX_LEVELS:
+        raise NotImplementedError(f"unet chain kernel: at most {_lib.UNET_MAX_LEVELS} levels")
+    d.dim = widths[0]
+    d.n_levels = len(widths)
+    for i, w in enumerate(widths):
+        if w % widths[0]:
+            raise NotImplementedError("unet chain kernel: level widths must be multiples of dim")
+        d.dim_mults[i] = w // widths[0]
+    d.kernel_size = conv0.kernel_size[0]
+    d.n_groups = norm0.num_groups
+    d.activation = act
+    d.cond_predict_scale = int(blk.cond_predict_scale)
+    d.groupnorm_eps = float(norm0.eps)
+    return d
+
+
 class ChainEngine:
     """One context per (model, device, precision)."""
 
@@ -69,7 +137,8 @@ class ChainEngine:
         self.ft = int(model.ft_denoising_steps)
         self.D = model.horizon_steps * model.action_dim
         self.S = int(model.ddim_steps) if model.use_ddim else int(model.denoising_steps)
-        desc = mlp_desc_of(model.actor)
+        self.is_unet = type(model.actor).__name__ == "Unet1D"
+        desc = unet_desc_of(model.actor, model.horizon_steps) if self.is_unet else mlp_desc_of(model.actor)
         sd = _lib.SchedDesc()
         sd.denoising_steps, sd.ft_denoising_steps = model.denoising_steps, self.ft
         sd.use_ddim, sd.ddim_steps = int(model.use_ddim), int(model.ddim_steps or 0)
@@ -102,8 +171,8 @@ class ChainEngine:
                 setattr(sd, name, host_f32(getattr(model, name)))
         self.ctx = C.c_void_p()
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        _lib.check(self.lib.dppo_ctx_create(C.byref(self.ctx), C.byref(desc), C.byref(sd), _lib.PRECISIONS[precision], idx),
-                   "dppo_ctx_create")
+        create = self.lib.dppo_ctx_create_unet if self.is_unet else self.lib.dppo_ctx_create
+        _lib.check(create(C.byref(self.ctx), C.byref(desc), C.byref(sd), _lib.PRECISIONS[precision], idx), "dppo_ctx_create")
         self._packed = {0: None, 1: None}
         self._ws = torch.zeros(32, dtype=torch.float64, device=dev)
 
@@ -122,7 +191,7 @@ class ChainEngine:
 
     # ------------------------------------------------------------------ weights
     def sync_weights(self, which, net):
-        ps = _mlp_param_list(net)
+        ps = _unet_param_list(net) if self.is_unet else _mlp_param_list(net)
         sig = tuple((id(p), p._version, p.data_ptr()) for p in ps)
         if self._packed[which] == sig:
             return False
@@ -130,7 +199,8 @@ class ChainEngine:
             if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
                 raise RuntimeError("dppo_pack_mlp needs contiguous fp32 CUDA parameters")
         arr = (C.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
-        _lib.check(self.lib.dppo_pack_mlp(self.ctx, which, arr, len(ps), _lib.stream_ptr()), "dppo_pack_mlp")
+        pack = self.lib.dppo_pack_unet if self.is_unet else self.lib.dppo_pack_mlp
+        _lib.check(pack(self.ctx, which, arr, len(ps), _lib.stream_ptr()), "dppo_pack_unet" if self.is_unet else "dppo_pack_mlp")
         self._packed[which] = sig
         return True
 

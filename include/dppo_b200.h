@@ -54,6 +54,24 @@ typedef struct dppo_mlp_desc {
   int32_t cond_out;      /* cond_mlp_dims[1] */
 } dppo_mlp_desc;
 
+/* Unet1D geometry (state conditioning, no cond_mlp).  reference dppo/model/diffusion/unet.py:121-265 */
+#define DPPO_UNET_MAX_LEVELS 4
+typedef struct dppo_unet_desc {
+  int32_t cond_dim;      /* To * Do, flattened observation (the FiLM conditioning vector is [time_mlp(t) | obs]) */
+  int32_t action_dim;    /* Da = input / output channels */
+  int32_t horizon_steps; /* Ta = sequence length; must be divisible by 2^(n_levels-1) */
+  int32_t time_dim;      /* diffusion_step_embed_dim e; time_mlp is Lin(e,4e) Mish Lin(4e,e) */
+  int32_t dim;           /* base channel width */
+  int32_t n_levels;      /* len(dim_mults) */
+  int32_t dim_mults[DPPO_UNET_MAX_LEVELS];
+  int32_t kernel_size;   /* odd; Conv1d(padding = k/2) */
+  int32_t n_groups;      /* GroupNorm groups */
+  int32_t activation;    /* DPPO_ACT_* */
+  int32_t cond_predict_scale; /* FiLM: 1 = scale and bias, 0 = bias only */
+  int32_t larger_encoder;     /* 1: Lin act Lin act Lin; 0: act Lin   (unet.py:66-84) */
+  float groupnorm_eps;
+} dppo_unet_desc;
+
 /* Schedule tables exactly as the reference builds them (fp32 tensors from the float64 cosine schedule).
  * reference dppo/model/diffusion/diffusion.py:98-148 (DDPM), :155-196 (DDIM, already flipped: index 0 = noisiest) */
 typedef struct dppo_sched_desc {
@@ -110,6 +128,25 @@ int dppo_ctx_destroy(dppo_ctx* ctx);
  *   per block b: l1.{weight,bias}, l2.{weight,bias}, [norm1.{weight,bias}, norm2.{weight,bias}],
  *   mlp_mean.layers.{n_blocks+1}.{weight,bias}                                                              */
 int dppo_pack_mlp(dppo_ctx* ctx, int which, const float* const* params, int n_params, void* stream);
+
+/* ---- Unet1D denoiser ------------------------------------------------------------------------------------------ */
+/* Same context type and the same dppo_sample_chain / dppo_chain_logprobs calls, with Unet1D.forward
+ * (unet.py:267-327) as the per-step network.  At pack time every Conv1d / ConvTranspose1d over the short action
+ * horizon is lowered to the dense map it is ([C_in*T_in] -> [C_out*T_out], a banded block-Toeplitz matrix), so the
+ * whole net becomes a program of tensor-core GEMMs with GroupNorm / Mish / FiLM / residual epilogues.              */
+int dppo_ctx_create_unet(dppo_ctx** out, const dppo_unet_desc* actor, const dppo_sched_desc* sched, int precision,
+                         int device);
+/* `params`: HOST array of DEVICE pointers, execution order:
+ *   time_mlp.1.{weight,bias}, time_mlp.3.{weight,bias};
+ *   residual blocks in execution order (down level l: 0, 1; mid 0, 1; up level l: 0, 1), each
+ *     blocks.0.block.0.{weight,bias}, blocks.0.block.2.{weight,bias}, blocks.1.block.0.{weight,bias},
+ *     blocks.1.block.2.{weight,bias}, cond_encoder Linear {weight,bias} x (3 | 1), [residual_conv.{weight,bias}];
+ *   with the Downsample1d conv {weight,bias} after a down level's two blocks (all but the last level) and the
+ *   Upsample1d conv {weight,bias} after an up level's two blocks;
+ *   final_conv.0.block.0.{weight,bias}, final_conv.0.block.2.{weight,bias}, final_conv.1.{weight,bias}.           */
+int dppo_pack_unet(dppo_ctx* ctx, int which, const float* const* params, int n_params, void* stream);
+/* number of parameter tensors dppo_pack_unet expects for this geometry (< 0: error) */
+int dppo_unet_param_count(const dppo_unet_desc* actor);
 
 /* ---- rollout: K-step denoising chain ------------------------------------------------------------------------- */
 /* Replaces VPGDiffusion.forward + p_mean_var (diffusion_vpg.py:139-315) and DiffusionMLP.forward

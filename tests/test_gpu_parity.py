@@ -13,6 +13,7 @@ from tests.helpers import GOLDEN_CASES, build_model, load_golden, make_inputs, o
 
 pytestmark = pytest.mark.gpu
 MLP_CASES = ["hopper", "walker2d", "transport_k20", "transport", "furniture", "furniture_ddpm100"]
+ALL_CASES = MLP_CASES + ["square_unet"]
 
 
 def rel_err(a, b):
@@ -68,7 +69,7 @@ def test_gae_matches_oracle():
         np.testing.assert_allclose(ret.cpu().numpy(), ret_o, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("case", MLP_CASES)
+@pytest.mark.parametrize("case", ALL_CASES)
 def test_chain_matches_reference(case):
     w, model, gold, inp = _setup(case)
     state, noise = inp["state"].cuda(), inp["noise"].cuda()
@@ -82,7 +83,7 @@ def test_chain_matches_reference(case):
     assert_close(out_d.trajectories.cpu().numpy(), gold["traj_det"], 1e-3, f"{case} trajectories (deterministic)", max_frac=2e-3)
 
 
-@pytest.mark.parametrize("case", MLP_CASES)
+@pytest.mark.parametrize("case", ALL_CASES)
 def test_chain_logprobs_match_reference(case):
     w, model, gold, inp = _setup(case)
     state = inp["state"].cuda()
@@ -94,7 +95,7 @@ def test_chain_logprobs_match_reference(case):
     assert_close(lp.cpu().numpy(), gold["logprobs"], 1e-3, f"{case} log-probs", max_frac=2e-3)
 
 
-@pytest.mark.parametrize("case", MLP_CASES)
+@pytest.mark.parametrize("case", ALL_CASES)
 def test_loss_and_gradients_match_reference(case):
     w, model, gold, inp = _setup(case)
     E, ft = GOLDEN_CASES[case]["n_envs"], w["ft_denoising_steps"]
@@ -177,6 +178,7 @@ def test_bf16_fast_mode_within_its_tolerance_report():
     ("hopper", 16, 1), ("hopper", 32, 2), ("hopper", 16, 4), ("hopper", 64, 4), ("walker2d", 64, 2), ("walker2d", 32, 4),
     ("transport_k20", 32, 2), ("transport_k20", 16, 8), ("transport", 32, 4),
     ("furniture", 16, 8), ("furniture", 32, 2), ("furniture_ddpm100", 16, 4),
+    ("square_unet", 16, 0), ("square_unet", 32, 0),
 ])
 def test_chain_and_logprobs_every_launch_shape(case, tile_envs, cluster):
     """Feature-split clusters (C CTAs share one env tile) and every tile size give the same chains / log-probs."""
