@@ -38,6 +38,12 @@ UNIT = "env-steps/s"
 def net_flops_per_sample(w):
     """Forward FLOPs of one denoiser evaluation (2 * MACs of every Linear), SURVEY.md §8 F_net."""
     a = w["actor"]
+    if a["kind"] == "unet":
+        # torch.utils.flop_counter on the reference Unet1D of cfg5 (SURVEY.md section 8: F_net = 5,359,104; convs counted
+        # as written, i.e. including the taps that fall into the zero padding)
+        if (a["dim"], tuple(a["dim_mults"]), a["kernel_size"], w["horizon_steps"], w["action_dim"]) != (64, (1, 2), 5, 4, 7):
+            raise NotImplementedError("F_net is tabulated for the cfg5 Unet1D only")
+        return 5359104
     D, cond = w["horizon_steps"] * w["action_dim"], w["obs_dim"] * w["cond_steps"]
     td, dims = a["time_dim"], a["mlp_dims"]
     macs = td * 2 * td + 2 * td * td
@@ -53,7 +59,8 @@ def net_flops_per_sample(w):
 
 def workload_name(w, E):
     kind = f"DDIM-{w['ddim_steps']}" if w["use_ddim"] else f"DDPM K={w['denoising_steps']}"
-    return (f"{w['yaml'].split('/')[2]} ft_ppo_diffusion_mlp, {E} synthetic envs, obs {w['obs_dim']}, act {w['action_dim']}, "
+    net = "unet" if w["actor"]["kind"] == "unet" else "mlp"
+    return (f"{w['yaml'].split('/')[2]} ft_ppo_diffusion_{net}, {E} synthetic envs, obs {w['obs_dim']}, act {w['action_dim']}, "
             f"Tp=Ta={w['horizon_steps']}, {kind}, ft={w['ft_denoising_steps']}")
 
 
@@ -248,7 +255,7 @@ def run_b200(args, w, E, rank, world, local_rank):
             "gpu_launches": args.steps,
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "chain_mlp_kernel",
+                         "traffic": traffic, "kernel": "chain_unet_kernel" if w["actor"]["kind"] == "unet" else "chain_mlp_kernel",
                          "note": ("algorithmic FLOPs S*F_net*E (1x); split3 issues 3 bf16 MMAs per logical MMA so frac <= 1/3; "
                                   "the kernel is bound by the per-SM L2->shared weight ingest (34.7 B/cycle/SM measured), "
                                   "see DESIGN.md section 3; traffic = ncu dram bytes per launch (bytes); "

@@ -163,6 +163,7 @@ static int ctx_create_common(dppo_ctx** out, const dppo_mlp_desc* mlp, const dpp
     rc = build_geometry(c);
   }
   if (rc == DPPO_OK) {
+    c->sample_dim = unet ? c->unet->D : c->g.D;
     build_rows(c, s);
     int dev_sms = 0;
     if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && dev_sms > 0)

@@ -12,6 +12,13 @@
 // (a group is a run of <= 32 consecutive features = TMEM lanes of one warp: shuffle reductions, no shared memory),
 // activation, FiLM (scale / bias per channel from this block's conditioning encoder, kept in a small fp32 buffer) and
 // the residual, and write the next operand.  Same warp roles and barrier protocol as chain_mlp.cu.
+//
+// Track-split CTA pairs (C = 2): the FiLM conditioning encoders (24 of the 44 layers of cfg5, 40 % of the weights)
+// depend on the timestep and the observation only, never on x.  A cluster of two CTAs shares one tile of environments:
+// rank 0 runs the main path (x -> eps -> posterior), rank 1 runs the encoders, up to two blocks ahead and across step
+// boundaries, and stores each block's (scale, bias) vectors straight into a double-buffered fp32 FiLM buffer in rank
+// 0's shared memory (st.shared::cluster + releasing remote mbarrier arrive).  Each CTA streams only its own track's
+// weights, so the per-SM weight ingest - the bound of this kernel family - is split between two SMs.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,9 +37,9 @@ constexpr int kMaxStages = 10;
 
 struct UArgs {
   int D, Da, Ta, Dc, nsplit, nstage;
+  int C;  // 1 = one CTA runs both tracks, 2 = track-split CTA pair
   int n_layers;
   const ULayer* layers;
-  uint32_t n_step_tiles;
   const uint8_t* tiles[2];
   const float* side[2];
   int chunk_x, chunk_state, chunk_state_act, KS, total_chunks, film_dim;
@@ -51,6 +58,7 @@ struct UArgs {
   float* logp;
   uint64_t seed, offset;
   int64_t env_offset;
+  unsigned long long* prof;  // optional [grid][16] cycle counters (bring-up / profiling), nullptr in production
 };
 
 // Philox4x32-10 keyed exactly like chain_mlp.cu (same draws for the same (seed, offset, element, slot))
@@ -79,15 +87,16 @@ __device__ __forceinline__ float act_f(float x) {
 struct USmem {
   uint8_t *op_hi, *op_lo, *ring;
   float *film, *eps;
-  uint64_t *full, *empty, *layer_done, *x_full;
+  uint64_t *full, *empty, *layer_done, *x_full, *film_full, *film_free;
   uint32_t* tmem_slot;
+  uint32_t film_stride;  // floats between the two FiLM buffers
 };
 
-__host__ __device__ inline size_t usmem_fixed_bytes(int NE, int total_chunks, int nsplit, int film_dim, int D) {
+__host__ __device__ inline size_t usmem_fixed_bytes(int NE, int total_chunks, int nsplit, int film_dim, int D, int C) {
   const size_t op = size_t(total_chunks) * NE * 128 * nsplit;
-  const size_t film = (size_t(NE) * film_dim * 4 + 127) & ~size_t(127);
+  const size_t film = C * ((size_t(NE) * film_dim * 4 + 127) & ~size_t(127));
   const size_t eps = (size_t(NE) * D * 4 + 127) & ~size_t(127);
-  return op + film + eps + 16 * kMaxStages + 64 + 1024 /* alignment slack */;
+  return op + film + eps + 16 * kMaxStages + 96 + 1024 /* alignment slack */;
 }
 
 template <int NE>
@@ -98,12 +107,16 @@ __device__ __forceinline__ USmem ucarve(uint8_t* base, const UArgs& a) {
   s.op_hi = p, p += opb;
   s.op_lo = p, p += (a.nsplit == 2 ? opb : 0);
   s.ring = p, p += size_t(a.nstage) * kTile;
-  s.film = reinterpret_cast<float*>(p), p += (size_t(NE) * a.film_dim * 4 + 127) & ~size_t(127);
+  const size_t film_bytes = (size_t(NE) * a.film_dim * 4 + 127) & ~size_t(127);
+  s.film = reinterpret_cast<float*>(p), p += film_bytes * a.C;
+  s.film_stride = uint32_t(film_bytes / 4);
   s.eps = reinterpret_cast<float*>(p), p += (size_t(NE) * a.D * 4 + 127) & ~size_t(127);
   s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
   s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.film_full = reinterpret_cast<uint64_t*>(p), p += 16;
+  s.film_free = reinterpret_cast<uint64_t*>(p), p += 16;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p);
   return s;
 }
@@ -117,7 +130,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
   const USmem s = ucarve<NE>(smem, a);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = a.nsplit == 2;
-  const int env0 = blockIdx.x * NE;
+  const int C = a.C;
+  const int rank = C > 1 ? int(cluster_ctarank()) : 0;
+  const int my_track = C > 1 ? rank : -1;  // -1: this CTA runs every layer
+  const int env0 = (blockIdx.x / C) * NE;
   constexpr uint32_t kChunk = NE * 128u;  // bytes of one 64-feature operand chunk (one half)
 
   if (threadIdx.x == 0) {
@@ -127,46 +143,71 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     }
     mbar_init(s.layer_done, 1);
     mbar_init(s.x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.film_full[i], kEpiThreads);  // every epilogue thread of the encoder CTA arrives after its own stores
+      mbar_init(&s.film_free[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (C > 1) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   const uint32_t tmem = *s.tmem_slot;
 
   if (warp == 0) {
     // ======================================================================================= weight-tile producer
-    // the per-step tile stream is the whole packed network in program order
+    // walks the same layer list as the MMA warp; a GEMM's tiles are contiguous (m-tile major, k-chunk minor, hi then lo)
     uint32_t stage = 0, phase = 0;
+    long long p_wait = 0;
+    const long long p_t0 = clock64();
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
-      const uint8_t* src = a.tiles[net];
-      for (uint32_t i = 0; i < a.n_step_tiles; ++i) {
-        mbar_wait(&s.empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&s.full[stage], kTile);
-          bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
+      for (int li = 0; li < a.n_layers; ++li) {
+        const ULayer* L = a.layers + li;
+        if (my_track >= 0 && L->track != my_track) continue;
+        const int n_gemm = L->n_gemm;
+        for (int gi = 0; gi < n_gemm; ++gi) {
+          const UGemm G = L->g[gi];
+          const uint8_t* src = a.tiles[net] + size_t(G.tile_off) * kTile;
+          const uint32_t n = uint32_t(G.mt) * G.kc * uint32_t(a.nsplit);
+          for (uint32_t i = 0; i < n; ++i) {
+            const long long tw = clock64();
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            p_wait += clock64() - tw;
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&s.full[stage], kTile);
+              bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
+            }
+            __syncwarp();
+            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
       }
     }
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = p_wait, a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0;
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, NE);
     uint32_t stage = 0, phase = 0, xr_phase = 0;
     const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
     const uint32_t op_hi = umma_desc_lo(smem_u32(s.op_hi)), op_lo = umma_desc_lo(smem_u32(s.op_lo));
+    long long m_wait_x = 0, m_wait_full = 0;
+    const long long m_t0 = clock64();
     for (int step = a.first_step; step < a.S; ++step) {
       for (int li = 0; li < a.n_layers; ++li) {
         const ULayer* L = a.layers + li;
+        if (my_track >= 0 && L->track != my_track) continue;
         const int n_gemm = L->n_gemm;
+        const UGemm G0 = L->g[0], G1 = L->g[1];  // fetched while the previous epilogue is still running
+        long long tw = clock64();
         mbar_wait(s.x_full, xr_phase);
+        m_wait_x += clock64() - tw;
         xr_phase ^= 1;
         tc_fence_after();
         for (int gi = 0; gi < n_gemm; ++gi) {
-          const UGemm G = L->g[gi];
+          const UGemm G = gi == 0 ? G0 : G1;
           for (int mt = 0; mt < int(G.mt); ++mt) {
             const uint32_t d = tmem + uint32_t(G.acc_tile + mt) * NE;
             for (int kc = 0; kc < int(G.kc); ++kc) {
@@ -174,7 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
                                                           : uint32_t(G.src_chunk[1]) + (kc - int(G.src_n[0]));
               const uint32_t boff = chunk * (kChunk / 16);
               const uint32_t bh = op_hi + boff, bl = op_lo + boff;
+              tw = clock64();
               mbar_wait(&s.full[stage], phase);
+              m_wait_full += clock64() - tw;
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t wa = ring_lo + stage * (kTile / 16);
@@ -194,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
               __syncwarp();
               if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
               if (split) {
+                tw = clock64();
                 mbar_wait(&s.full[stage], phase);
+                m_wait_full += clock64() - tw;
                 tc_fence_after();
                 if (elect_one()) {
                   const uint32_t wa = ring_lo + stage * (kTile / 16);
@@ -212,6 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         __syncwarp();
       }
     }
+    if (a.prof && lane == 0) {
+      a.prof[blockIdx.x * 16 + 2] = m_wait_x, a.prof[blockIdx.x * 16 + 3] = m_wait_full;
+      a.prof[blockIdx.x * 16 + 4] = clock64() - m_t0;
+    }
   } else {
     // ======================================================================================= epilogue warps
     const int et = threadIdx.x - 64;   // 0..255
@@ -222,11 +271,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const uint32_t odd = lane & 1;
     uint32_t ld_phase = 0;
+    uint32_t film_n = 0;  // FiLM blocks produced (encoder CTA) / consumed (main CTA) so far; buffer = film_n & 1
     float xreg[CPT];
     const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
 
+    long long e_wait = 0, e_film = 0;
+    const long long e_t0 = clock64();
     auto wait_layer = [&]() {
+      const long long tw = clock64();
       mbar_wait(s.layer_done, ld_phase);
+      e_wait += clock64() - tw;
       ld_phase ^= 1;
       tc_fence_after();
     };
@@ -265,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
       for (int j = 0; j < CPT; ++j) {
         const int i = et + j * kEpiThreads;
         float x = 0.f;
-        if (i < nxe) {
+        if (i < nxe && rank == 0) {
           const int e = i / a.D, f = i - e * a.D;
           const int env = env0 + e;
           if (env < a.E) {
@@ -291,45 +345,69 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
       const float* side = a.side[net];
       for (int li = 0; li < a.n_layers; ++li) {
         const ULayer* L = a.layers + li;
+        if (my_track >= 0 && L->track != my_track) continue;
         const int kind = L->kind, acc_tile = L->acc_tile, MTl = L->mt, nf = L->nf;
         const float* bias = side + L->bias_off + size_t(L->bias_tstride) * row.t;
+        const int gs = L->gn_size, do_act = L->act, film = L->film, film_c = L->film_c, tshift = L->film_tshift;
+        const int res = L->res;
+        const float* gamma = side + L->gamma_off;
+        const float* beta = side + L->beta_off;
+        const float gn_eps = L->gn_eps;
+        const float* res_bias = side + L->res_bias_off;
+        // per-feature constants of the first two M tiles are fetched (L2 latency) while the MMAs of this layer still run
+        float pb[2], pg[2], pbe[2], prb[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int f = (i < MTl ? i : 0) * 128 + fl;
+          pb[i] = bias[f], pg[i] = gamma[f], pbe[i] = beta[f], prb[i] = res_bias[f];
+        }
         wait_layer();
         if (kind == U_EPI_OPERAND) {
-          const int gs = L->gn_size, do_act = L->act, film = L->film, film_c = L->film_c, tshift = L->film_tshift;
-          const int res = L->res;
-          const float* gamma = side + L->gamma_off;
-          const float* beta = side + L->beta_off;
-          const float gn_eps = L->gn_eps;
-          const float* res_bias = side + L->res_bias_off;
           const uint32_t dst_base = uint32_t(L->dst_chunk) * kChunk;
           const uint32_t res_base = uint32_t(res == U_RES_SLOT ? L->res_chunk : 0) * kChunk;
           const uint32_t res_tile = uint32_t(L->res_acc_tile);
+          const float* film_buf = s.film;
+          if (film && C > 1) {
+            // this block's (scale, bias) vectors arrive from the encoder CTA
+            const long long tw = clock64();
+            mbar_wait_cluster(&s.film_full[film_n & 1], (film_n >> 1) & 1);
+            e_film += clock64() - tw;
+            film_buf = s.film + (film_n & 1) * s.film_stride;
+          }
           for (int mt = 0; mt < MTl; ++mt) {
             float v[CPT];
             tmem_ld(tmem + lane_addr + uint32_t(acc_tile + mt) * NE + col0, v);
             const int f = mt * 128 + fl;
-            const float b = bias[f];
+            const float b = mt < 2 ? pb[mt & 1] : bias[f];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) v[c] += b;
             if (gs) {
-              // GroupNorm over gs consecutive features (lanes) of each environment column: mean, then centred variance
-              const float inv = 1.f / float(gs), g = gamma[f], be = beta[f];
+              // GroupNorm over gs consecutive features (lanes) of each environment column: mean, then centred variance.
+              // Stage-major loops keep CPT independent shuffles in flight per butterfly stage.
+              const float inv = 1.f / float(gs);
+              const float g = mt < 2 ? pg[mt & 1] : gamma[f], be = mt < 2 ? pbe[mt & 1] : beta[f];
+              float sm[CPT];
 #pragma unroll
-              for (int c = 0; c < CPT; ++c) {
-                float sm = v[c];
-                for (int o = gs >> 1; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-                const float dlt = v[c] - sm * inv;
-                float sq = dlt * dlt;
-                for (int o = gs >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                v[c] = dlt * rsqrtf(sq * inv + gn_eps) * g + be;
+              for (int c = 0; c < CPT; ++c) sm[c] = v[c];
+              for (int o = gs >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) sm[c] += __shfl_xor_sync(0xffffffffu, sm[c], o);
               }
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) v[c] -= sm[c] * inv, sm[c] = v[c] * v[c];
+              for (int o = gs >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) sm[c] += __shfl_xor_sync(0xffffffffu, sm[c], o);
+              }
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) v[c] = v[c] * rsqrtf(sm[c] * inv + gn_eps) * g + be;
             }
             if (do_act) {
 #pragma unroll
               for (int c = 0; c < CPT; ++c) v[c] = act_f<ACT>(v[c]);
             }
             if (film && f < nf) {
-              const float* fr = s.film + size_t(col0) * a.film_dim + (f >> tshift);
+              const float* fr = film_buf + size_t(col0) * a.film_dim + (f >> tshift);
 #pragma unroll
               for (int c = 0; c < CPT; ++c) {
                 const float* fe = fr + size_t(c) * a.film_dim;
@@ -339,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             if (res == U_RES_ACC) {
               float r[CPT];
               tmem_ld(tmem + lane_addr + (res_tile + uint32_t(mt)) * NE + col0, r);
-              const float rb = res_bias[f];
+              const float rb = mt < 2 ? prb[mt & 1] : res_bias[f];
 #pragma unroll
               for (int c = 0; c < CPT; ++c) v[c] += r[c] + rb;
             }
@@ -372,16 +450,39 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
                     __floats2bfloat162_rn(fa - __low2float(h2), fb - __high2float(h2));
             }
           }
+          if (film && C > 1) {
+            // every epilogue thread is done reading the buffer: hand it back to the encoder CTA
+            named_bar_sync(1, kEpiThreads);
+            if (et == 0) mbar_arrive_remote(&s.film_free[film_n & 1], 1);
+            ++film_n;
+          }
         } else if (kind == U_EPI_FILM) {
+          float* film_buf = s.film;
+          if (C > 1) {
+            // double-buffered in the MAIN CTA's shared memory; block n may be written once block n - 2 was consumed
+            const long long tw = clock64();
+            if (film_n >= 2) mbar_wait_cluster(&s.film_free[film_n & 1], ((film_n >> 1) - 1) & 1);
+            e_film += clock64() - tw;
+            film_buf = s.film + (film_n & 1) * s.film_stride;
+          }
           for (int mt = 0; mt < MTl; ++mt) {
             float v[CPT];
             tmem_ld(tmem + lane_addr + uint32_t(acc_tile + mt) * NE + col0, v);
             const int f = mt * 128 + fl;
             if (f < nf) {
-              const float b = bias[f];
+              const float b = mt < 2 ? pb[mt & 1] : bias[f];
+              if (C > 1) {
 #pragma unroll
-              for (int c = 0; c < CPT; ++c) s.film[size_t(col0 + c) * a.film_dim + f] = v[c] + b;
+                for (int c = 0; c < CPT; ++c) st_remote_f32(film_buf + size_t(col0 + c) * a.film_dim + f, 0, v[c] + b);
+              } else {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) film_buf[size_t(col0 + c) * a.film_dim + f] = v[c] + b;
+              }
             }
+          }
+          if (C > 1) {
+            mbar_arrive_remote(&s.film_full[film_n & 1], 0);  // release.cluster: orders this thread's remote stores
+            ++film_n;
           }
         } else {
           // output layer + posterior (diffusion_vpg.py:165-224, 279-311): eps -> [env][flat element] fp32 tile, then all
@@ -390,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             float v[CPT];
             tmem_ld(tmem + lane_addr + uint32_t(acc_tile) * NE + col0, v);
             if (fl < a.D) {
-              const float bo = bias[fl];
+              const float bo = pb[0];
 #pragma unroll
               for (int c = 0; c < CPT; ++c) s.eps[(col0 + c) * a.D + fl] = v[c] + bo;
             }
@@ -456,12 +557,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         signal_x();
       }
     }
+    if (a.prof && et == 0) a.prof[blockIdx.x * 16 + 5] = e_wait, a.prof[blockIdx.x * 16 + 6] = clock64() - e_t0, a.prof[blockIdx.x * 16 + 7] = e_film;
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 8 + (warp - 2)] = (clock64() - e_t0) - e_wait - e_film;
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (C > 1) cluster_sync_all();  // no CTA leaves while its peer can still signal it or store into it
 }
 
 template <int NE, int ACT>
@@ -474,42 +578,65 @@ int ulaunch(const UArgs& a, size_t smem_bytes, cudaStream_t st) {
     configured = true;
   }
   const int tiles = (a.E + NE - 1) / NE;
-  chain_unet_kernel<NE, ACT><<<tiles, kThreads, smem_bytes, st>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(tiles * a.C)), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(a.C), attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, a);
   if (e != cudaSuccess) return cuda_fail(e, "chain_unet_kernel launch");
   return DPPO_OK;
 }
 
 }  // namespace
 
-// Tile size: the kernel is bound by the weight ingest of one SM (the whole lowered net, every step, whatever NE is),
-// so the smallest tile that still fits every environment in one wave wins; larger tiles only when E needs them.
-static int pick_unet_tile(const dppo_ctx* ctx, int E, int* nstage_out) {
+// Launch shape (NE environments per tile, C = 1 | 2 CTAs per tile).  The kernel is bound by the weight ingest of one SM
+// (its whole track, every step, whatever NE is) plus a per-layer epilogue / hand-off latency, so the smallest tile that
+// still fits every environment in one wave wins, and the track-split pair wins whenever the pairs fit in one wave.
+struct UShape {
+  int NE, C, nstage;
+};
+static UShape pick_unet_shape(const dppo_ctx* ctx, int E) {
   const UnetPlan& P = *ctx->unet;
-  static int env_ne = -1;
+  static int env_ne = -1, env_c = -1;
   if (env_ne < 0) {
     const char* e = getenv("DPPO_B200_TILE_ENVS");
     env_ne = e ? atoi(e) : 0;
+    e = getenv("DPPO_B200_CLUSTER");
+    env_c = e ? atoi(e) : 0;
   }
-  const int forced = ctx->force_ne ? ctx->force_ne : env_ne;
+  const int forced_ne = ctx->force_ne ? ctx->force_ne : env_ne, forced_c = ctx->force_c ? ctx->force_c : env_c;
   const size_t budget = 232448;
-  int best = 0, best_stage = 0;
+  UShape best{0, 1, 0};
   double best_t = 1e30;
-  for (int NE = 16; NE <= 64; NE *= 2) {
-    if (forced > 0 && NE != forced) continue;
-    if (2 * P.MTmax * NE > 512) continue;
-    const size_t fixed = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D);
-    if (fixed + 2 * kTile > budget) continue;
-    int nstage = int((budget - fixed) / kTile);
-    if (nstage > kMaxStages) nstage = kMaxStages;
-    const int tiles = (E + NE - 1) / NE;
-    const int waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
-    const double ingest = double(P.n_tiles) * 16384.0 / (nstage >= 3 ? 34.7 : 20.0);
-    const double epi = double(P.layers.size()) * (double(NE) * P.MTmax * 128 / 256.0 * 37.0 + 1500.0);
-    const double t = waves * (ingest + epi);
-    if (t < best_t) best_t = t, best = NE, best_stage = nstage;
+  for (int C = 1; C <= 2; ++C) {
+    if (forced_c > 0 && C != forced_c) continue;
+    if (C == 2 && P.track_layers[1] == 0) continue;
+    for (int NE = 16; NE <= 64; NE *= 2) {
+      if (forced_ne > 0 && NE != forced_ne) continue;
+      if (2 * P.MTmax * NE > 512) continue;
+      const size_t fixed = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D, C);
+      if (fixed + 2 * kTile > budget) continue;
+      int nstage = int((budget - fixed) / kTile);
+      if (nstage > kMaxStages) nstage = kMaxStages;
+      const int tiles = (E + NE - 1) / NE;
+      const int slots = ctx->sm_count / C;
+      const int waves = (tiles + slots - 1) / slots;
+      const double rate = nstage >= 3 ? 34.7 : 20.0;
+      const double per_layer = double(NE) * P.MTmax * 128 / 256.0 * 37.0 + 4000.0;
+      double t;
+      if (C == 1) {
+        t = double(P.n_tiles) * 16384.0 / rate + double(P.layers.size()) * per_layer;
+      } else {
+        const double t0 = double(P.track_tiles[0]) * 16384.0 / rate + P.track_layers[0] * per_layer;
+        const double t1 = double(P.track_tiles[1]) * 16384.0 / rate + P.track_layers[1] * per_layer;
+        t = t0 > t1 ? t0 : t1;
+      }
+      t *= waves;
+      if (t < best_t) best_t = t, best = UShape{NE, C, nstage};
+    }
   }
-  *nstage_out = best_stage;
   return best;
 }
 
@@ -519,7 +646,7 @@ int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float
   const UnetPlan& P = *ctx->unet;
   UArgs a{};
   a.D = P.D, a.Da = P.d.action_dim, a.Ta = P.d.horizon_steps, a.Dc = P.d.cond_dim, a.nsplit = P.nsplit;
-  a.n_layers = int(P.layers.size()), a.layers = ctx->d_unet_layers, a.n_step_tiles = uint32_t(P.n_tiles);
+  a.n_layers = int(P.layers.size()), a.layers = ctx->d_unet_layers;
   for (int w = 0; w < 2; ++w) a.tiles[w] = ctx->nets[w].tiles, a.side[w] = ctx->nets[w].side;
   a.chunk_x = P.chunk_x, a.chunk_state = P.chunk_state, a.chunk_state_act = P.chunk_state_act, a.KS = P.KS;
   a.total_chunks = P.total_chunks, a.film_dim = P.film_dim;
@@ -531,12 +658,13 @@ int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float
   a.eps_clip = ctx->eps_clip;
   a.state = state, a.E = E, a.noise = noise, a.traj = traj, a.chain = chain, a.chains_in = chains_in, a.logp = logp;
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
+  a.prof = ctx->d_prof;
 
-  int nstage = 0;
-  const int NE = pick_unet_tile(ctx, E, &nstage);
+  const UShape shape = pick_unet_shape(ctx, E);
+  const int NE = shape.NE;
   if (NE == 0) return set_error("unet chain kernel: no tile size fits this geometry in shared memory / TMEM"), DPPO_ERR_UNSUPPORTED;
-  a.nstage = nstage;
-  const size_t smem_bytes = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D) + size_t(nstage) * kTile;
+  a.nstage = shape.nstage, a.C = shape.C;
+  const size_t smem_bytes = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D, a.C) + size_t(a.nstage) * kTile;
 #define DPPO_ULAUNCH(NE_) \
   (P.d.activation == DPPO_ACT_RELU ? ulaunch<NE_, DPPO_ACT_RELU>(a, smem_bytes, st) : ulaunch<NE_, DPPO_ACT_MISH>(a, smem_bytes, st))
   if (NE == 64) return DPPO_ULAUNCH(64);

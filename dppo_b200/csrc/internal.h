@@ -86,6 +86,7 @@ struct dppo_ctx {
   dppo::USideJob* d_unet_side_jobs = nullptr;
   dppo::ULayer* d_unet_layers = nullptr;
   const float** d_unet_params[2] = {nullptr, nullptr};
+  int sample_dim = 0;  // Ta * Da of either denoiser kind
   int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

@@ -141,23 +141,23 @@ struct Builder {
       L1.n_gemm = 1, L1.g[0] = lin_gemm(pcond, fd, d.cond_dim, gin, d.time_dim, P.chunk_state, 0);
       L1.kind = U_EPI_OPERAND, L1.acc_tile = 0, L1.mt = fdp / 128, L1.nf = fd;
       L1.bias_off = side_time(pcond, fd, fdp, gin, 0), L1.bias_tstride = fdp;
-      L1.act = 1, L1.dst_chunk = P.chunk_condh;
+      L1.act = 1, L1.dst_chunk = P.chunk_condh, L1.track = 1;
       P.layers.push_back(L1);
       ULayer L2 = blank();
       L2.n_gemm = 1, L2.g[0] = lin_gemm(pcond + 2, fd, fd, fd, 0, P.chunk_condh, 0);
       L2.kind = U_EPI_OPERAND, L2.acc_tile = 0, L2.mt = fdp / 128, L2.nf = fd;
-      L2.bias_off = side_copy(pcond + 3, fd, 1, 0, fdp), L2.act = 1, L2.dst_chunk = P.chunk_condh;
+      L2.bias_off = side_copy(pcond + 3, fd, 1, 0, fdp), L2.act = 1, L2.dst_chunk = P.chunk_condh, L2.track = 1;
       P.layers.push_back(L2);
       ULayer L3 = blank();
       L3.n_gemm = 1, L3.g[0] = lin_gemm(pcond + 4, fd, fd, fd, 0, P.chunk_condh, 0);
       L3.kind = U_EPI_FILM, L3.acc_tile = 0, L3.mt = fdp / 128, L3.nf = fd;
-      L3.bias_off = side_copy(pcond + 5, fd, 1, 0, fdp);
+      L3.bias_off = side_copy(pcond + 5, fd, 1, 0, fdp), L3.track = 1;
       P.layers.push_back(L3);
     } else {
       ULayer L = blank();
       L.n_gemm = 1, L.g[0] = lin_gemm(pcond, fd, d.cond_dim, gin, d.time_dim, P.chunk_state_act, 0);
       L.kind = U_EPI_FILM, L.acc_tile = 0, L.mt = fdp / 128, L.nf = fd;
-      L.bias_off = side_time(pcond, fd, fdp, gin, 1), L.bias_tstride = fdp;
+      L.bias_off = side_time(pcond, fd, fdp, gin, 1), L.bias_tstride = fdp, L.track = 1;
       P.layers.push_back(L);
     }
     // ---- blocks[0]: conv -> GroupNorm -> act, then FiLM
@@ -300,7 +300,6 @@ int unet_build_plan(const dppo_unet_desc& d, int K, int precision, UnetPlan* out
   // time-major (t * Da + d) = the flat sample index the posterior step uses
   {
     const int C = widths[1];
-    if (nl == 1 && false) (void)0;
     const Seg h{chunk_h, C};
     ULayer L = B.blank();
     L.n_gemm = 1, L.g[0] = B.conv_gemm(B.pc, U_PACK_CONV, &h, 1, T, C, T, d.kernel_size, 1, d.kernel_size / 2, 0, 0);
@@ -322,6 +321,10 @@ int unet_build_plan(const dppo_unet_desc& d, int K, int precision, UnetPlan* out
   P.n_params = B.pc;
   P.n_side = B.side;
   P.n_tiles = B.tile;
+  for (const ULayer& L : P.layers) {
+    ++P.track_layers[L.track];
+    for (int gi = 0; gi < L.n_gemm; ++gi) P.track_tiles[L.track] += size_t(L.g[gi].mt) * L.g[gi].kc * P.nsplit;
+  }
   if (2 * P.MTmax * 16 > 512) return set_error("unet: %d features per activation exceed the TMEM budget", P.MTmax * 128), DPPO_ERR_UNSUPPORTED;
   return DPPO_OK;
 }

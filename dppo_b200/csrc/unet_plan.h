@@ -43,6 +43,7 @@ struct ULayer {
   int32_t res;                     // U_RES_*
   int32_t res_acc_tile, res_bias_off, res_chunk;
   int32_t dst_chunk;               // operand chunk the result is written to (U_EPI_OPERAND)
+  int32_t track;                   // 0 = main path (x -> eps), 1 = FiLM conditioning encoders (depend on t and obs only)
 };
 
 enum : int32_t { U_PACK_LINEAR = 0, U_PACK_CONV = 1, U_PACK_CONVT = 2 };
@@ -108,6 +109,8 @@ struct UnetPlan {
   std::vector<UPackJob> jobs;
   std::vector<USideJob> side_jobs;
   size_t n_side = 0, n_tiles = 0;
+  size_t track_tiles[2] = {0, 0};  // weight tiles per evaluation on each track
+  int track_layers[2] = {0, 0};
   double macs_dense = 0;   // MACs per sample and evaluation of the lowered net (zero padding excluded)
 };
 

@@ -331,17 +331,17 @@ extern "C" int dppo_logprob_rows(dppo_ctx* ctx, const float* eps, const float* x
                                  const int64_t* dinds, int n_rows, float* logp, float* dlogp_deps, void* stream) {
   if (!ctx || !eps || !x_prev || !x_next || !dinds || !logp) return set_error("dppo_logprob_rows: null argument"), DPPO_ERR_INVALID;
   if (n_rows <= 0) return n_rows == 0 ? DPPO_OK : (set_error("dppo_logprob_rows: n_rows < 0"), DPPO_ERR_INVALID);
-  const long long total = (long long)n_rows * ctx->g.D;
+  const long long total = (long long)n_rows * ctx->sample_dim;
   logprob_rows_kernel<<<unsigned((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       eps, x_prev, x_next, dinds, ctx->d_rows, ctx->S - ctx->ft, ctx->use_ddim, ctx->x0_clip, ctx->eps_clip,
-      ctx->min_logprob_std, ctx->g.D, total, logp, dlogp_deps);
+      ctx->min_logprob_std, ctx->sample_dim, total, logp, dlogp_deps);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "logprob_rows_kernel launch");
 }
 
 static int loss_impl(dppo_ctx* ctx, LossArgs a, const int64_t* stat_inds, const dppo_loss_hp* hp, float* scalars,
                      void* workspace, void* stream, const char* who) {
-  const int D = ctx->g.D;
+  const int D = ctx->sample_dim;
   if (a.n_rows < 0 || a.global_rows < 1 || a.n_rows > a.global_rows)
     return set_error("%s: bad row counts %d of %d", who, a.n_rows, a.global_rows), DPPO_ERR_INVALID;
   if (hp->ft_denoising_steps != ctx->ft || hp->horizon_steps * hp->action_dim != D)

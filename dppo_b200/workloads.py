@@ -97,20 +97,24 @@ def make_agent_cfg(w: dict, device: str, logdir: str, n_envs: int = None, n_step
                    batch_size: int = None, update_epochs: int = None, seed: int = 42, precision: str = None):
     """
     Config tree for dppo_b200.agent.finetune.train_ppo_diffusion_agent.TrainPPODiffusionAgent with the keys of the
-    reference YAML cited in `w["yaml"]` (model node = Hydra-style `_target_` dicts).  Only DiffusionMLP actors.
+    reference YAML cited in `w["yaml"]` (model node = Hydra-style `_target_` dicts); DiffusionMLP or Unet1D actors.
     """
     from dppo_b200.util.config import Cfg
 
     a = dict(w["actor"])
-    if a.pop("kind") != "mlp":
-        raise NotImplementedError("agent configs are built for DiffusionMLP actors")
+    kind = a.pop("kind")
     t = w["train"]
     cond_dim = w["obs_dim"] * w["cond_steps"]
     E = n_envs or w["n_envs"]
+    if kind == "mlp":
+        actor = dict({"_target_": "dppo_b200.model.diffusion.mlp_diffusion.DiffusionMLP", "action_dim": w["action_dim"],
+                      "horizon_steps": w["horizon_steps"], "cond_dim": cond_dim}, **a)
+    else:
+        actor = dict({"_target_": "dppo_b200.model.diffusion.unet.Unet1D", "action_dim": w["action_dim"],
+                      "cond_dim": cond_dim}, **a)
     model = {
         "_target_": "dppo_b200.model.diffusion.diffusion_ppo.PPODiffusion",
-        "actor": dict({"_target_": "dppo_b200.model.diffusion.mlp_diffusion.DiffusionMLP", "action_dim": w["action_dim"],
-                       "horizon_steps": w["horizon_steps"], "cond_dim": cond_dim}, **a),
+        "actor": actor,
         "critic": dict({"_target_": "dppo_b200.model.common.critic.CriticObs", "cond_dim": cond_dim}, **w["critic"]),
         "ft_denoising_steps": w["ft_denoising_steps"], "horizon_steps": w["horizon_steps"], "obs_dim": w["obs_dim"],
         "action_dim": w["action_dim"], "denoising_steps": w["denoising_steps"], "device": device,

@@ -35,6 +35,13 @@ b.record()
 torch.cuda.synchronize()
 p = prof.view(grid, 16).cpu()
 used = p[p[:, 4] > 0]
+if "unet" in name and cl == 2:  # track-split pair: even CTAs = main path, odd CTAs = FiLM encoders
+    for r, lab in ((0, "main"), (1, "encoders")):
+        sub = p[r::2][p[r::2][:, 4] > 0]
+        print(f"  -- rank {r} ({lab}), {len(sub)} CTAs")
+        for i, n in enumerate(["prod_wait_empty", "prod_total", "mma_wait_x", "mma_wait_full", "mma_total", "epi_wait_layer", "epi_total", "epi_film_wait", "epi_work_warp2"]):
+            col = sub[:, i].double()
+            print(f"     {n:16s} mean {col.mean() / 1e3:10.1f} kcyc   max {col.max() / 1e3:10.1f} kcyc")
 names = ["prod_wait_empty", "prod_total", "mma_wait_x", "mma_wait_full", "mma_total", "epi_wait_layer", "epi_total", "epi_handshake"] + [f"epi_work_warp{i+2}" for i in range(8)]
 print(f"{name} E={E} {prec} NE={ne} C={cl}: kernel {a.elapsed_time(b):.3f} ms, {len(used)} CTAs")
 for i, n in enumerate(names):

@@ -20,25 +20,33 @@ def rel(a, b):
     return np.abs(a - b) / np.maximum(1.0, np.abs(b))
 
 
-for ne in (16, 32):
-    model.engine().set_launch_shape(ne, 0)
-    out = model(cond={"state": state}, deterministic=False, return_chain=True, noise=noise)
+for ne, cc in ((16, 1), (16, 2), (32, 1), (32, 2)):
+    model.engine().set_launch_shape(ne, cc)
+    try:
+        out = model(cond={"state": state}, deterministic=False, return_chain=True, noise=noise)
+    except RuntimeError as ex:
+        print(f"NE={ne} C={cc}: {ex}")
+        continue
     torch.cuda.synchronize()
     e = rel(out.chains.cpu().numpy(), gold["chains"])
-    print(f"NE={ne} chains max rel err {e.max():.3e}  per-slot max {e.reshape(e.shape[0], e.shape[1], -1).max(axis=(0, 2))}")
+    print(f"NE={ne} C={cc} chains max rel err {e.max():.3e}  per-slot max {e.reshape(e.shape[0], e.shape[1], -1).max(axis=(0, 2))}")
     with torch.no_grad():
         lp = model.get_logprobs({"state": state}, torch.from_numpy(gold["chains"]).cuda())
     e = rel(lp.cpu().numpy(), gold["logprobs"])
-    print(f"NE={ne} logprobs max rel err {e.max():.3e}")
+    print(f"NE={ne} C={cc} logprobs max rel err {e.max():.3e}")
     out = model(cond={"state": state}, deterministic=True, return_chain=True, noise=noise)
     e = rel(out.chains.cpu().numpy(), gold["chains_det"])
-    print(f"NE={ne} deterministic chains max rel err {e.max():.3e}")
+    print(f"NE={ne} C={cc} deterministic chains max rel err {e.max():.3e}")
 
 model.engine().set_launch_shape(0, 0)
 for E in (1024, 2048, 4096):
     st = torch.rand(E, 1, w["obs_dim"], device="cuda") * 2 - 1
-    for ne in (16, 32):
-        model.engine().set_launch_shape(ne, 0)
+    for ne, cc in ((16, 1), (16, 2), (32, 1), (32, 2), (0, 0)):
+        model.engine().set_launch_shape(ne, cc)
+        try:
+            model(cond={"state": st})
+        except RuntimeError:
+            continue
         for _ in range(3):
             model(cond={"state": st})
         torch.cuda.synchronize()
@@ -49,4 +57,4 @@ for E in (1024, 2048, 4096):
         t1.record()
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / 10
-        print(f"E={E} NE={ne}: {ms:.3f} ms/chain  {E * w['act_steps'] / ms * 1e3 / 1e6:.2f} M env-steps/s")
+        print(f"E={E} NE={ne} C={cc}: {ms:.3f} ms/chain  {E * w['act_steps'] / ms * 1e3 / 1e6:.2f} M env-steps/s")

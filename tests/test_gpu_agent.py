@@ -9,10 +9,10 @@ from dppo_b200.workloads import get_workload, make_agent_cfg
 pytestmark = pytest.mark.gpu
 
 
-def _agent(tmp_path, **kw):
+def _agent(tmp_path, workload="hopper", **kw):
     from dppo_b200.agent.finetune.train_ppo_diffusion_agent import TrainPPODiffusionAgent
 
-    w = get_workload("hopper")
+    w = get_workload(workload)
     cfg = make_agent_cfg(w, "cuda:0", str(tmp_path), **kw)
     return w, TrainPPODiffusionAgent(cfg)
 
@@ -83,3 +83,13 @@ def test_update_equals_plain_autograd_minibatch(tmp_path):
     g_ref = torch.cat([p.grad.reshape(-1) for p in ag.grads.params])
     assert float((g_flat - g_ref).abs().max()) <= 1e-5 * max(1.0, float(g_ref.abs().max()))
     assert abs(float(ag.grads.scalars[0]) - float(r0[0])) <= 1e-6 * max(1.0, abs(float(r0[0])))
+
+
+def test_unet_agent_runs_two_iterations(tmp_path):
+    """cfg5 (Unet1D denoiser, DDIM-10): rollout through the unet chain kernel, update through autograd + the loss kernel."""
+    w, ag = _agent(tmp_path, workload="square_unet", n_envs=8, n_steps=4, batch_size=64, update_epochs=1, n_train_itr=3)
+    ag.n_critic_warmup_itr = 1
+    before = {k: v.clone() for k, v in ag.model.actor_ft.state_dict().items()}
+    res = ag.run()
+    assert len(res) == 3 and all(np.isfinite(r["pg_loss"]) and np.isfinite(r["v_loss"]) for r in res)
+    assert any(not torch.equal(before[k], v) for k, v in ag.model.actor_ft.state_dict().items())
