@@ -299,9 +299,11 @@ def bench_update(args, w, model, dev, E, rank, world):
     from dppo_b200 import distributed as D
 
     bs = min(w["train"]["batch_size"], N * ft)
-    opt_a = torch.optim.AdamW(model.actor_ft.parameters(), lr=w["train"]["actor_lr"])
-    opt_c = torch.optim.AdamW(model.critic.parameters(), lr=w["train"]["critic_lr"])
-    grads = D.FlatGradBuffer(list(model.actor_ft.parameters()) + list(model.critic.parameters()))
+    from dppo_b200.optim import FlatAdamW
+
+    opt_a = FlatAdamW(model.actor_ft.parameters(), lr=w["train"]["actor_lr"], weight_decay=0)
+    opt_c = FlatAdamW(model.critic.parameters(), lr=w["train"]["critic_lr"], weight_decay=0)
+    grads = D.FlatGradBuffer([list(model.actor_ft.parameters()), list(model.critic.parameters())])
     lo, hi = D.minibatch_slice(bs, rank, world)
     per_rank = bs // world
 
@@ -331,7 +333,7 @@ def bench_update(args, w, model, dev, E, rank, world):
     return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
             "minibatch_rows": per_rank * world, "buffer_rows": N * ft,
             "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
-                     "network GEMMs via torch autograd (cuBLAS fp32); AdamW torch")}
+                     "network GEMMs via torch autograd (cuBLAS fp32); fused flat AdamW kernel per network")}
 
 
 def main():

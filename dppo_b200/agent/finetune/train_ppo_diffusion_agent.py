@@ -33,6 +33,7 @@ import torch
 
 from dppo_b200 import distributed as D
 from dppo_b200 import engine as E_
+from dppo_b200.optim import FlatAdamW
 from dppo_b200.util.config import instantiate
 from dppo_b200.util.reward_scaling import RunningRewardScaler
 
@@ -96,10 +97,11 @@ class TrainPPODiffusionAgent:
         self.logprob_batch_size = cfg.train.get("logprob_batch_size", 10000)
         self.gamma = cfg.train.gamma
         self.n_critic_warmup_itr = cfg.train.n_critic_warmup_itr
-        self.actor_optimizer = torch.optim.AdamW(self.model.actor_ft.parameters(), lr=cfg.train.actor_lr,
-                                                 weight_decay=cfg.train.actor_weight_decay)
-        self.critic_optimizer = torch.optim.AdamW(self.model.critic.parameters(), lr=cfg.train.critic_lr,
-                                                  weight_decay=cfg.train.critic_weight_decay)
+        # torch.optim.AdamW's update rule as one fused kernel per network over flat parameter / gradient segments
+        self.actor_optimizer = FlatAdamW(self.model.actor_ft.parameters(), lr=cfg.train.actor_lr,
+                                         weight_decay=cfg.train.actor_weight_decay)
+        self.critic_optimizer = FlatAdamW(self.model.critic.parameters(), lr=cfg.train.critic_lr,
+                                          weight_decay=cfg.train.critic_weight_decay)
         self._sched = {"actor": -1, "critic": -1}
         self._apply_lr()
         self.gae_lambda = cfg.train.get("gae_lambda", 0.95)
@@ -118,7 +120,7 @@ class TrainPPODiffusionAgent:
             raise NotImplementedError("learned eta is outside the hot path (no YAML enables it)")
 
         # gradients of both networks + 8 diagnostics in ONE flat buffer -> one all-reduce per minibatch
-        self.grads = D.FlatGradBuffer(list(self.model.actor_ft.parameters()) + list(self.model.critic.parameters()))
+        self.grads = D.FlatGradBuffer([list(self.model.actor_ft.parameters()), list(self.model.critic.parameters())])
         self.timings = {}
 
     # ------------------------------------------------------------------ schedules
@@ -233,9 +235,7 @@ class TrainPPODiffusionAgent:
                              + float(bc_loss) * self.bc_loss_coeff)
                 clipfracs.append(s[3])
                 if self.itr >= self.n_critic_warmup_itr:
-                    if self.max_grad_norm is not None:
-                        torch.nn.utils.clip_grad_norm_(self.model.actor_ft.parameters(), self.max_grad_norm)
-                    self.actor_optimizer.step()
+                    self.actor_optimizer.step(max_grad_norm=self.max_grad_norm)  # clip_grad_norm_ folded into the kernel
                 self.critic_optimizer.step()
                 if self.target_kl is not None and s[2] > self.target_kl:
                     flag_break = True

@@ -80,16 +80,22 @@ class FlatGradBuffer:
     Backward writes straight into the views - there is no pack / unpack copy.
     """
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], n_scalars: int = 8):
-        self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+    def __init__(self, params: Sequence, n_scalars: int = 8):
+        """`params`: a list of parameters, or a list of parameter LISTS (one per optimiser): every group then starts on
+        a 16-byte boundary, which is what the fused AdamW kernel (dppo_b200.optim.FlatAdamW) reads with float4 loads."""
+        groups = [list(g) for g in params] if params and isinstance(params[0], (list, tuple)) else [list(params)]
+        groups = [[p for p in g if p.requires_grad] for g in groups]
+        self.params = [p for g in groups for p in g]
+        n = sum((sum(p.numel() for p in g) + 3) // 4 * 4 for g in groups)
         dev = self.params[0].device
         self.flat = torch.zeros(n + n_scalars, dtype=torch.float32, device=dev)
         self.n_grad, self.n_scalars = n, n_scalars
         o = 0
-        for p in self.params:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
-            o += p.numel()
+        for g in groups:
+            for p in g:
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+            o = (o + 3) // 4 * 4
 
     @property
     def scalars(self) -> torch.Tensor:

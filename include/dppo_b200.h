@@ -207,6 +207,16 @@ int dppo_gae_f64(const double* reward, const double* terminated, const double* v
                  int n_steps, int n_envs, double gamma, double gae_lambda, double reward_scale_const,
                  double* advantages, double* returns, void* stream);
 
+/* ---- optimiser ------------------------------------------------------------------------------------------------ */
+/* torch.optim.AdamW step (train_ppo_diffusion_agent.py:360-373, optimisers built at train_ppo_agent.py:34-53) over ONE
+ * flat fp32 segment: params / grads / exp_avg / exp_avg_sq are 16-byte aligned device arrays of n floats (the gradient
+ * segment is the flat all-reduced buffer the backward writes into).  `step` = 1-based step count (bias correction).
+ * max_grad_norm >= 0 applies torch.nn.utils.clip_grad_norm_'s coefficient min(1, max / (||g||_2 + 1e-6)) computed on the
+ * device (workspace: >= 8 bytes); < 0 = no clipping.                                                              */
+int dppo_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float max_grad_norm,
+                    void* workspace, void* stream);
+
 /* ---- bring-up ------------------------------------------------------------------------------------------------- */
 /* Single-CTA tcgen05 GEMM that validates the shared-memory / instruction descriptor encodings on hardware:
  * c[128,N] = a[128,K] * b[N,K]^T in bf16 with fp32 accumulation.  scratch >= K/64 * 16 KiB.                      */

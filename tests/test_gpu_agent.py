@@ -73,7 +73,7 @@ def test_update_equals_plain_autograd_minibatch(tmp_path):
     r1 = m.loss_gathered(obs_k, chains_k, lp_k, ret.reshape(-1), values.reshape(-1), adv.reshape(-1), inds,
                          reward_horizon=ag.reward_horizon, scalars_out=ag.grads.scalars)
     (r1[0] + 0.5 * r1[2]).backward()
-    g_flat = ag.grads.flat[: ag.grads.n_grad].clone()
+    g_flat = torch.cat([p.grad.reshape(-1).clone() for p in ag.grads.params])  # groups are padded to 16 bytes
     for p in ag.grads.params:
         p.grad = None
     b, d = inds // ft, inds % ft
@@ -93,3 +93,37 @@ def test_unet_agent_runs_two_iterations(tmp_path):
     res = ag.run()
     assert len(res) == 3 and all(np.isfinite(r["pg_loss"]) and np.isfinite(r["v_loss"]) for r in res)
     assert any(not torch.equal(before[k], v) for k, v in ag.model.actor_ft.state_dict().items())
+
+
+@pytest.mark.parametrize("clip", [None, 0.05])
+def test_flat_adamw_matches_torch_adamw(clip):
+    """dppo_adamw_flat == torch.optim.AdamW (+ clip_grad_norm_) over several steps, odd sizes, both flat-buffer groups."""
+    from dppo_b200 import distributed as D
+    from dppo_b200.optim import FlatAdamW
+
+    torch.manual_seed(0)
+    shapes = [(37, 19), (19,), (5, 7, 3), (1,), (130, 64)]
+    mine = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    other = [torch.nn.Parameter(torch.randn(3, 11, device="cuda"))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    opt = FlatAdamW(mine, lr=3e-3, weight_decay=0.01)
+    opt2 = FlatAdamW(other, lr=1e-3, weight_decay=0.0)
+    buf = D.FlatGradBuffer([other, mine])  # `mine` is the SECOND group: its segment starts on a padded boundary
+    topt = torch.optim.AdamW(ref, lr=3e-3, weight_decay=0.01)
+    for it in range(6):
+        for p, r in zip(mine, ref):
+            g = torch.randn_like(p) * (0.1 + it)
+            p.grad.copy_(g)
+            r.grad = g.clone()
+        other[0].grad.fill_(0.5)
+        v0 = [p._version for p in mine]
+        opt.param_groups[0]["lr"] = topt.param_groups[0]["lr"] = 3e-3 * (1 + 0.1 * it)
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(ref, clip)
+        opt.step(max_grad_norm=clip)
+        opt2.step()
+        topt.step()
+        assert all(p._version > v for p, v in zip(mine, v0))
+        for p, r in zip(mine, ref):
+            assert torch.allclose(p, r, rtol=2e-6, atol=2e-7), (it, float((p - r).abs().max()))
+    assert buf.flat.numel() == 36 + sum(p.numel() for p in mine) + (-sum(p.numel() for p in mine)) % 4 + 8
