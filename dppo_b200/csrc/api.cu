@@ -33,6 +33,8 @@ int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float
                            int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
                            const float* chains_in, float* logp, cudaStream_t st);
 
+int small_chain_query_clusters(int H, int D, int Dc, int nb, int S);
+
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // Per-step rows.  DDPM follows reference diffusion_vpg.py:214-223 (+ the chain rule :305-311); DDIM :167-213.
@@ -164,6 +166,8 @@ static int ctx_create_common(dppo_ctx** out, const dppo_mlp_desc* mlp, const dpp
   }
   if (rc == DPPO_OK) {
     c->sample_dim = unet ? c->unet->D : c->g.D;
+    if (!unet && !c->g.CH && !c->g.ln && c->g.H % 64 == 0 && c->S <= 128)
+      c->small_clusters = small_chain_query_clusters(c->g.H, c->g.D, c->g.Dc, c->g.nb, c->S);
     build_rows(c, s);
     int dev_sms = 0;
     if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && dev_sms > 0)

@@ -691,7 +691,7 @@ static LaunchShape pick_shape(const dppo_ctx* ctx, int E) {
     e = getenv("DPPO_B200_CLUSTER");
     env_c = e ? atoi(e) : 0;
   }
-  const int forced_ne = ctx->force_ne ? ctx->force_ne : env_ne, forced_c = ctx->force_c ? ctx->force_c : env_c;
+  const int forced_ne = ctx->force_ne ? ctx->force_ne : env_ne, forced_c = ctx->force_c > 0 ? ctx->force_c : env_c;
   const int max_clusters[4] = {ctx->sm_count, ctx->sm_count / 2, (ctx->sm_count - 16) / 4, 16};  // C = 1, 2, 4, 8
   LaunchShape best{cap, 1};
   double best_t = 1e30;
@@ -738,10 +738,33 @@ static int launch(const ChainArgs& a, size_t smem_bytes, cudaStream_t st) {
   return DPPO_OK;
 }
 
+int small_chain_capacity(const dppo_ctx* ctx);
+int sample_chain_small_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
+                            int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
+                            cudaStream_t st);
+
 int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noise, uint64_t seed, uint64_t offset,
                       int64_t env_offset, int deterministic, int use_base, float min_std, float* traj, float* chain,
                       const float* chains_in, float* logp, cudaStream_t st) {
   const MlpGeom& g = ctx->g;
+  // A handful of environments is pure latency: the weights-stationary cluster kernel (chain_small.cu) takes the call when
+  // its geometry applies.  dppo_debug_set_shape(ctx, 0, -1) forces it, any explicit tile / cluster shape bypasses it,
+  // DPPO_B200_SMALL=0 disables it.
+  {
+    static int env_small = -1;
+    if (env_small < 0) {
+      const char* e = getenv("DPPO_B200_SMALL");
+      env_small = e ? atoi(e) : 1;
+    }
+    const bool forced = ctx->force_c == -1;
+    if (!chains_in && (forced || (env_small && ctx->force_ne == 0 && ctx->force_c == 0))) {
+      bool ok = E <= small_chain_capacity(ctx);
+      for (int w = 0; w < 2 && ok; ++w)
+        for (const float* q : ctx->nets[w].raw) ok = ok && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+      if (ok) return sample_chain_small_impl(ctx, state, E, noise, seed, offset, env_offset, deterministic, use_base, min_std, traj, chain, st);
+      if (forced) return set_error("small chain kernel: geometry, alignment or %d environments outside its range", E), DPPO_ERR_UNSUPPORTED;
+    }
+  }
   ChainArgs a{};
   a.D = g.D, a.Dc_in = g.Dc_in, a.Dc = g.Dc, a.H = g.H, a.nb = g.nb, a.act = g.act, a.ln = g.ln, a.CH = g.CH, a.CO = g.CO;
   a.MT = g.MT, a.KCH = g.KCH, a.KC0 = g.KC0, a.KCc = g.KCc, a.MTc = g.MTc, a.nsplit = g.nsplit;

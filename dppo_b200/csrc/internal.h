@@ -63,6 +63,7 @@ struct PackedNet {
   uint8_t* tiles = nullptr;  // device
   float* side = nullptr;     // device
   bool packed = false;
+  std::vector<const float*> raw;  // the caller's fp32 parameter tensors as of the last pack (device pointers)
 };
 
 }  // namespace dppo
@@ -87,6 +88,7 @@ struct dppo_ctx {
   dppo::ULayer* d_unet_layers = nullptr;
   const float** d_unet_params[2] = {nullptr, nullptr};
   int sample_dim = 0;  // Ta * Da of either denoiser kind
+  int small_clusters = 0;  // 16-CTA clusters of the weights-stationary small-batch kernel the device co-schedules
   int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

@@ -163,6 +163,7 @@ int pack_mlp_impl(dppo_ctx* ctx, int which, const float* const* p, int n_params,
     copy_pad(bo, g.D, net.side + g.off_bout, 128, st);
   }
   if (cudaGetLastError() != cudaSuccess) goto fail;
+  net.raw.assign(p, p + n_params);
   net.packed = true;
   return DPPO_OK;
 fail:

@@ -86,7 +86,7 @@ class FlatGradBuffer:
         groups = [list(g) for g in params] if params and isinstance(params[0], (list, tuple)) else [list(params)]
         groups = [[p for p in g if p.requires_grad] for g in groups]
         self.params = [p for g in groups for p in g]
-        n = sum((sum(p.numel() for p in g) + 3) // 4 * 4 for g in groups)
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)  # every tensor padded to 16 bytes (same layout as FlatAdamW)
         dev = self.params[0].device
         self.flat = torch.zeros(n + n_scalars, dtype=torch.float32, device=dev)
         self.n_grad, self.n_scalars = n, n_scalars
@@ -94,8 +94,7 @@ class FlatGradBuffer:
         for g in groups:
             for p in g:
                 p.grad = self.flat[o:o + p.numel()].view_as(p)
-                o += p.numel()
-            o = (o + 3) // 4 * 4
+                o += (p.numel() + 3) // 4 * 4
 
     @property
     def scalars(self) -> torch.Tensor:

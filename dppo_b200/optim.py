@@ -26,10 +26,11 @@ class FlatAdamW:
         if dev.type != "cuda":
             raise RuntimeError("FlatAdamW runs on CUDA devices only; there is no CPU path")
         self.lib = _lib.load()
-        n = sum(p.numel() for p in self.params)
-        pad = (-n) % 4
+        # every tensor starts on a 16-byte boundary (float4 loads in the kernels that read the parameters in place);
+        # FlatGradBuffer lays the gradients out with the same padding, so one index addresses p, g, m and v
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
         self.n = n
-        self.flat = torch.zeros(n + pad, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         o = 0
         with torch.no_grad():
             for p in self.params:
@@ -38,7 +39,7 @@ class FlatAdamW:
                 k = p.numel()
                 self.flat[o:o + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + k].view_as(p)
-                o += k
+                o += (k + 3) // 4 * 4
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self._ws = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -57,7 +58,7 @@ class FlatAdamW:
         for p in self.params:
             if p.grad is None or p.grad.data_ptr() != ptr or not p.grad.is_contiguous():
                 raise RuntimeError("FlatAdamW needs gradients laid out contiguously in parameter order (FlatGradBuffer)")
-            ptr += p.numel() * 4
+            ptr += (p.numel() + 3) // 4 * 16
         base = first.untyped_storage()
         off = (first.data_ptr() - base.data_ptr()) // 4
         whole = torch.empty(0, dtype=torch.float32, device=first.device).set_(base)
@@ -87,12 +88,12 @@ class FlatAdamW:
                 p.grad.zero_()
 
     def state_dict(self):
-        return dict(step=self.step_count, exp_avg=self.exp_avg[:self.n].clone(), exp_avg_sq=self.exp_avg_sq[:self.n].clone(),
+        return dict(step=self.step_count, exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(),
                     param_groups=[dict(g) for g in self.param_groups])
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
-        self.exp_avg[:self.n].copy_(sd["exp_avg"])
-        self.exp_avg_sq[:self.n].copy_(sd["exp_avg_sq"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         for g, h in zip(self.param_groups, sd["param_groups"]):
             g.update(h)

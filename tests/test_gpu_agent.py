@@ -126,4 +126,4 @@ def test_flat_adamw_matches_torch_adamw(clip):
         assert all(p._version > v for p, v in zip(mine, v0))
         for p, r in zip(mine, ref):
             assert torch.allclose(p, r, rtol=2e-6, atol=2e-7), (it, float((p - r).abs().max()))
-    assert buf.flat.numel() == 36 + sum(p.numel() for p in mine) + (-sum(p.numel() for p in mine)) % 4 + 8
+    assert buf.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in other + mine) + 8  # every tensor padded to 16 bytes

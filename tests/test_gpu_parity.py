@@ -192,3 +192,36 @@ def test_chain_and_logprobs_every_launch_shape(case, tile_envs, cluster):
     with torch.no_grad():
         lp = model.get_logprobs({"state": state}, torch.from_numpy(gold["chains"]).cuda())
     assert_close(lp.cpu().numpy(), gold["logprobs"], 1e-3, f"{case} log-probs NE={tile_envs} C={cluster}", max_frac=2e-3)
+
+
+@pytest.mark.parametrize("case,n_envs", [("hopper", 40), ("hopper", 1), ("hopper", 7), ("walker2d", 48), ("walker2d", 33)])
+def test_small_batch_cluster_kernel_matches_tcgen05_and_oracle(case, n_envs):
+    """Weights-stationary 16-CTA-cluster kernel (chain_small.cu, exact fp32) vs the tcgen05 kernel and the CPU oracle."""
+    from oracle import dppo_oracle as O
+
+    w = get_workload(GOLDEN_CASES[case]["workload"])
+    model = build_model(w, "cuda:0", our_classes())
+    inp = make_inputs(w, n_envs, 16, seed=3)
+    state, noise = inp["state"].cuda(), inp["noise"].cuda()
+    eng = model.engine()
+    eng.set_launch_shape(0, -1)  # force the small-batch kernel (raises if it cannot take the call)
+    small = model(cond={"state": state}, noise=noise)
+    small_det = model(cond={"state": state}, noise=noise, deterministic=True)
+    eng.set_launch_shape(16, 1)  # explicit tcgen05 shape
+    big = model(cond={"state": state}, noise=noise)
+    torch.cuda.synchronize()
+    nc, dc = oracle_cfgs(w)
+    traj_o, chains_o = O.sample_chain(oracle_params(model), nc, dc, inp["state"], inp["noise"], faithful_cost=False)
+    assert_close(small.chains.cpu().numpy(), chains_o.numpy(), 2e-5, f"{case} E={n_envs} small kernel vs oracle")
+    assert_close(small.trajectories.cpu().numpy(), traj_o.numpy(), 2e-5, f"{case} E={n_envs} small kernel traj vs oracle")
+    assert_close(small.chains.cpu().numpy(), big.chains.cpu().numpy(), 1e-3, f"{case} E={n_envs} small vs tcgen05", max_frac=2e-3)
+    assert torch.isfinite(small_det.chains).all()
+    # Philox path: same (seed, offset, env) keys as the tcgen05 kernel -> same draws
+    eng.set_launch_shape(0, -1)
+    torch.manual_seed(5)
+    model._rng_offset = 0
+    a = model(cond={"state": state}).chains
+    eng.set_launch_shape(16, 1)
+    model._rng_offset = 0
+    b = model(cond={"state": state}).chains
+    assert_close(a.cpu().numpy(), b.cpu().numpy(), 1e-3, f"{case} E={n_envs} philox small vs tcgen05", max_frac=2e-3)
