@@ -148,6 +148,10 @@ def ptr(t):
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (raw getter: ~0.3 us instead of ~5 us)."""
     import torch
 
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -108,6 +108,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 __device__ __forceinline__ void st_remote_f32(float* local, uint32_t rank, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_u32(smem_u32(local), rank)), "f"(v) : "memory");
 }
+// 16-byte variant (the address must be 16-byte aligned)
+__device__ __forceinline__ void st_remote_v4(float* local, uint32_t rank, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mapa_u32(smem_u32(local), rank)), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 // acquire at cluster scope: pairs with mbar_arrive_remote of a peer CTA
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

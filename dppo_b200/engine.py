@@ -174,6 +174,7 @@ class ChainEngine:
         create = self.lib.dppo_ctx_create_unet if self.is_unet else self.lib.dppo_ctx_create
         _lib.check(create(C.byref(self.ctx), C.byref(desc), C.byref(sd), _lib.PRECISIONS[precision], idx), "dppo_ctx_create")
         self._packed = {0: None, 1: None}
+        self._plists = {}
         self._ws = torch.zeros(32, dtype=torch.float64, device=dev)
 
     def __del__(self):
@@ -191,8 +192,16 @@ class ChainEngine:
 
     # ------------------------------------------------------------------ weights
     def sync_weights(self, which, net):
-        ps = _unet_param_list(net) if self.is_unet else _mlp_param_list(net)
-        sig = tuple((id(p), p._version, p.data_ptr()) for p in ps)
+        # hot path of every rollout decision: the parameter list is cached per module object and the signature is the
+        # tensors' version counters (every in-place update bumps them; FlatAdamW bumps them explicitly) plus the first
+        # tensor's address (catches a wholesale re-homing of the storage)
+        cached = self._plists.get(which)
+        if cached is None or cached[0] is not net:
+            cached = (net, _unet_param_list(net) if self.is_unet else _mlp_param_list(net))
+            self._plists[which] = cached
+            self._packed[which] = None
+        ps = cached[1]
+        sig = (ps[0].data_ptr(), ps[-1].data_ptr()) + tuple([p._version for p in ps])
         if self._packed[which] == sig:
             return False
         for p in ps:
@@ -208,7 +217,9 @@ class ChainEngine:
     def sample(self, state, noise=None, seed=0, offset=0, env_offset=0, deterministic=False, use_base_policy=False,
                min_sampling_std=0.1, return_chain=True):
         E = state.shape[0]
-        state = state.reshape(E, -1).contiguous().float()
+        if state.dtype != torch.float32 or not state.is_contiguous():
+            state = state.contiguous().float()
+        state = state.view(E, -1)
         traj = torch.empty((E, self.D), dtype=torch.float32, device=state.device)
         chain = torch.empty((E, self.ft + 1, self.D), dtype=torch.float32, device=state.device) if return_chain else None
         if noise is not None:

@@ -39,6 +39,7 @@ class FlatAdamW:
                 k = p.numel()
                 self.flat[o:o + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + k].view_as(p)
+                torch.autograd.graph.increment_version(p)  # derived weight caches key on the version counter
                 o += (k + 3) // 4 * 4
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
