@@ -35,7 +35,7 @@ from dppo_b200 import distributed as D
 from dppo_b200 import engine as E_
 from dppo_b200.optim import FlatAdamW
 from dppo_b200.util.config import instantiate
-from dppo_b200.util.reward_scaling import RunningRewardScaler
+from dppo_b200.util.reward_scaling import RunningRewardScaler, RunningRewardScalerCUDA  # noqa: F401
 
 log = logging.getLogger(__name__)
 
@@ -111,7 +111,8 @@ class TrainPPODiffusionAgent:
         self.vf_coef = cfg.train.get("vf_coef", 0)
         self.reward_scale_running = cfg.train.reward_scale_running
         if self.reward_scale_running:
-            self.running_reward_scaler = RunningRewardScaler(self.n_envs)
+            # device-resident statistics feeding the GAE kernel directly (host mirror: RunningRewardScaler)
+            self.running_reward_scaler = RunningRewardScalerCUDA(self.n_envs, self.device)
         self.reward_scale_const = cfg.train.get("reward_scale_const", 1)
         self.use_bc_loss = cfg.train.get("use_bc_loss", False)
         self.bc_loss_coeff = cfg.train.get("bc_loss_coeff", 0)
@@ -193,12 +194,13 @@ class TrainPPODiffusionAgent:
             values[s:e] = self.model.critic({"state": obs_k[s:e]}).view(-1)
             logprobs[s:e] = self.model.get_logprobs({"state": obs_k[s:e]}, chains_k[s:e]).view(e - s, ft, self.horizon_steps,
                                                                                              self.action_dim)
+        f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)  # noqa: E731
+        reward_dev = f64(reward_trajs)
         if self.reward_scale_running:
-            reward_trajs = self.running_reward_scaler(reward=reward_trajs.T, first=firsts_trajs[:-1].T).T
+            reward_dev = self.running_reward_scaler(reward=reward_dev, first=f64(firsts_trajs[:-1]))
         next_value = self.model.critic({"state": torch.from_numpy(np.ascontiguousarray(last_obs["state"], dtype=np.float32))
                                         .to(self.device)}).view(-1)
-        f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)  # noqa: E731
-        adv, ret = E_.gae(f64(reward_trajs), f64(terminated_trajs), values.view(n, E).double(), next_value.double(),
+        adv, ret = E_.gae(reward_dev, f64(terminated_trajs), values.view(n, E).double(), next_value.double(),
                           self.gamma, self.gae_lambda, self.reward_scale_const)
         return values.view(n, E), logprobs.view(n, E, ft, self.horizon_steps, self.action_dim), adv.float(), ret.float()
 

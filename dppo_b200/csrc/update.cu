@@ -378,9 +378,99 @@ __global__ void adamw_kernel(const AdamArgs a) {
   for (long long i = (n4 << 2) + i0; i < a.n; i += stride) adamw_one(a.p[i], a.g[i], a.m[i], a.v[i], a, coef);
 }
 
+
+// ---------------------------------------------------------------------------------------------- running reward scaling
+// RunningRewardScaler (reference dppo/util/reward_scaling.py:42-87, called at train_ppo_diffusion_agent.py:243-247):
+// rets_t = r_t + (1 - first_t) gamma rets_{t-1} per env (forward scan, one thread per env, coalesced over envs), batch
+// mean / variance of all rets folded into the running statistics (parallel-variance update), rewards divided by
+// sqrt(var + eps) and clipped.  float64 like the reference's numpy.  Three phases so that an env-sharded run can
+// all-reduce the two batch sums in between (ws[0] = sum, ws[1] = centred sum of squares).
+__global__ void reward_scan_kernel(const double* __restrict__ reward, const double* __restrict__ first, int n_steps, int E,
+                                   double gamma, double* __restrict__ ret_state, double* __restrict__ rets,
+                                   double* __restrict__ ws) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double sum = 0.0;
+  if (e < E) {
+    double prev = ret_state[e];
+    for (int t = 0; t < n_steps; ++t) {
+      const size_t i = size_t(t) * E + e;
+      prev = reward[i] + (1.0 - first[i]) * gamma * prev;
+      rets[i] = prev;
+      sum += prev;
+    }
+    ret_state[e] = prev;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&ws[0], sum);
+}
+
+__global__ void reward_centred_sq_kernel(const double* __restrict__ rets, long long n, long long n_global,
+                                         double* __restrict__ ws) {
+  const double mean = ws[0] / double(n_global);
+  double acc = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double d = rets[i] - mean;
+    acc += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&ws[1], acc);
+}
+
+// stats = [mean, var, count]; thread 0 of block 0 folds the batch in, every thread then scales its rewards with the
+// NEW variance (the reference updates the statistics before scaling)
+__global__ void reward_apply_kernel(const double* __restrict__ reward, long long n, long long n_global, double eps,
+                                    double cliprew, const double* __restrict__ ws, double* __restrict__ stats,
+                                    double* __restrict__ out) {
+  const double b_n = double(n_global);
+  const double b_mean = ws[0] / b_n, b_var = ws[1] / b_n;
+  const double mean = stats[0], var = stats[1], count = stats[2];
+  const double delta = b_mean - mean, tot = count + b_n;
+  const double m2 = var * count + b_var * b_n + delta * delta * count * b_n / tot;
+  const double new_var = m2 / (tot - 1.0);
+  const double inv = 1.0 / sqrt(new_var + eps);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = fmin(fmax(reward[i] * inv, -cliprew), cliprew);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // every block has read stats[] above only through registers of its own threads; the update is published through
+    // ws[2..4] and copied back by the host-ordered follow-up memcpy, so no block can observe a half-updated state
+    double* nxt = const_cast<double*>(ws) + 2;
+    nxt[0] = mean + delta * b_n / tot, nxt[1] = new_var, nxt[2] = tot;
+  }
+}
+
 }  // namespace dppo
 
 using namespace dppo;
+
+extern "C" int dppo_reward_scale_f64(const double* reward, const double* first, int n_steps, int n_envs, long long n_global,
+                                     double gamma, double epsilon, double cliprew, double* ret_state, double* stats,
+                                     double* rets_scratch, double* ws, double* scaled, int phase, void* stream) {
+  if (!reward || !first || !ret_state || !stats || !rets_scratch || !ws || !scaled)
+    return set_error("dppo_reward_scale_f64: null argument"), DPPO_ERR_INVALID;
+  if (n_steps < 1 || n_envs < 1 || n_global < (long long)n_steps * n_envs)
+    return set_error("dppo_reward_scale_f64: bad sizes %d x %d of %lld", n_steps, n_envs, n_global), DPPO_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)n_steps * n_envs;
+  int blocks = int((n + 255) / 256);
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  if (phase == 0) {
+    DPPO_CUDA(cudaMemsetAsync(ws, 0, 8 * sizeof(double), st));
+    reward_scan_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(reward, first, n_steps, n_envs, gamma, ret_state, rets_scratch, ws);
+  } else if (phase == 1) {
+    reward_centred_sq_kernel<<<blocks, 256, 0, st>>>(rets_scratch, n, n_global, ws);
+  } else if (phase == 2) {
+    reward_apply_kernel<<<blocks, 256, 0, st>>>(reward, n, n_global, epsilon, cliprew, ws, stats, scaled);
+    DPPO_CUDA(cudaMemcpyAsync(stats, ws + 2, 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  } else {
+    return set_error("dppo_reward_scale_f64: phase %d", phase), DPPO_ERR_INVALID;
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "dppo_reward_scale_f64 launch");
+}
 
 extern "C" int dppo_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                                float lr, float beta1, float beta2, float eps, float weight_decay, int step,

@@ -207,6 +207,20 @@ int dppo_gae_f64(const double* reward, const double* terminated, const double* v
                  int n_steps, int n_envs, double gamma, double gae_lambda, double reward_scale_const,
                  double* advantages, double* returns, void* stream);
 
+/* ---- running reward scaling ----------------------------------------------------------------------------------- */
+/* RunningRewardScaler.__call__ (dppo/util/reward_scaling.py:42-87; call site train_ppo_diffusion_agent.py:243-247) on
+ * the device, float64, (n_steps, n_envs) row-major like the GAE inputs it feeds:
+ *   phase 0  per-env forward scan rets_t = r_t + (1 - first_t) gamma rets_{t-1} from ret_state[n_envs] (updated),
+ *            rets -> rets_scratch, ws[0] = sum(rets)
+ *   phase 1  ws[1] = sum((rets - ws[0] / n_global)^2)
+ *   phase 2  stats[3] = (mean, var, count) <- parallel-variance update with the batch (ws[0..1], n_global);
+ *            scaled = clip(reward / sqrt(var_new + epsilon), +-cliprew)
+ * A single process calls the phases back to back with n_global = n_steps * n_envs; env-sharded ranks all-reduce
+ * ws[0] after phase 0 and ws[1] after phase 1 and pass the global element count.  ws: >= 8 doubles.              */
+int dppo_reward_scale_f64(const double* reward, const double* first, int n_steps, int n_envs, long long n_global,
+                          double gamma, double epsilon, double cliprew, double* ret_state, double* stats,
+                          double* rets_scratch, double* ws, double* scaled, int phase, void* stream);
+
 /* ---- optimiser ------------------------------------------------------------------------------------------------ */
 /* torch.optim.AdamW step (train_ppo_diffusion_agent.py:360-373, optimisers built at train_ppo_agent.py:34-53) over ONE
  * flat fp32 segment: params / grads / exp_avg / exp_avg_sq are 16-byte aligned device arrays of n floats (the gradient

@@ -127,3 +127,91 @@ def test_flat_adamw_matches_torch_adamw(clip):
         for p, r in zip(mine, ref):
             assert torch.allclose(p, r, rtol=2e-6, atol=2e-7), (it, float((p - r).abs().max()))
     assert buf.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in other + mine) + 8  # every tensor padded to 16 bytes
+
+
+def test_reward_scaler_kernel_matches_host_mirror():
+    """dppo_reward_scale_f64 (three phases) == RunningRewardScaler over successive iterations, state included."""
+    from dppo_b200.util.reward_scaling import RunningRewardScaler, RunningRewardScalerCUDA
+
+    rng = np.random.default_rng(9)
+    for n, E in [(500, 40), (7, 1), (88, 1000)]:
+        host, dev = RunningRewardScaler(E), RunningRewardScalerCUDA(E, "cuda:0")
+        for it in range(3):
+            r = rng.standard_normal((n, E)) * (1 + 5 * it)
+            first = (rng.random((n, E)) < 0.03).astype(np.float64)
+            first[0] = it == 0
+            want = host(reward=r.T, first=first.T).T
+            got = dev(reward=torch.from_numpy(r).cuda(), first=torch.from_numpy(first).cuda())
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
+            hs, ds = host.state_dict(), dev.state_dict()
+            np.testing.assert_allclose(ds["ret"], hs["ret"], rtol=1e-12, atol=1e-12)
+            for k in ("mean", "var", "count"):
+                assert abs(ds[k] - hs[k]) <= 1e-11 * max(1.0, abs(hs[k])), (k, ds[k], hs[k])
+        fresh = RunningRewardScalerCUDA(E, "cuda:0")
+        fresh.load_state_dict(host.state_dict())
+        assert abs(fresh.state_dict()["var"] - host.var) <= 1e-15 * max(1.0, host.var)
+
+
+@pytest.mark.parametrize("workload", ["hopper", "furniture", "square_unet"])
+def test_diffusion_eval_loads_checkpoint_and_matches_rollout_model(tmp_path, workload):
+    """DiffusionEval (checkpoint key remapping, base + fine-tuned nets) samples what PPODiffusion samples deterministically."""
+    from dppo_b200.model.diffusion.diffusion_eval import DiffusionEval
+    from tests.helpers import build_model, make_inputs, our_classes
+
+    w = get_workload(workload)
+    model = build_model(w, "cuda:0", our_classes())
+    path = tmp_path / "state.pt"
+    torch.save({"itr": 3, "model": model.state_dict()}, path)
+    cls = our_classes()
+    a = dict(w["actor"])
+    kind = a.pop("kind")
+    cond_dim = w["obs_dim"] * w["cond_steps"]
+    net = (cls["mlp"](action_dim=w["action_dim"], horizon_steps=w["horizon_steps"], cond_dim=cond_dim, **a) if kind == "mlp"
+           else cls["unet"](action_dim=w["action_dim"], cond_dim=cond_dim, **a))
+    ev = DiffusionEval(network_path=str(path), ft_denoising_steps=w["ft_denoising_steps"], network=net,
+                       horizon_steps=w["horizon_steps"], obs_dim=w["obs_dim"], action_dim=w["action_dim"], device="cuda:0",
+                       denoising_steps=w["denoising_steps"], use_ddim=w["use_ddim"], ddim_steps=w["ddim_steps"],
+                       randn_clip_value=w["ppo"]["randn_clip_value"])
+    inp = make_inputs(w, 24, 8)
+    state, noise = inp["state"].cuda(), inp["noise"].cuda()
+    got = ev(cond={"state": state}, deterministic=True, noise=noise)
+    want = model(cond={"state": state}, deterministic=True, noise=noise)
+    assert got.chains is None and torch.equal(got.trajectories, want.trajectories)
+    # a pre-training checkpoint (network.* only) needs ft_denoising_steps = 0
+    torch.save({"model": {k: v for k, v in model.state_dict().items() if k.startswith("network.")}}, path)
+    with pytest.raises(ValueError):
+        DiffusionEval(network_path=str(path), ft_denoising_steps=2, network=net, horizon_steps=w["horizon_steps"],
+                      obs_dim=w["obs_dim"], action_dim=w["action_dim"], device="cuda:0", denoising_steps=w["denoising_steps"],
+                      use_ddim=w["use_ddim"], ddim_steps=w["ddim_steps"])
+    pre = DiffusionEval(network_path=str(path), ft_denoising_steps=0, network=net, horizon_steps=w["horizon_steps"],
+                        obs_dim=w["obs_dim"], action_dim=w["action_dim"], device="cuda:0", denoising_steps=w["denoising_steps"],
+                        use_ddim=w["use_ddim"], ddim_steps=w["ddim_steps"], randn_clip_value=w["ppo"]["randn_clip_value"])
+    base = model(cond={"state": state}, deterministic=True, noise=noise, use_base_policy=True)
+    assert torch.equal(pre(cond={"state": state}, noise=noise).trajectories, base.trajectories)
+
+
+def test_eval_agent_runs_on_the_synthetic_env(tmp_path):
+    from dppo_b200.agent.eval.eval_diffusion_agent import EvalDiffusionAgent
+    from dppo_b200.util.config import Cfg
+    from tests.helpers import build_model, our_classes
+
+    w = get_workload("hopper")
+    model = build_model(w, "cuda:0", our_classes())
+    path = tmp_path / "state.pt"
+    torch.save({"itr": 0, "model": model.state_dict()}, path)
+    cond_dim = w["obs_dim"] * w["cond_steps"]
+    a = dict(w["actor"])
+    a.pop("kind")
+    cfg = Cfg(device="cuda:0", seed=7, logdir=str(tmp_path), obs_dim=w["obs_dim"], action_dim=w["action_dim"],
+              cond_steps=w["cond_steps"], act_steps=w["act_steps"], horizon_steps=w["horizon_steps"], n_steps=30,
+              env=dict(n_envs=6, name="synthetic", max_episode_steps=40, best_reward_threshold_for_success=0.1),
+              model={"_target_": "dppo_b200.model.diffusion.diffusion_eval.DiffusionEval", "network_path": str(path),
+                     "ft_denoising_steps": w["ft_denoising_steps"], "horizon_steps": w["horizon_steps"], "obs_dim": w["obs_dim"],
+                     "action_dim": w["action_dim"], "device": "cuda:0", "denoising_steps": w["denoising_steps"],
+                     "randn_clip_value": w["ppo"]["randn_clip_value"],
+                     "network": dict({"_target_": "dppo_b200.model.diffusion.mlp_diffusion.DiffusionMLP",
+                                      "action_dim": w["action_dim"], "horizon_steps": w["horizon_steps"], "cond_dim": cond_dim}, **a)})
+    res = EvalDiffusionAgent(cfg).run()
+    assert res["num_episode"] >= 6 and np.isfinite(res["eval_episode_reward"]) and 0.0 <= res["eval_success_rate"] <= 1.0
+    saved = np.load(tmp_path / "eval.npz")
+    assert int(saved["num_episode"]) == res["num_episode"]
