@@ -118,7 +118,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
   s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
-  s.can_send = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.can_send = reinterpret_cast<uint64_t*>(p), p += 16;  // two barriers, used alternately (see wait_layer)
   s.ln_bar = reinterpret_cast<uint64_t*>(p), p += 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
   s.ln_part = reinterpret_cast<float*>(p), p += kEpiWarps * 2 * 32 * 4;
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     }
     mbar_init(s.layer_done, 1);
     mbar_init(s.x_full, 1);
-    mbar_init(s.can_send, C > 1 ? C - 1 : 1);
+    mbar_init(&s.can_send[0], C > 1 ? C - 1 : 1);
+    mbar_init(&s.can_send[1], C > 1 ? C - 1 : 1);
     mbar_init(s.ln_bar, C * NE);
     fence_mbar_init();
   }
@@ -299,7 +300,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
 
     long long e_wait = 0, e_hand = 0;
     const long long e_t0 = clock64();
-    uint32_t cs_phase = 0;
+    // Handshakes alternate between TWO barriers.  Consecutive handshakes are not always separated by an all-to-all data
+    // dependency: the output layer ends with a handshake but no push, and layer 0 of the next step runs on the local x0
+    // operand, so a fast peer can send its NEXT handshake arrival while a slow peer has not sent the current one.  With a
+    // single barrier that early arrival completes the current phase prematurely, blocks get pushed into a copy of X
+    // that is still being read and the transaction counts of x_full drift until a wait never completes (seen once per
+    // ~3000 launches).  A peer can be at most one handshake ahead (the next one needs everybody's push), so two suffice.
+    uint32_t cs_phase[2] = {0u, 0u}, hs = 0;
     // `handshake`: this epilogue overwrites parts of X (its column block, or the s_eps alias), so (a) the peers must have
     // consumed the block pushed earlier and (b) they must be done reading their copy before a new block is pushed
     auto wait_layer = [&](bool exchange) {
@@ -310,15 +317,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       tc_fence_after();
       if (exchange && C > 1) {
         // this CTA's MMAs no longer read its copy of X: the peers may overwrite their column blocks in it ...
+        uint64_t* bar = &s.can_send[hs & 1u];
         if (et == 0)
           for (uint32_t p = 0; p < uint32_t(C); ++p)
-            if (p != rank) mbar_arrive_remote(s.can_send, p);
+            if (p != rank) mbar_arrive_remote(bar, p);
         // ... and once every peer says the same, (a) the block this CTA pushed after the previous layer has been
         // consumed, so its source may be overwritten, and (b) the new block may be pushed into the peers' copies
         const long long th = clock64();
-        mbar_wait_cluster(s.can_send, cs_phase);
+        mbar_wait_cluster(bar, hs & 1u ? cs_phase[1] : cs_phase[0]);
         e_hand += clock64() - th;
-        cs_phase ^= 1;
+        if (hs & 1u) cs_phase[1] ^= 1u; else cs_phase[0] ^= 1u;
+        ++hs;
       }
     };
     // hand the operand written by this epilogue over to the MMA warp (and, for an exchange layer, to the peers)
