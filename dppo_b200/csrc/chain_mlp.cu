@@ -368,6 +368,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // TWO consecutive features of one env row: one packed bf16x2 convert and one 4-byte store per operand half.
     const uint32_t odd = lane & 1;
     uint32_t ln_phase = 0;
+    // Per-feature constants (bias, LayerNorm gain / shift) of the first four M tiles are fetched BEFORE the wait for the
+    // layer's MMAs: they come from the L2-resident side table (the L1 is a few KB next to 220 KB of shared memory), and
+    // a load issued after tcgen05.ld would put ~700 cycles of L2 latency on the critical path of every M tile.
+    float pre_b[4], pre_g[4], pre_be[4];
+    auto prefetch_side = [&](int mt_first, int MTl, const float* bias_a, const float* bias_b, const float* ln_g,
+                             const float* ln_b) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = (mt_first + (i < MTl ? i : 0)) * 128 + fl;
+        pre_b[i] = bias_a[f] + (bias_b ? bias_b[f] : 0.f);
+        pre_g[i] = (LN && ln_g != nullptr) ? ln_g[f] : 1.f;
+        pre_be[i] = (LN && ln_g != nullptr) ? ln_b[f] : 0.f;
+      }
+    };
     // `whole_row`: this CTA holds every feature of the layer (cond_mlp), otherwise they are split over the cluster
     auto epi_hidden = [&](uint32_t region, int mt_first, int MTl, const float* bias_a, const float* bias_b, bool identity,
                           const float* ln_g, const float* ln_b, bool whole_row) {
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           float v[CPT];
           tmem_ld(tmem + lane_addr + region + uint32_t(mt) * NE + col0, v);
           const int f = (mt_first + mt) * 128 + fl;
-          const float b = bias_a[f] + (bias_b ? bias_b[f] : 0.f);
+          const float b = mt < 4 ? pre_b[mt & 3] : bias_a[f] + (bias_b ? bias_b[f] : 0.f);
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
             const float x = v[c] + b;
@@ -453,9 +467,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         float v[CPT];
         tmem_ld(tmem + lane_addr + region + uint32_t(mt) * NE + col0, v);
         const int f = (mt_first + mt) * 128 + fl;
-        const float b = bias_a[f] + (bias_b ? bias_b[f] : 0.f);
+        const float b = mt < 4 ? pre_b[mt & 3] : bias_a[f] + (bias_b ? bias_b[f] : 0.f);
         float g = 1.f, be = 0.f;
-        if (LN && ln_g != nullptr) g = ln_g[f], be = ln_b[f];
+        if (LN && ln_g != nullptr) g = mt < 4 ? pre_g[mt & 3] : ln_g[f], be = mt < 4 ? pre_be[mt & 3] : ln_b[f];
         const uint32_t kp = uint32_t(f) & ~1u;  // first feature of the pair this thread stores
         const uint32_t j16 = (kp & 63u) >> 3;
         const uint32_t base = (kp >> 6) * (NE * 128u) + ((kp & 7u) << 1) + (uint32_t(col0) + odd) * 128u;
@@ -574,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             identity = true;  // no activation between the last block and the output layer
           }
         }
+        prefetch_side(mt_first, MTl, ba, bb, lg, lb);
         wait_layer(L >= 0);
         epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0);
         signal_x(L >= 0);
@@ -584,6 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       // quarter holds valid features move it (+ bias) to a [env][feature] fp32 tile in shared memory (aliasing X, which
       // the completed output-layer MMAs no longer read), then ALL epilogue threads run the posterior on the flat mapping.
       // Every CTA of a cluster does this redundantly (same inputs, same noise); rank 0 alone writes to global memory.
+      const float bo = fl < a.D ? side[a.off_bout + fl] : 0.f;  // fetched while the output-layer MMAs run
       wait_layer(true);
       {
         float* s_eps = reinterpret_cast<float*>(s.x_hi);
@@ -591,7 +607,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           float v[CPT];
           tmem_ld(tmem + lane_addr + col_y + col0, v);
           if (fl < a.D) {
-            const float bo = side[a.off_bout + fl];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) s_eps[(col0 + c) * a.D + fl] = v[c] + bo;
           }
