@@ -19,7 +19,7 @@ PRECISIONS = {"split3": PRECISION_SPLIT3, "bf16": PRECISION_BF16}
 EXPORTS = [
     "dppo_last_error", "dppo_version", "dppo_ctx_create", "dppo_ctx_destroy", "dppo_pack_mlp", "dppo_ctx_create_unet",
     "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain",
-    "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64", "dppo_reward_scale_f64", "dppo_adamw_flat",
+    "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64", "dppo_split3_pack", "dppo_reward_scale_f64", "dppo_adamw_flat",
     "dppo_selftest_umma",
 ]
 
@@ -121,6 +121,7 @@ def load(build_if_missing=True):
                                           vp, vp, vp]
     lib.dppo_ppo_loss_rows.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(LossHp), vp, vp, vp, vp, vp]
     lib.dppo_gae_f64.argtypes = [vp, vp, vp, vp, i32, i32, f64, f64, f64, vp, vp, vp]
+    lib.dppo_split3_pack.argtypes = [vp, i64, i32, i64, vp, i32, vp]
     lib.dppo_reward_scale_f64.argtypes = [vp, vp, i32, i32, C.c_longlong, f64, f64, f64, vp, vp, vp, vp, vp, i32, vp]
     lib.dppo_adamw_flat.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp]
     lib.dppo_selftest_umma.argtypes = [vp, vp, vp, vp, i32, i32, u64, C.c_uint32, vp]

@@ -442,9 +442,58 @@ __global__ void reward_apply_kernel(const double* __restrict__ reward, long long
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- split-3 operand packing
+// Update-path GEMMs (actor_ft / critic Linear layers, forward + dgrad + wgrad; reference get_logprobs_subsample
+// diffusion_vpg.py:398-461, CriticObs.forward critic.py:40-54, loss.backward() train_ppo_diffusion_agent.py:360-364)
+// run on the bf16 tensor cores at fp32-grade precision with the same 3-product split as the chain kernel:
+// x w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi.  One pass turns an fp32 matrix [M, K] into the bf16 matrix [M, 3 Kp]
+// (Kp = K rounded up to 8, zero padded) whose row is [hi | hi | lo] (pattern 0, activations / gradients) or
+// [hi | lo | hi] (pattern 1, weights): a single bf16 GEMM with fp32 accumulation over the 3 Kp-long rows is then the
+// whole split product.  HBM-bound: 4 B read + 6 B written per element.
+__global__ void split3_pack_kernel(const float* __restrict__ x, long long M, int K, long long ldx, int Kp, int pattern,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int q = Kp >> 2;  // groups of 4 columns per row
+  const long long total = M * q;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / q;
+    const int c = int(i - r * q) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = c + j < K ? x[r * ldx + c + j] : 0.f;
+    __align__(8) __nv_bfloat16 hi[4];
+    __align__(8) __nv_bfloat16 lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+    __nv_bfloat16* row = out + r * 3 * (long long)Kp + c;
+    const uint2 h = *reinterpret_cast<const uint2*>(hi), l = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(row) = h;
+    *reinterpret_cast<uint2*>(row + Kp) = pattern == 0 ? h : l;
+    *reinterpret_cast<uint2*>(row + 2 * Kp) = pattern == 0 ? l : h;
+  }
+}
+
 }  // namespace dppo
 
 using namespace dppo;
+
+extern "C" int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, void* out, int pattern, void* stream) {
+  if (!x || !out) return set_error("dppo_split3_pack: null argument"), DPPO_ERR_INVALID;
+  if (rows < 0 || cols < 1 || ldx < cols || (pattern != 0 && pattern != 1))
+    return set_error("dppo_split3_pack: rows=%lld cols=%d ldx=%lld pattern=%d", (long long)rows, cols, (long long)ldx, pattern),
+           DPPO_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(out) & 7) return set_error("dppo_split3_pack: output must be 8-byte aligned"), DPPO_ERR_INVALID;
+  if (rows == 0) return DPPO_OK;
+  const int Kp = (cols + 7) & ~7;
+  const long long total = rows * (Kp / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split3_pack_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols, ldx, Kp, pattern,
+                                                                                     static_cast<__nv_bfloat16*>(out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "split3_pack_kernel launch");
+}
 
 extern "C" int dppo_reward_scale_f64(const double* reward, const double* first, int n_steps, int n_envs, long long n_global,
                                      double gamma, double epsilon, double cliprew, double* ret_state, double* stats,

@@ -9,13 +9,17 @@ parameter-creation order (hence seeded initialisation) are identical:
   TwoLayerPreActivationResNetLinear   -> /root/reference/dppo/model/common/mlp.py:128-154
 
 The `forward` methods here are the autograd (update-path) implementation; the rollout path never calls them, it
-runs the packed weights through the sm_100a denoise-chain kernel (dppo_b200/csrc/chain_kernel.cu).
+runs the packed weights through the sm_100a denoise-chain kernels (dppo_b200/csrc/chain_*.cu).  Every Linear is a
+SplitLinear: on CUDA its forward / dgrad / wgrad GEMMs run on the bf16 tensor cores with the 3-product split
+(fp32-grade), see split_linear.py.
 """
 
 from collections import OrderedDict
 
 import torch
 from torch import nn
+
+from dppo_b200.model.common.split_linear import SplitLinear
 
 _ACTIVATIONS = {
     "ReLU": nn.ReLU,
@@ -62,7 +66,7 @@ class MLP(nn.Module):
                 fan_in += append_dim
             last = k == n_stage - 1
             parts = OrderedDict()
-            parts["linear_1"] = nn.Linear(fan_in, fan_out)
+            parts["linear_1"] = SplitLinear(fan_in, fan_out)
             if use_layernorm and (not last or use_layernorm_final):
                 parts["norm_1"] = nn.LayerNorm(fan_out)
             if dropout > 0 and (not last or use_drop_final):
@@ -84,8 +88,8 @@ class TwoLayerPreActivationResNetLinear(nn.Module):
 
     def __init__(self, hidden_dim, activation_type="Mish", use_layernorm=False, dropout=0):
         super().__init__()
-        self.l1 = nn.Linear(hidden_dim, hidden_dim)
-        self.l2 = nn.Linear(hidden_dim, hidden_dim)
+        self.l1 = SplitLinear(hidden_dim, hidden_dim)
+        self.l2 = SplitLinear(hidden_dim, hidden_dim)
         self.act = make_activation(activation_type)
         if use_layernorm:
             self.norm1 = nn.LayerNorm(hidden_dim, eps=1e-06)
@@ -121,7 +125,7 @@ class ResidualMLP(nn.Module):
         self.hidden_dim = hidden
         self.activation_type = activation_type
         self.use_layernorm = use_layernorm
-        seq = [nn.Linear(dim_list[0], hidden)]
+        seq = [SplitLinear(dim_list[0], hidden)]
         for _ in range(n_hidden_linear // 2):
             seq.append(
                 TwoLayerPreActivationResNetLinear(
@@ -131,7 +135,7 @@ class ResidualMLP(nn.Module):
                     dropout=dropout,
                 )
             )
-        seq.append(nn.Linear(hidden, dim_list[-1]))
+        seq.append(SplitLinear(hidden, dim_list[-1]))
         if use_layernorm_final:
             seq.append(nn.LayerNorm(dim_list[-1]))
         seq.append(make_activation(out_activation_type))

@@ -207,6 +207,15 @@ int dppo_gae_f64(const double* reward, const double* terminated, const double* v
                  int n_steps, int n_envs, double gamma, double gae_lambda, double reward_scale_const,
                  double* advantages, double* returns, void* stream);
 
+/* ---- update-path GEMM operands --------------------------------------------------------------------------------- */
+/* fp32 [rows, cols] (row stride ldx) -> bf16 [rows, 3 * cols_p], cols_p = cols rounded up to 8 (zero padded), each row
+ * [hi | hi | lo] (pattern 0: activations, gradients) or [hi | lo | hi] (pattern 1: weights), hi = bf16(x),
+ * lo = bf16(x - hi).  A bf16 GEMM with fp32 accumulation over these rows is the 3-product split
+ * x w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi the chain kernel uses, i.e. fp32-grade Linear layers (forward, dgrad, wgrad
+ * of actor_ft / critic: diffusion_vpg.py:398-461, critic.py:40-54, train_ppo_diffusion_agent.py:360-364) on the tensor
+ * cores instead of fp32 SIMT GEMMs.  `out` must be 8-byte aligned.                                                  */
+int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, void* out, int pattern, void* stream);
+
 /* ---- running reward scaling ----------------------------------------------------------------------------------- */
 /* RunningRewardScaler.__call__ (dppo/util/reward_scaling.py:42-87; call site train_ppo_diffusion_agent.py:243-247) on
  * the device, float64, (n_steps, n_envs) row-major like the GAE inputs it feeds:
