@@ -333,7 +333,8 @@ def bench_update(args, w, model, dev, E, rank, world):
     return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
             "minibatch_rows": per_rank * world, "buffer_rows": N * ft,
             "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
-                     "network GEMMs via torch autograd (cuBLAS fp32); fused flat AdamW kernel per network")}
+                     "Linear layers as 3-product bf16-split tensor-core GEMMs (dppo_split3_pack + cuBLASLt bf16, fp32 accumulate) under "
+                     "torch autograd; fused flat AdamW kernel per network")}
 
 
 def main():

@@ -121,7 +121,7 @@ def load(build_if_missing=True):
                                           vp, vp, vp]
     lib.dppo_ppo_loss_rows.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(LossHp), vp, vp, vp, vp, vp]
     lib.dppo_gae_f64.argtypes = [vp, vp, vp, vp, i32, i32, f64, f64, f64, vp, vp, vp]
-    lib.dppo_split3_pack.argtypes = [vp, i64, i32, i64, vp, i32, vp]
+    lib.dppo_split3_pack.argtypes = [vp, i64, i32, i64, i32, vp, vp, i32, vp]
     lib.dppo_reward_scale_f64.argtypes = [vp, vp, i32, i32, C.c_longlong, f64, f64, f64, vp, vp, vp, vp, vp, i32, vp]
     lib.dppo_adamw_flat.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp]
     lib.dppo_selftest_umma.argtypes = [vp, vp, vp, vp, i32, i32, u64, C.c_uint32, vp]

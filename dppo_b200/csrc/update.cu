@@ -451,8 +451,10 @@ __global__ void reward_apply_kernel(const double* __restrict__ reward, long long
 // (Kp = K rounded up to 8, zero padded) whose row is [hi | hi | lo] (pattern 0, activations / gradients) or
 // [hi | lo | hi] (pattern 1, weights): a single bf16 GEMM with fp32 accumulation over the 3 Kp-long rows is then the
 // whole split product.  HBM-bound: 4 B read + 6 B written per element.
+// extra_mode 1 appends a column of ones (activations: the bias rides along as one more K column of the weights, and the
+// wgrad GEMM's last column is the bias gradient), extra_mode 2 appends extra[r] (weights: the bias vector).
 __global__ void split3_pack_kernel(const float* __restrict__ x, long long M, int K, long long ldx, int Kp, int pattern,
-                                   __nv_bfloat16* __restrict__ out) {
+                                   int extra_mode, const float* __restrict__ extra, __nv_bfloat16* __restrict__ out) {
   const int q = Kp >> 2;  // groups of 4 columns per row
   const long long total = M * q;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -461,7 +463,10 @@ __global__ void split3_pack_kernel(const float* __restrict__ x, long long M, int
     const int c = int(i - r * q) * 4;
     float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = c + j < K ? x[r * ldx + c + j] : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      v[j] = c + j < K ? x[r * ldx + c + j] : 0.f;
+      if (extra_mode && c + j == K) v[j] = extra_mode == 1 ? 1.f : extra[r];
+    }
     __align__(8) __nv_bfloat16 hi[4];
     __align__(8) __nv_bfloat16 lo[4];
 #pragma unroll
@@ -478,19 +483,22 @@ __global__ void split3_pack_kernel(const float* __restrict__ x, long long M, int
 
 using namespace dppo;
 
-extern "C" int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, void* out, int pattern, void* stream) {
+extern "C" int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, int extra_mode, const float* extra,
+                                void* out, int pattern, void* stream) {
   if (!x || !out) return set_error("dppo_split3_pack: null argument"), DPPO_ERR_INVALID;
+  if (extra_mode < 0 || extra_mode > 2 || (extra_mode == 2 && !extra))
+    return set_error("dppo_split3_pack: extra_mode %d", extra_mode), DPPO_ERR_INVALID;
   if (rows < 0 || cols < 1 || ldx < cols || (pattern != 0 && pattern != 1))
     return set_error("dppo_split3_pack: rows=%lld cols=%d ldx=%lld pattern=%d", (long long)rows, cols, (long long)ldx, pattern),
            DPPO_ERR_INVALID;
   if (reinterpret_cast<uintptr_t>(out) & 7) return set_error("dppo_split3_pack: output must be 8-byte aligned"), DPPO_ERR_INVALID;
   if (rows == 0) return DPPO_OK;
-  const int Kp = (cols + 7) & ~7;
+  const int Kp = (cols + (extra_mode ? 1 : 0) + 7) & ~7;
   const long long total = rows * (Kp / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  split3_pack_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols, ldx, Kp, pattern,
-                                                                                     static_cast<__nv_bfloat16*>(out));
+  split3_pack_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, cols, ldx, Kp, pattern, extra_mode, extra, static_cast<__nv_bfloat16*>(out));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "split3_pack_kernel launch");
 }

@@ -8,8 +8,8 @@ The update path of DPPO (PPODiffusion.loss -> get_logprobs_subsample -> actor_ft
 3-product split the chain kernel uses, x w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi (bf16 halves, fp32 accumulation):
 `dppo_split3_pack` (libdppo_b200) writes [hi | hi | lo] / [hi | lo | hi] operand rows in one pass, and ONE bf16 GEMM
 over the 3K-long rows (a plain library GEMM: torch.mm(..., out_dtype=float32) -> cuBLASLt) is the whole product.
-forward: y = x W^T + b;  backward: dx = dy W (same trick on dy and W^T), dW = dy^T x (three small-output GEMMs on
-the hi / lo column blocks of the packed operands), db = column sums.  Parameters, names and state_dict are nn.Linear's.
+forward: y = [x | 1] [W | b]^T (the bias rides along as one more K column);  backward: dx = dy W (same trick on dy and
+W^T), [dW | db] = dy^T [x | 1] (three small-output GEMMs on the hi / lo column blocks of the packed operands).  Parameters, names and state_dict are nn.Linear's.
 On CPU tensors (oracle / host-logic tests) the module is plain F.linear.
 """
 
@@ -24,15 +24,16 @@ from dppo_b200 import _lib
 ENABLED = True  # module-level switch (tests compare both paths)
 
 
-def _pack(x2d, pattern):
-    """fp32 [M, K] (unit column stride) -> bf16 [M, 3 * Kp]"""
+def _pack(x2d, pattern, ones=False, extra=None):
+    """fp32 [M, K] (unit column stride) -> bf16 [M, 3 * Kp]; `ones` / `extra` append one more column before the padding"""
     M, K = x2d.shape
     if x2d.stride(1) != 1:
         x2d = x2d.contiguous()
-    Kp = (K + 7) // 8 * 8
+    mode = 1 if ones else (2 if extra is not None else 0)
+    Kp = (K + (1 if mode else 0) + 7) // 8 * 8
     out = torch.empty((M, 3 * Kp), dtype=torch.bfloat16, device=x2d.device)
-    _lib.check(_lib.load().dppo_split3_pack(C.c_void_p(x2d.data_ptr()), M, K, x2d.stride(0), _lib.ptr(out), pattern,
-                                            _lib.stream_ptr()), "dppo_split3_pack")
+    _lib.check(_lib.load().dppo_split3_pack(C.c_void_p(x2d.data_ptr()), M, K, x2d.stride(0), mode, _lib.ptr(extra),
+                                            _lib.ptr(out), pattern, _lib.stream_ptr()), "dppo_split3_pack")
     return out, Kp
 
 
@@ -41,11 +42,10 @@ class _Split3Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        xp, Kp = _pack(x2, 0)
-        wp, _ = _pack(weight, 1)
+        # the bias is one more K column: [x | 1] . [W | b]^T
+        xp, Kp = _pack(x2, 0, ones=bias is not None)
+        wp, _ = _pack(weight, 1, extra=None if bias is None else bias.contiguous())
         y = torch.mm(xp, wp.t(), out_dtype=torch.float32)
-        if bias is not None:
-            y += bias
         ctx.save_for_backward(xp, weight)
         ctx.meta = (shape, Kp, bias is not None)
         return y.view(*shape[:-1], weight.shape[0])
@@ -61,15 +61,15 @@ class _Split3Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wtp, _ = _pack(weight.t(), 1)  # [K, 3 Np]
             gx = torch.mm(gyp, wtp.t(), out_dtype=torch.float32).view(shape)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             gyh, gyl = gyp[:, :Np], gyp[:, 2 * Np:]
             xh, xl = xp[:, :Kp], xp[:, 2 * Kp:]
-            gw = torch.mm(gyh.t(), xh, out_dtype=torch.float32)
-            gw += torch.mm(gyh.t(), xl, out_dtype=torch.float32)
-            gw += torch.mm(gyl.t(), xh, out_dtype=torch.float32)
-            gw = gw[:N, :K]
-        if has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(0)
+            gwb = torch.mm(gyh.t(), xh, out_dtype=torch.float32)
+            gwb += torch.mm(gyh.t(), xl, out_dtype=torch.float32)
+            gwb += torch.mm(gyl.t(), xh, out_dtype=torch.float32)
+            gw = gwb[:N, :K]
+            if has_bias:
+                gb = gwb[:N, K]  # the ones column of [x | 1]: column sums of dy
         return gx, gw, gb
 
 

@@ -213,8 +213,11 @@ int dppo_gae_f64(const double* reward, const double* terminated, const double* v
  * lo = bf16(x - hi).  A bf16 GEMM with fp32 accumulation over these rows is the 3-product split
  * x w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi the chain kernel uses, i.e. fp32-grade Linear layers (forward, dgrad, wgrad
  * of actor_ft / critic: diffusion_vpg.py:398-461, critic.py:40-54, train_ppo_diffusion_agent.py:360-364) on the tensor
- * cores instead of fp32 SIMT GEMMs.  `out` must be 8-byte aligned.                                                  */
-int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, void* out, int pattern, void* stream);
+ * cores instead of fp32 SIMT GEMMs.  extra_mode 1 appends a column of ones before the padding (activations), 2 appends
+ * extra[row] (weights: the bias), so that y = x W^T + b is ONE GEMM and the bias gradient is the last column of the
+ * wgrad GEMM; cols_p then rounds cols + 1 up.  `out` must be 8-byte aligned.                                        */
+int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, int extra_mode, const float* extra, void* out,
+                     int pattern, void* stream);
 
 /* ---- running reward scaling ----------------------------------------------------------------------------------- */
 /* RunningRewardScaler.__call__ (dppo/util/reward_scaling.py:42-87; call site train_ppo_diffusion_agent.py:243-247) on
