@@ -333,6 +333,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // hand the operand written by this epilogue over to the MMA warp (and, for an exchange layer, to the peers)
     const uint32_t blk_chunks = 2u * uint32_t(MTo), blk_bytes = blk_chunks * NE * 128u;  // this CTA's column block of X
     const uint32_t blk_off = uint32_t(mt0) * 2u * NE * 128u;
+    // The block is pushed M tile by M tile: the epilogue pushes tile mt as soon as its columns are written (the copy of
+    // the first tiles overlaps the arithmetic of the later ones), signal_x pushes the last tile and posts the expected
+    // byte count (peers' bytes may land before it: the transaction count is signed).
+    const uint32_t tile_bytes = 2u * NE * 128u;  // one M tile = two 64-feature chunks of X
+    auto push_tile = [&](int mt) {
+      const uint32_t off = blk_off + uint32_t(mt) * tile_bytes;
+      for (uint32_t p = 0; p < uint32_t(C); ++p) {
+        if (p == rank) continue;
+        bulk_s2peer(s.x_hi + off, s.x_hi + off, tile_bytes, s.x_full, p);
+        if (split) bulk_s2peer(s.x_lo + off, s.x_lo + off, tile_bytes, s.x_full, p);
+      }
+    };
     auto signal_x = [&](bool exchange) {
       tmem_wait_st();
       tc_fence_before();
@@ -341,11 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       if (et == 0) {
         if (exchange && C > 1) {
           mbar_arrive_expect_tx(s.x_full, uint32_t(C - 1) * blk_bytes * uint32_t(a.nsplit));
-          for (uint32_t p = 0; p < uint32_t(C); ++p) {
-            if (p == rank) continue;
-            bulk_s2peer(s.x_hi + blk_off, s.x_hi + blk_off, blk_bytes, s.x_full, p);
-            if (split) bulk_s2peer(s.x_lo + blk_off, s.x_lo + blk_off, blk_bytes, s.x_full, p);
-          }
+          push_tile(MTo - 1);
         } else {
           mbar_arrive(s.x_full);
         }
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     };
     // `whole_row`: this CTA holds every feature of the layer (cond_mlp), otherwise they are split over the cluster
     auto epi_hidden = [&](uint32_t region, int mt_first, int MTl, const float* bias_a, const float* bias_b, bool identity,
-                          const float* ln_g, const float* ln_b, bool whole_row) {
+                          const float* ln_g, const float* ln_b, bool whole_row, bool push) {
       float mean[LN ? CPT : 1], rstd[LN ? CPT : 1];
       if (LN && ln_g != nullptr) {
         float s1[CPT], s2[CPT];
@@ -490,6 +498,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             *reinterpret_cast<__nv_bfloat162*>(s.x_lo + off) =
                 __floats2bfloat162_rn(fa - __low2float(h2), fb - __high2float(h2));
         }
+        if (push && mt + 1 < MTl) {
+          // tile mt of this CTA's block is complete in shared memory: start its copy into the peers now
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) push_tile(mt);
+        }
       }
     };
 
@@ -590,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         }
         prefetch_side(mt_first, MTl, ba, bb, lg, lb);
         wait_layer(L >= 0);
-        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0);
+        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0, L >= 0 && C > 1);
         signal_x(L >= 0);
       }
       cur_net = net;
