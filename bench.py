@@ -204,6 +204,22 @@ def run_b200(args, w, E, rank, world, local_rank):
         e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    # the B200 agent keeps the rollout buffers on the device: only the action chunk returns to the host
+    def e2e_resident_step(i):
+        obs = host_obs[i % n_bufs].to(dev, non_blocking=True)
+        out = model(cond={"state": obs}, deterministic=False, return_chain=True)
+        host_traj.copy_(out.trajectories, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(args.warmup):
+        e2e_resident_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_resident_step(i)
+    barrier()
+    e2e_res_s = time.perf_counter() - t0
     # the timed regions are tens of milliseconds, nvidia-smi samples every 100 ms: keep issuing the SAME launches (untimed)
     # until the sampler has seen the device under this load for at least a second
     t_load = time.perf_counter()
@@ -220,10 +236,10 @@ def run_b200(args, w, E, rank, world, local_rank):
     # ---- update (secondary): one PPO minibatch = fused loss kernel + autograd backward + both optimiser steps
     upd = bench_update(args, w, model, dev, E, rank, world) if args.update else None
 
-    t = torch.tensor([total_ms, e2e_s, wall], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s, wall, e2e_res_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, wall = t.tolist()
+    total_ms, e2e_s, wall, e2e_res_s = t.tolist()
     if rank == 0:
         act = w["act_steps"]
         value = world * E * act * args.steps / (total_ms * 1e-3)
@@ -252,6 +268,10 @@ def run_b200(args, w, E, rank, world, local_rank):
                        "weights": "random init seed 42, actor_ft perturbed 1e-2", "noise": "in-kernel Philox4x32-10"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
                     "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e_device_resident_buffers": {
+                "value": world * E * act * args.steps / e2e_res_s, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
+                "d2h_bytes_per_step": E * D * 4, "ms_per_step": 1e3 * e2e_res_s / args.steps,
+                "note": "same call; chains stay in the device-resident rollout buffer (what dppo_b200's agent does), only the action chunk is copied back"},
             "gpu_launches": args.steps,
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
