@@ -327,13 +327,27 @@ def bench_update(args, w, model, dev, E, rank, world):
     lo, hi = D.minibatch_slice(bs, rank, world)
     per_rank = bs // world
 
-    def minibatch(k):
-        inds = D.broadcast_permutation(N * ft, dev)[:bs]
+    def fwd_bwd(inds):
         grads.zero()
         res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo,
                                   row_count=hi - lo, reward_horizon=w["act_steps"], scalars_out=grads.scalars)
         (res[0] + w["train"]["vf_coef"] * res[2]).backward()
         grads.allreduce()  # gradients of both networks + loss diagnostics: one NCCL all-reduce
+
+    graphed = None
+    if args.graph_update:
+        from dppo_b200.agent.finetune.graphed import GraphedMinibatch
+
+        try:
+            graphed = GraphedMinibatch(fwd_bwd, bs, dev)
+        except Exception as ex:  # capture is an optimisation: report and run eagerly
+            print(f"[bench] CUDA-graph capture of the minibatch failed ({type(ex).__name__}: {str(ex)[:200]}); running eagerly",
+                  file=sys.stderr, flush=True)
+            torch.cuda.synchronize(dev)
+
+    def minibatch(k):
+        inds = D.broadcast_permutation(N * ft, dev)[:bs]
+        (graphed or fwd_bwd)(inds)
         kl = grads.scalars.tolist()[2]  # the agent's early-stop test: one device->host read per minibatch
         opt_a.step()
         opt_c.step()
@@ -354,7 +368,9 @@ def bench_update(args, w, model, dev, E, rank, world):
             "minibatch_rows": per_rank * world, "buffer_rows": N * ft,
             "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
                      "Linear layers as 3-product bf16-split tensor-core GEMMs (dppo_split3_pack + cuBLASLt bf16, fp32 accumulate) under "
-                     "torch autograd; fused flat AdamW kernel per network")}
+                     "torch autograd; fused flat AdamW kernel per network; "
+                     + ("forward + loss + backward + all-reduce replayed as ONE CUDA graph per minibatch" if graphed
+                        else "eager launches"))}
 
 
 def main():
@@ -368,6 +384,8 @@ def main():
     ap.add_argument("--precision", default="split3", choices=["split3", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-update", dest="update", action="store_false", help="skip the secondary PPO-update measurement")
+    ap.add_argument("--no-graph-update", dest="graph_update", action="store_false",
+                    help="run the PPO minibatch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -33,6 +33,7 @@ import torch
 
 from dppo_b200 import distributed as D
 from dppo_b200 import engine as E_
+from dppo_b200.agent.finetune.graphed import GraphedMinibatch
 from dppo_b200.optim import FlatAdamW
 from dppo_b200.util.config import instantiate
 from dppo_b200.util.reward_scaling import RunningRewardScaler, RunningRewardScalerCUDA  # noqa: F401
@@ -117,6 +118,7 @@ class TrainPPODiffusionAgent:
         self.use_bc_loss = cfg.train.get("use_bc_loss", False)
         self.bc_loss_coeff = cfg.train.get("bc_loss_coeff", 0)
         self.reward_horizon = cfg.get("reward_horizon", self.act_steps)
+        self.cuda_graph_update = cfg.train.get("cuda_graph_update", True)
         if self.model.learn_eta:
             raise NotImplementedError("learned eta is outside the hot path (no YAML enables it)")
 
@@ -218,23 +220,44 @@ class TrainPPODiffusionAgent:
         total_steps = n * Eg * ft
         num_batch = max(1, total_steps // self.batch_size)  # the tail rows of each permutation are skipped, as in the reference
         clipfracs, stats, flag_break = [], None, False
+        lo, hi = D.minibatch_slice(min(self.batch_size, total_steps), self.rank, self.world)
+        eta_mean = self.model._eta_value()
+        ent_const = -eta_mean  # the entropy term of a fixed-eta policy is a constant (diffusion_ppo.py:183-187)
+
+        def fwd_bwd(inds_b):
+            """zero grads -> actor_ft / critic forward -> fused loss kernel -> backward -> one all-reduce (no host sync)"""
+            self.grads.zero()
+            res = self.model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
+                                           row_count=hi - lo, use_bc_loss=self.use_bc_loss,
+                                           reward_horizon=self.reward_horizon, scalars_out=self.grads.scalars)
+            pg_loss, entropy_loss, v_loss, bc_loss = res[0], res[1], res[2], res[6]
+            loss = pg_loss + entropy_loss * self.ent_coef + v_loss * self.vf_coef + bc_loss * self.bc_loss_coeff
+            loss.backward()
+            self.grads.allreduce()  # gradients + [pg, v, kl, clipfrac, ratio] partial means, one collective
+            return bc_loss
+
+        # the minibatch is launch-bound: replay it as one CUDA graph when the iteration has enough minibatches to
+        # amortise the capture (the rollout buffers get new addresses every iteration, so the graph is per iteration)
+        step_fn = fwd_bwd
+        n_minibatches = self.update_epochs * num_batch
+        if (self.cuda_graph_update and not self.use_bc_loss and n_minibatches >= 16
+                and total_steps >= self.batch_size):
+            try:
+                step_fn = GraphedMinibatch(fwd_bwd, self.batch_size, self.device)
+            except Exception as ex:  # capture is an optimisation only
+                log.warning("CUDA-graph capture of the PPO minibatch failed (%s); running eagerly", ex)
+                torch.cuda.synchronize()
+                self.cuda_graph_update = False
         for update_epoch in range(self.update_epochs):
             inds_k = D.broadcast_permutation(total_steps, self.device)
             for batch in range(num_batch):
                 inds_b = inds_k[batch * self.batch_size:(batch + 1) * self.batch_size]
-                lo, hi = D.minibatch_slice(inds_b.numel(), self.rank, self.world)
-                self.grads.zero()
-                res = self.model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
-                                               row_count=hi - lo, use_bc_loss=self.use_bc_loss,
-                                               reward_horizon=self.reward_horizon, scalars_out=self.grads.scalars)
-                pg_loss, entropy_loss, v_loss, bc_loss = res[0], res[1], res[2], res[6]
-                loss = pg_loss + entropy_loss * self.ent_coef + v_loss * self.vf_coef + bc_loss * self.bc_loss_coeff
-                loss.backward()
-                self.grads.allreduce()  # gradients + [pg, v, kl, clipfrac, ratio] partial means, one collective
+                bc_loss = step_fn(inds_b)
+                bc_loss = 0.0 if bc_loss is None else float(bc_loss)
                 s = self.grads.scalars.tolist()  # the one device->host read of the minibatch
-                stats = dict(pg_loss=s[0], v_loss=s[1], approx_kl=s[2], clipfrac=s[3], ratio=s[4], bc_loss=float(bc_loss),
-                             eta=res[7], loss=s[0] + float(entropy_loss) * self.ent_coef + s[1] * self.vf_coef
-                             + float(bc_loss) * self.bc_loss_coeff)
+                stats = dict(pg_loss=s[0], v_loss=s[1], approx_kl=s[2], clipfrac=s[3], ratio=s[4], bc_loss=bc_loss,
+                             eta=eta_mean, loss=s[0] + ent_const * self.ent_coef + s[1] * self.vf_coef
+                             + bc_loss * self.bc_loss_coeff)
                 clipfracs.append(s[3])
                 if self.itr >= self.n_critic_warmup_itr:
                     self.actor_optimizer.step(max_grad_norm=self.max_grad_norm)  # clip_grad_norm_ folded into the kernel

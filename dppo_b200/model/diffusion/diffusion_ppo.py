@@ -71,10 +71,19 @@ class PPODiffusion(VPGDiffusion):
         bc = self.get_logprobs(obs, samples.chains, get_ent=False, use_base_policy=False)
         return -bc.clamp(min=-5, max=2).mean(dim=(-1, -2)).view(-1).mean()
 
+    def _eta_value(self):
+        """EtaFixed's value, read from the device once (the reference calls .item() per loss call, eta.py:40)."""
+        if not (self.use_ddim and hasattr(self, "eta")):
+            return 1.0
+        key = tuple(p._version for p in self.eta.parameters())
+        if getattr(self, "_eta_cache", (None, None))[0] != key:
+            self._eta_cache = (key, float(self.eta.value()))
+        return self._eta_cache[1]
+
     def _finish(self, eps, vpred, grad_eps, grad_v, scalars, obs, use_bc_loss, scalars_out=None):
         pg_loss, v_loss = _FusedLoss.apply(eps, vpred, grad_eps, grad_v, scalars)
         bc_loss = self._bc_loss(obs) if use_bc_loss else 0
-        eta_mean = float(self.eta.value()) if self.use_ddim and hasattr(self, "eta") else 1.0
+        eta_mean = self._eta_value()
         entropy_loss = torch.full((), -eta_mean, device=eps.device)
         if scalars_out is not None:
             # multi-rank caller: the partial means stay on the device and ride the gradient all-reduce
@@ -107,7 +116,7 @@ class PPODiffusion(VPGDiffusion):
         `scalars_out` (8 floats, device): the kernel's partial means are copied there and NOT read back to the host
         (the caller all-reduces them together with the gradients); elements 3-5 of the return are then device scalars.
         """
-        eng = self.engine()
+        eng = self.engine(sync=False)  # the update reads the nn.Parameters, not the packed rollout copies
         ft = self.ft_denoising_steps
         row_count = inds_all.numel() - row_begin if row_count is None else row_count
         mine = inds_all[row_begin:row_begin + row_count]

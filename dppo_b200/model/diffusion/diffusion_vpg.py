@@ -90,12 +90,14 @@ class VPGDiffusion(DiffusionModel):
         self._rng_offset = 0
 
     # ------------------------------------------------------------------ engine plumbing
-    def engine(self):
-        """The kernel context (created on first use; rebuilt when the fine-tuning window is annealed)."""
+    def engine(self, sync=True):
+        """The kernel context (created on first use; rebuilt when the fine-tuning window is annealed).  `sync` refreshes
+        the packed weight copies the chain kernels read (not needed by the loss kernels)."""
         if self._engine is None or self._engine.ft != int(self.ft_denoising_steps):
             self._engine = ChainEngine(self, precision=self.engine_precision)
-        self._engine.sync_weights(0, self.actor)
-        self._engine.sync_weights(1, self.actor_ft)
+        if sync:
+            self._engine.sync_weights(0, self.actor)
+            self._engine.sync_weights(1, self.actor_ft)
         return self._engine
 
     # ------------------------------------------------------------------ annealing (reference :102-136)

@@ -13,7 +13,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "furniture"
 w = get_workload(name)
 from dppo_b200.agent.finetune.train_ppo_diffusion_agent import TrainPPODiffusionAgent
 
-cfg = make_agent_cfg(w, f"cuda:{local}", tempfile.mkdtemp(), n_envs=50 if name != "hopper" else 40, n_steps=6, batch_size=500,
+cfg = make_agent_cfg(w, f"cuda:{local}", tempfile.mkdtemp(), n_envs=50 if name != "hopper" else 40, n_steps=6, batch_size=100,
                      update_epochs=2, n_train_itr=3)
 ag = TrainPPODiffusionAgent(cfg)
 ag.n_critic_warmup_itr = 1
