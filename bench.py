@@ -220,6 +220,21 @@ def run_b200(args, w, E, rank, world, local_rank):
         e2e_resident_step(i)
     barrier()
     e2e_res_s = time.perf_counter() - t0
+    # zero-copy variant of the same call: observations read from pinned host memory by the kernel prologue, trajectories
+    # and chains stored by the kernel straight into pinned host memory (PCIe writes overlap the chain)
+    def e2e_zero_copy_step(i):
+        model(cond={"state": host_obs[i % n_bufs]}, deterministic=False, return_chain=True, out_trajectories=host_traj,
+              out_chains=host_chain)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(args.warmup):
+        e2e_zero_copy_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_zero_copy_step(i)
+    barrier()
+    e2e_zc_s = time.perf_counter() - t0
     # the timed regions are tens of milliseconds, nvidia-smi samples every 100 ms: keep issuing the SAME launches (untimed)
     # until the sampler has seen the device under this load for at least a second
     t_load = time.perf_counter()
@@ -236,10 +251,10 @@ def run_b200(args, w, E, rank, world, local_rank):
     # ---- update (secondary): one PPO minibatch = fused loss kernel + autograd backward + both optimiser steps
     upd = bench_update(args, w, model, dev, E, rank, world) if args.update else None
 
-    t = torch.tensor([total_ms, e2e_s, wall, e2e_res_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, wall, e2e_res_s = t.tolist()
+    total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s = t.tolist()
     if rank == 0:
         act = w["act_steps"]
         value = world * E * act * args.steps / (total_ms * 1e-3)
@@ -268,6 +283,10 @@ def run_b200(args, w, E, rank, world, local_rank):
                        "weights": "random init seed 42, actor_ft perturbed 1e-2", "noise": "in-kernel Philox4x32-10"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
                     "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e_zero_copy": {
+                "value": world * E * act * args.steps / e2e_zc_s, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
+                "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_zc_s / args.steps,
+                "note": "same call with pinned host tensors passed in: the kernel reads the observations from and stores trajectories + chains into page-locked host memory itself (no copy launches)"},
             "e2e_device_resident_buffers": {
                 "value": world * E * act * args.steps / e2e_res_s, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
                 "d2h_bytes_per_step": E * D * 4, "ms_per_step": 1e3 * e2e_res_s / args.steps,

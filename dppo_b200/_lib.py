@@ -149,6 +149,19 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def ptr_dev_or_pinned(t):
+    """Pointer of a contiguous CUDA tensor or of a PINNED host tensor (page-locked memory is mapped into the device's
+    address space under unified addressing: a kernel can read observations from it / write results into it directly,
+    which replaces a separate copy launch by PCIe transactions overlapped with the kernel)."""
+    if t is None:
+        return None
+    if not (t.is_cuda or t.is_pinned()):
+        raise RuntimeError("dppo_b200 kernels need CUDA tensors or pinned host tensors; there is no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError("dppo_b200 kernels need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
 def stream_ptr():
     """cudaStream_t of torch's current stream on the current device (raw getter: ~0.3 us instead of ~5 us)."""
     import torch

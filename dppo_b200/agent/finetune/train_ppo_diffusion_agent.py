@@ -168,10 +168,10 @@ class TrainPPODiffusionAgent:
         for step in range(n):
             pinned_obs.copy_(torch.from_numpy(np.ascontiguousarray(prev_obs_venv["state"], dtype=np.float32)))
             obs_buf[step].copy_(pinned_obs, non_blocking=True)
-            samples = self.model(cond={"state": obs_buf[step]}, deterministic=eval_mode, return_chain=True,
-                                 env_offset=self.env_begin)
-            chains_buf[step].copy_(samples.chains)
-            pinned_act.copy_(samples.trajectories, non_blocking=True)
+            # the kernel stores the chains straight into the device-resident rollout buffer and the action chunk straight
+            # into pinned host memory: no copy launches after it
+            self.model(cond={"state": obs_buf[step]}, deterministic=eval_mode, return_chain=True, env_offset=self.env_begin,
+                       out_trajectories=pinned_act, out_chains=chains_buf[step])
             torch.cuda.current_stream().synchronize()  # the simulator needs the action chunk on the host
             action_venv = pinned_act.numpy()[:, : self.act_steps]
             obs_venv, reward_venv, terminated_venv, truncated_venv, _ = self.venv.step(action_venv)

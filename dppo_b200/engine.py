@@ -215,19 +215,27 @@ class ChainEngine:
 
     # ------------------------------------------------------------------ rollout
     def sample(self, state, noise=None, seed=0, offset=0, env_offset=0, deterministic=False, use_base_policy=False,
-               min_sampling_std=0.1, return_chain=True):
+               min_sampling_std=0.1, return_chain=True, out_traj=None, out_chain=None):
+        """`state` may be a pinned host tensor (read once by the kernel prologue); `out_traj` (E, D) / `out_chain`
+        (E, ft+1, D) may be preallocated CUDA or PINNED HOST tensors the kernel writes into directly (zero-copy)."""
         E = state.shape[0]
         if state.dtype != torch.float32 or not state.is_contiguous():
             state = state.contiguous().float()
         state = state.view(E, -1)
-        traj = torch.empty((E, self.D), dtype=torch.float32, device=state.device)
-        chain = torch.empty((E, self.ft + 1, self.D), dtype=torch.float32, device=state.device) if return_chain else None
+        if not (state.is_cuda or state.is_pinned()):
+            state = state.to(self.device)
+        traj = out_traj if out_traj is not None else torch.empty((E, self.D), dtype=torch.float32, device=self.device)
+        chain = out_chain if out_chain is not None else (
+            torch.empty((E, self.ft + 1, self.D), dtype=torch.float32, device=self.device) if return_chain else None)
+        for name, t, shape in (("out_traj", out_traj, E * self.D), ("out_chain", out_chain, E * (self.ft + 1) * self.D)):
+            if t is not None and (t.dtype != torch.float32 or t.numel() != shape):
+                raise RuntimeError(f"{name}: expected {shape} float32 elements")
         if noise is not None:
             noise = noise.reshape(self.S + 1, E, self.D).contiguous().float()
         _lib.check(
-            self.lib.dppo_sample_chain(self.ctx, _lib.ptr(state), E, _lib.ptr(noise), seed, offset, env_offset,
+            self.lib.dppo_sample_chain(self.ctx, _lib.ptr_dev_or_pinned(state), E, _lib.ptr(noise), seed, offset, env_offset,
                                        int(deterministic), int(use_base_policy), float(min_sampling_std),
-                                       _lib.ptr(traj), _lib.ptr(chain), _lib.stream_ptr()),
+                                       _lib.ptr_dev_or_pinned(traj), _lib.ptr_dev_or_pinned(chain), _lib.stream_ptr()),
             "dppo_sample_chain")
         return traj, chain
 

@@ -124,9 +124,13 @@ class VPGDiffusion(DiffusionModel):
 
     # ------------------------------------------------------------------ sampling (reference :227-315)
     @torch.no_grad()
-    def forward(self, cond, deterministic=False, return_chain=True, use_base_policy=False, noise=None, env_offset=0):
+    def forward(self, cond, deterministic=False, return_chain=True, use_base_policy=False, noise=None, env_offset=0,
+                out_trajectories=None, out_chains=None):
         """
         cond["state"]: (B, To, Do).  Returns Sample(trajectories (B, Ta, Da), chains (B, ft+1, Ta, Da)).
+        `out_trajectories` / `out_chains`: optional preallocated float32 tensors of those shapes, on the device or in
+        PINNED host memory - the kernel then stores straight into them (over PCIe for pinned memory, overlapped with the
+        chain instead of a copy after it) and they are what Sample holds; cond["state"] may be pinned host memory too.
         `noise` (S+1, B, Ta, Da) injects the draws the reference takes from torch.randn / randn_like (parity tests);
         without it the kernel draws Philox normals seeded from torch's generator.  `env_offset` = global index of
         row 0 (env-sharded ranks then draw what one process would draw for the same envs).
@@ -139,10 +143,12 @@ class VPGDiffusion(DiffusionModel):
             seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
             self._rng_offset += 1
             offset = self._rng_offset
+        if not (state.is_cuda or state.is_pinned()):
+            state = state.to(self.device)
         traj, chain = eng.sample(
-            state.to(self.device), noise=noise, seed=seed, offset=offset, env_offset=env_offset, deterministic=deterministic,
+            state, noise=noise, seed=seed, offset=offset, env_offset=env_offset, deterministic=deterministic,
             use_base_policy=use_base_policy, min_sampling_std=float(self.get_min_sampling_denoising_std()),
-            return_chain=return_chain,
+            return_chain=return_chain, out_traj=out_trajectories, out_chain=out_chains if return_chain else None,
         )
         traj = traj.view(B, self.horizon_steps, self.action_dim)
         if chain is not None:

@@ -225,3 +225,19 @@ def test_small_batch_cluster_kernel_matches_tcgen05_and_oracle(case, n_envs):
     model._rng_offset = 0
     b = model(cond={"state": state}).chains
     assert_close(a.cpu().numpy(), b.cpu().numpy(), 1e-3, f"{case} E={n_envs} philox small vs tcgen05", max_frac=2e-3)
+
+
+@pytest.mark.parametrize("case", ["hopper", "walker2d", "square_unet"])
+def test_zero_copy_pinned_io_matches_device_io(case):
+    """Pinned host observations in / pinned host trajectories + chains out (kernel-side PCIe access) == device tensors."""
+    w, model, gold, inp = _setup(case)
+    state, noise = inp["state"], inp["noise"].cuda()
+    want = model(cond={"state": state.cuda()}, noise=noise)
+    E, ft = state.shape[0], w["ft_denoising_steps"]
+    h_state = state.clone().pin_memory()
+    h_traj = torch.zeros((E, w["horizon_steps"], w["action_dim"])).pin_memory()
+    h_chain = torch.zeros((E, ft + 1, w["horizon_steps"], w["action_dim"])).pin_memory()
+    got = model(cond={"state": h_state}, noise=noise, out_trajectories=h_traj, out_chains=h_chain)
+    torch.cuda.synchronize()
+    assert got.trajectories.data_ptr() == h_traj.data_ptr() and not got.chains.is_cuda
+    assert torch.equal(h_traj, want.trajectories.cpu()) and torch.equal(h_chain, want.chains.cpu())
