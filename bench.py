@@ -364,8 +364,16 @@ def bench_update(args, w, model, dev, E, rank, world):
                   file=sys.stderr, flush=True)
             torch.cuda.synchronize(dev)
 
+    perm = [None]
+
     def minibatch(k):
-        inds = D.broadcast_permutation(N * ft, dev)[:bs]
+        # one permutation per epoch, sliced per minibatch, exactly like the reference loop
+        # (train_ppo_diffusion_agent.py:311-316); an epoch of this buffer is N*ft // bs minibatches
+        per_epoch = max(1, (N * ft) // bs)
+        if perm[0] is None or k % per_epoch == 0:
+            perm[0] = D.broadcast_permutation(N * ft, dev)
+        j = k % per_epoch
+        inds = perm[0][j * bs:(j + 1) * bs]
         (graphed or fwd_bwd)(inds)
         kl = grads.scalars.tolist()[2]  # the agent's early-stop test: one device->host read per minibatch
         opt_a.step()
@@ -376,6 +384,7 @@ def bench_update(args, w, model, dev, E, rank, world):
         minibatch(k)
     torch.cuda.synchronize(dev)
     reps = 10
+    perm[0] = None  # the timed region draws (and broadcasts) its own permutation
     t0 = time.perf_counter()
     for k in range(reps):
         minibatch(k)
