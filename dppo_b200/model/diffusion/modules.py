@@ -10,6 +10,8 @@ import math
 import torch
 from torch import nn
 
+from dppo_b200.model.diffusion.dense_conv import DenseConv1d, DenseConvTranspose1d
+
 
 class SinusoidalPosEmb(nn.Module):
     """t -> [sin(t f_j), cos(t f_j)], f_j = exp(-j ln(1e4) / (dim/2 - 1)), j < dim/2."""
@@ -29,7 +31,7 @@ class SinusoidalPosEmb(nn.Module):
 class Downsample1d(nn.Module):
     def __init__(self, dim):
         super().__init__()
-        self.conv = nn.Conv1d(dim, dim, 3, 2, 1)
+        self.conv = DenseConv1d(dim, dim, 3, 2, 1)
 
     def forward(self, x):
         return self.conv(x)
@@ -38,10 +40,27 @@ class Downsample1d(nn.Module):
 class Upsample1d(nn.Module):
     def __init__(self, dim):
         super().__init__()
-        self.conv = nn.ConvTranspose1d(dim, dim, 4, 2, 1)
+        self.conv = DenseConvTranspose1d(dim, dim, 4, 2, 1)
 
     def forward(self, x):
         return self.conv(x)
+
+
+class FastGroupNorm(nn.GroupNorm):
+    """nn.GroupNorm (same parameters / state_dict).  On CUDA the statistics are a layer_norm over each group's
+    contiguous (C/G * L) elements - torch's GroupNorm backward is built for images and takes 12 of the 30 ms of a cfg5
+    minibatch on (B, C, 1, 4) tensors - followed by the per-channel affine; numerically the same biased-variance formula."""
+
+    def forward(self, x):
+        if not (x.is_cuda and x.is_contiguous() and x.dim() >= 3):
+            return super().forward(x)
+        B, C = x.shape[0], x.shape[1]
+        G = self.num_groups
+        y = torch.nn.functional.layer_norm(x.view(B * G, -1), (x[0].numel() // G,), None, None, self.eps).view(x.shape)
+        if self.affine:
+            shape = (1, C) + (1,) * (x.dim() - 2)
+            y = y * self.weight.view(shape) + self.bias.view(shape)
+        return y
 
 
 class _AddAxis(nn.Module):
@@ -69,9 +88,9 @@ class Conv1dBlock(nn.Module):
             raise ValueError("Unknown activation type for Conv1dBlock")
         grouped = n_groups is not None
         self.block = nn.Sequential(
-            nn.Conv1d(inp_channels, out_channels, kernel_size, padding=kernel_size // 2),
+            DenseConv1d(inp_channels, out_channels, kernel_size, padding=kernel_size // 2),
             _AddAxis() if grouped else nn.Identity(),
-            nn.GroupNorm(n_groups, out_channels, eps=eps) if grouped else nn.Identity(),
+            FastGroupNorm(n_groups, out_channels, eps=eps) if grouped else nn.Identity(),
             _DropAxis() if grouped else nn.Identity(),
             act,
         )

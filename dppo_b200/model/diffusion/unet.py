@@ -11,6 +11,8 @@ import torch
 from torch import nn
 
 from dppo_b200.model.common.mlp import ResidualMLP
+from dppo_b200.model.common.split_linear import SplitLinear
+from dppo_b200.model.diffusion.dense_conv import DenseConv1d
 from dppo_b200.model.diffusion.modules import Conv1dBlock, Downsample1d, SinusoidalPosEmb, Upsample1d
 
 
@@ -49,11 +51,11 @@ class ResidualBlock1D(nn.Module):
         self.out_channels = out_channels
         if larger_encoder:
             self.cond_encoder = nn.Sequential(
-                nn.Linear(cond_dim, film), act, nn.Linear(film, film), act, nn.Linear(film, film), _Col()
+                SplitLinear(cond_dim, film), act, SplitLinear(film, film), act, SplitLinear(film, film), _Col()
             )
         else:
-            self.cond_encoder = nn.Sequential(act, nn.Linear(cond_dim, film), _Col())
-        self.residual_conv = nn.Conv1d(in_channels, out_channels, 1) if in_channels != out_channels else nn.Identity()
+            self.cond_encoder = nn.Sequential(act, SplitLinear(cond_dim, film), _Col())
+        self.residual_conv = DenseConv1d(in_channels, out_channels, 1) if in_channels != out_channels else nn.Identity()
 
     def forward(self, x, cond):
         y = self.blocks[0](x)
@@ -121,7 +123,7 @@ class Unet1D(nn.Module):
         self.final_conv = nn.Sequential(
             Conv1dBlock(dim, dim, kernel_size=kernel_size, n_groups=n_groups, activation_type=activation_type,
                         eps=groupnorm_eps),
-            nn.Conv1d(dim, action_dim, 1),
+            DenseConv1d(dim, action_dim, 1),
         )
         self.time_dim = e
 

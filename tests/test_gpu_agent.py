@@ -285,3 +285,30 @@ def test_agent_run_with_graphed_update(tmp_path):
     assert res[-1]["minibatches"] == 2 * (16 * 8 * w["ft_denoising_steps"] // 64)
     assert all(np.isfinite(r["pg_loss"]) and np.isfinite(r["v_loss"]) and np.isfinite(r["approx_kl"]) for r in res)
     assert ag.cuda_graph_update  # capture did not fall back
+
+
+@pytest.mark.parametrize("kind,cin,cout,ks,stride,pad,T", [
+    ("conv", 7, 64, 5, 1, 2, 4), ("conv", 64, 64, 5, 1, 2, 4), ("conv", 256, 64, 5, 1, 2, 2), ("conv", 64, 64, 3, 2, 1, 4),
+    ("conv", 64, 7, 1, 1, 0, 4), ("convT", 64, 64, 4, 2, 1, 2), ("conv", 32, 32, 3, 1, 1, 16),
+])
+def test_dense_lowered_convs_match_float64_convs(kind, cin, cout, ks, stride, pad, T):
+    """DenseConv1d / DenseConvTranspose1d (gathered Toeplitz matrix + split-3 tensor-core GEMM) vs float64 convolutions."""
+    import torch.nn.functional as F
+
+    from dppo_b200.model.diffusion.dense_conv import DenseConv1d, DenseConvTranspose1d
+
+    torch.manual_seed(2)
+    mod = (DenseConv1d(cin, cout, ks, stride, pad) if kind == "conv" else DenseConvTranspose1d(cin, cout, ks, stride, pad)).cuda()
+    x = torch.randn(300, cin, T, device="cuda", requires_grad=True)
+    y = mod(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xd = x.detach().double().requires_grad_(True)
+    wd, bd = mod.weight.detach().double().requires_grad_(True), mod.bias.detach().double().requires_grad_(True)
+    yd = F.conv1d(xd, wd, bd, stride, pad) if kind == "conv" else F.conv_transpose1d(xd, wd, bd, stride, pad)
+    assert yd.shape == y.shape
+    yd.backward(gy.double())
+    for name, a, b in (("y", y.detach(), yd.detach()), ("dx", x.grad, xd.grad), ("dW", mod.weight.grad, wd.grad),
+                       ("db", mod.bias.grad, bd.grad)):
+        err = float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        assert err < 5e-5, (name, err)
