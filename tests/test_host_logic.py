@@ -56,3 +56,66 @@ def test_cfg_and_instantiate():
     assert cfg.b.d.e == 3 and cfg.get("zz", 7) == 7 and "a" in cfg
     obj = instantiate({"_target_": "dppo_b200.util.reward_scaling.RunningRewardScaler", "num_envs": 3})
     assert obj.ret.shape == (3,)
+
+
+def test_dense_conv_lowering_equals_convolutions_on_cpu():
+    """The index / mask / inverse maps of dense_conv._lowering reproduce Conv1d / ConvTranspose1d (forward and dW)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    from dppo_b200.model.diffusion.dense_conv import _GatherDense, _lowering
+
+    torch.manual_seed(0)
+    for kind, cin, cout, ks, stride, pad, T in [("conv", 7, 16, 5, 1, 2, 4), ("conv", 16, 16, 3, 2, 1, 4), ("conv", 8, 4, 1, 1, 0, 2),
+                                                ("convT", 16, 16, 4, 2, 1, 2), ("conv", 6, 5, 5, 1, 2, 8)]:
+        w = torch.randn((cout, cin, ks) if kind == "conv" else (cin, cout, ks), dtype=torch.float64, requires_grad=True)
+        x = torch.randn(9, cin, T, dtype=torch.float64)
+        t_out, idx, mask, inv = _lowering(kind, cin, cout, ks, stride, pad, T)
+        dense = _GatherDense.apply(w, torch.from_numpy(idx), torch.from_numpy(mask).double(), torch.from_numpy(inv))
+        y = (x.reshape(9, -1) @ dense.t()).view(9, cout, t_out)
+        ref = F.conv1d(x, w, None, stride, pad) if kind == "conv" else F.conv_transpose1d(x, w, None, stride, pad)
+        assert ref.shape == y.shape
+        np.testing.assert_allclose(y.detach().numpy(), ref.detach().numpy(), rtol=1e-12, atol=1e-12)
+        g = torch.randn_like(ref)
+        (gw,) = torch.autograd.grad(y, w, g)
+        (gw_ref,) = torch.autograd.grad(ref, w, g)
+        np.testing.assert_allclose(gw.numpy(), gw_ref.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_fast_group_norm_formula_and_split_linear_cpu_path():
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    from dppo_b200.model.common.split_linear import SplitLinear
+    from dppo_b200.model.diffusion.modules import FastGroupNorm
+
+    torch.manual_seed(1)
+    gn = FastGroupNorm(8, 64, eps=1e-5).double()
+    with torch.no_grad():
+        gn.weight.normal_()
+        gn.bias.normal_()
+    for shape in [(5, 64, 1, 4), (3, 64, 2)]:
+        x = torch.randn(shape, dtype=torch.float64)
+        np.testing.assert_allclose(gn.via_layer_norm(x).detach().numpy(),
+                                   F.group_norm(x, 8, gn.weight, gn.bias, 1e-5).detach().numpy(), rtol=1e-10, atol=1e-12)
+    lin = SplitLinear(11, 7)
+    x = torch.randn(4, 11)
+    assert torch.equal(lin(x), F.linear(x, lin.weight, lin.bias))  # CPU tensors: the stock fp32 path
+    assert set(lin.state_dict()) == {"weight", "bias"}
+
+
+def test_flat_grad_buffer_pads_every_tensor_to_16_bytes():
+    import torch
+
+    from dppo_b200 import distributed as D
+
+    a = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7))]
+    b = [torch.nn.Parameter(torch.zeros(2, 2))]
+    buf = D.FlatGradBuffer([a, b], n_scalars=8)
+    assert buf.flat.numel() == 16 + 8 + 4 + 8
+    offs = [(p.grad.data_ptr() - buf.flat.data_ptr()) // 4 for p in a + b]
+    assert offs == [0, 16, 24] and all(o % 4 == 0 for o in offs)
+    a[1].grad.fill_(2.0)
+    assert float(buf.flat[16:23].sum()) == 14.0 and float(buf.flat[23]) == 0.0
