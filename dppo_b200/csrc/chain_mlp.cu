@@ -98,7 +98,7 @@ __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, int row,
 
 struct Smem {
   uint8_t *x_hi, *x_lo, *x0_hi, *x0_lo, *ring;
-  uint64_t *full, *empty, *layer_done, *x_full, *can_send, *ln_bar;
+  uint64_t *full, *empty, *layer_done, *x_full, *x0_full, *can_send, *ln_bar;
   uint32_t* tmem_slot;
   float* ln_part;  // [kEpiWarps][2][32] per-warp partial sums
   float* ln_x;     // [8 ranks][64 envs][2] per-CTA partial sums of a cluster (LayerNorm over features split across CTAs)
@@ -117,7 +117,8 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
-  s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.x_full = reinterpret_cast<uint64_t*>(p), p += 64;   // one barrier per M tile (= K-chunk pair) of X, MT <= 8
+  s.x0_full = reinterpret_cast<uint64_t*>(p), p += 8;   // layer-0 / cond_mlp operands (written as a whole)
   s.can_send = reinterpret_cast<uint64_t*>(p), p += 16;  // two barriers, used alternately (see wait_layer)
   s.ln_bar = reinterpret_cast<uint64_t*>(p), p += 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
@@ -128,7 +129,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
 
 static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
   const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
-  return xb + x0b + 16 * kMaxStages + 64 + kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 + 1024 /* alignment slack */;
+  return xb + x0b + 16 * kMaxStages + 160 + kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 + 1024 /* alignment slack */;
 }
 
 // ============================================================================================== the kernel
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       mbar_init(&s.empty[i], 1);
     }
     mbar_init(s.layer_done, 1);
-    mbar_init(s.x_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&s.x_full[i], 1);
+    mbar_init(s.x0_full, 1);
     mbar_init(&s.can_send[0], C > 1 ? C - 1 : 1);
     mbar_init(&s.can_send[1], C > 1 ? C - 1 : 1);
     mbar_init(s.ln_bar, C * NE);
@@ -175,36 +177,42 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     const long long p_t0 = clock64();
     // tiles of M-tiles [m_begin, m_end) of one Linear whose tile group starts at `base` (layout: m-tile major, k-chunk minor,
     // hi tile then lo tile)
-    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl) {
+    // `rot`: the K chunks are visited starting at chunk `rot` (wrapping): layers that read X start with the chunks this
+    // CTA produced itself, which are ready first (see the MMA warp)
+    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot) {
       for (int mt = m_begin; mt < m_end; ++mt) {
         const uint8_t* src = base + size_t(mt) * KCl * a.nsplit * kTile;
-        const int n = KCl * a.nsplit;
-        for (int i = 0; i < n; ++i) {
-          const long long tw = clock64();
-          mbar_wait(&s.empty[stage], phase ^ 1);
-          p_wait += clock64() - tw;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&s.full[stage], kTile);
-            bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
+        for (int j = 0; j < KCl; ++j) {
+          int kc = j + rot;
+          if (kc >= KCl) kc -= KCl;
+          for (int h = 0; h < a.nsplit; ++h) {
+            const long long tw = clock64();
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            p_wait += clock64() - tw;
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&s.full[stage], kTile);
+              bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(kc * a.nsplit + h) * kTile, kTile, &s.full[stage]);
+            }
+            __syncwarp();
+            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           }
-          __syncwarp();
-          if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
         }
       }
     };
+    const int rot = mt0 * 2;
     const size_t lin0 = size_t(a.MT) * a.KC0 * a.nsplit * kTile, linh = size_t(a.MT) * a.KCH * a.nsplit * kTile;
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
       if (a.CH && net != cur_net) {
-        stream(a.tiles[net], 0, a.MTc, a.KCc);
-        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64);
+        stream(a.tiles[net], 0, a.MTc, a.KCc, 0);
+        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64, 0);
       }
       cur_net = net;
       const uint8_t* base = a.tiles[net] + a.off_step_tiles;
-      stream(base, mt0, mt0 + MTo, a.KC0);
+      stream(base, mt0, mt0 + MTo, a.KC0, 0);
       base += lin0;
-      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH);
-      stream(base, 0, 1, a.KCH);
+      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH, rot);
+      stream(base, 0, 1, a.KCH, rot);
     }
     if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = p_wait, a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0;
   } else if (warp == 1) {
@@ -212,20 +220,43 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // Whole warp runs the loop (uniform control flow => descriptor arithmetic stays in uniform registers); one elected
     // lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t idesc = umma_idesc_bf16(128, NE);
-    uint32_t stage = 0, phase = 0, xr_phase = 0;
+    // Operand hand-off.  Layers that read X (block layers, output layer) wait per M tile of the previous layer's output
+    // (x_full[t] = chunk pair t of X is complete: written by this CTA's epilogue or pushed by its owner) and visit the K
+    // chunks starting with this CTA's own tiles, so the next layer's MMAs begin while the previous layer's epilogue is
+    // still writing its later tiles and the peers' blocks are still in flight (the accumulator regions alternate between
+    // consecutive layers, so those MMAs never touch what the epilogue is reading).  Layer 0 / cond_mlp read operands
+    // that are written as a whole: one barrier (x0_full).
+    uint32_t stage = 0, phase = 0, x0_phase = 0, xf_phase = 0;
+    const int rot = mt0 * 2;
     long long m_wait_x = 0, m_wait_full = 0;
     const long long m_t0 = clock64();
     const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
-    auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc) {
+    auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc, bool tiled) {
       long long tw = clock64();
-      mbar_wait(s.x_full, xr_phase);
+      if (!tiled) {
+        mbar_wait(s.x0_full, x0_phase);
+        x0_phase ^= 1;
+        tc_fence_after();
+      }
       m_wait_x += clock64() - tw;
-      xr_phase ^= 1;
-      tc_fence_after();
+      uint32_t waited = 0;
       const uint32_t bh = umma_desc_lo(smem_u32(b_hi)), bl = umma_desc_lo(smem_u32(b_lo));
       for (int mt = 0; mt < MTl; ++mt) {
         const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
-        for (int kc = 0; kc < KCl; ++kc) {
+        for (int j = 0; j < KCl; ++j) {
+          int kc = j;
+          if (tiled) {
+            kc = j + rot;
+            if (kc >= KCl) kc -= KCl;
+            const uint32_t t = uint32_t(kc) >> 1;
+            if (!((waited >> t) & 1u)) {
+              tw = clock64();
+              mbar_wait(&s.x_full[t], (xf_phase >> t) & 1u);
+              m_wait_x += clock64() - tw;
+              tc_fence_after();
+              waited |= 1u << t;
+            }
+          }
           const uint32_t boff = uint32_t(kc) * (NE * 128 / 16);
           tw = clock64();
           mbar_wait(&s.full[stage], phase);
@@ -233,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           tc_fence_after();
           if (elect_one()) {
             const uint32_t wa = ring_lo + stage * (kTile / 16);
-            if (acc || kc > 0) {
+            if (acc || j > 0) {
               umma_bf16_lo(d, wa, bh + boff, idesc, true);
             } else {
               umma_bf16_lo(d, wa, bh + boff, idesc, false);
@@ -264,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         }
       }
+      xf_phase ^= waited;
       if (elect_one()) umma_commit(s.layer_done);
       __syncwarp();
     };
@@ -271,16 +303,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
       if (a.CH && net != cur_net) {
-        run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false);
-        run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false);
+        run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false, false);
+        run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false, false);
       }
       cur_net = net;
-      run_layer(s.x0_hi, s.x0_lo, MTo, a.KC0, col_h, false);
+      run_layer(s.x0_hi, s.x0_lo, MTo, a.KC0, col_h, false, false);
       for (int b = 0; b < a.nb; ++b) {
-        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_y, false);
-        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_h, true);
+        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_y, false, true);
+        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_h, true, true);
       }
-      run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false);
+      run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false, true);
     }
     if (a.prof && lane == 0) {
       a.prof[blockIdx.x * 16 + 2] = m_wait_x, a.prof[blockIdx.x * 16 + 3] = m_wait_full;
@@ -330,6 +362,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         ++hs;
       }
     };
+    // before an exchange layer's epilogue: this CTA's barriers of the PEERS' tiles expect the bytes their owners will push
+    // (the bytes may land first: the transaction count is signed)
+    auto expect_peer_tiles = [&]() {
+      if (C > 1 && et == 0) {
+        for (int t = 0; t < a.MT; ++t)
+          if (t < mt0 || t >= mt0 + MTo) mbar_arrive_expect_tx(&s.x_full[t], 2u * NE * 128u * uint32_t(a.nsplit));
+      }
+    };
     // hand the operand written by this epilogue over to the MMA warp (and, for an exchange layer, to the peers)
     const uint32_t blk_chunks = 2u * uint32_t(MTo), blk_bytes = blk_chunks * NE * 128u;  // this CTA's column block of X
     const uint32_t blk_off = uint32_t(mt0) * 2u * NE * 128u;
@@ -337,25 +377,29 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // the first tiles overlaps the arithmetic of the later ones), signal_x pushes the last tile and posts the expected
     // byte count (peers' bytes may land before it: the transaction count is signed).
     const uint32_t tile_bytes = 2u * NE * 128u;  // one M tile = two 64-feature chunks of X
-    auto push_tile = [&](int mt) {
+    // tile `mt` of this CTA's block is complete in shared memory: copy it into the peers (completing on THEIR barrier of
+    // that tile) and release it to this CTA's MMA warp
+    auto publish_tile = [&](int mt) {
       const uint32_t off = blk_off + uint32_t(mt) * tile_bytes;
+      uint64_t* bar = &s.x_full[mt0 + mt];
       for (uint32_t p = 0; p < uint32_t(C); ++p) {
         if (p == rank) continue;
-        bulk_s2peer(s.x_hi + off, s.x_hi + off, tile_bytes, s.x_full, p);
-        if (split) bulk_s2peer(s.x_lo + off, s.x_lo + off, tile_bytes, s.x_full, p);
+        bulk_s2peer(s.x_hi + off, s.x_hi + off, tile_bytes, bar, p);
+        if (split) bulk_s2peer(s.x_lo + off, s.x_lo + off, tile_bytes, bar, p);
       }
+      mbar_arrive(bar);
     };
+    // `exchange`: the epilogue wrote (the last tile of) this CTA's block of X; otherwise a whole-operand hand-off
     auto signal_x = [&](bool exchange) {
       tmem_wait_st();
       tc_fence_before();
       fence_proxy_async_smem();
       named_bar_sync(1, kEpiThreads);
       if (et == 0) {
-        if (exchange && C > 1) {
-          mbar_arrive_expect_tx(s.x_full, uint32_t(C - 1) * blk_bytes * uint32_t(a.nsplit));
-          push_tile(MTo - 1);
+        if (exchange) {
+          publish_tile(MTo - 1);
         } else {
-          mbar_arrive(s.x_full);
+          mbar_arrive(s.x0_full);
         }
       }
     };
@@ -499,10 +543,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
                 __floats2bfloat162_rn(fa - __low2float(h2), fb - __high2float(h2));
         }
         if (push && mt + 1 < MTl) {
-          // tile mt of this CTA's block is complete in shared memory: start its copy into the peers now
+          // tile mt of this CTA's block is complete in shared memory: hand it to the MMA warp and the peers now
+          tc_fence_before();
           fence_proxy_async_smem();
           named_bar_sync(1, kEpiThreads);
-          if (et == 0) push_tile(mt);
+          if (et == 0) publish_tile(mt);
         }
       }
     };
@@ -604,7 +649,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         }
         prefetch_side(mt_first, MTl, ba, bb, lg, lb);
         wait_layer(L >= 0);
-        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0, L >= 0 && C > 1);
+        if (L >= 0) expect_peer_tiles();
+        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0, L >= 0);
         signal_x(L >= 0);
       }
       cur_net = net;
