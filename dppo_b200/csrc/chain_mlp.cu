@@ -35,6 +35,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTile = 16384;
+constexpr uint32_t kPeerBar = 8;  // x_full[] slot (after the 8 tile slots) shared by every peer tile when each CTA owns a single M tile
 constexpr int kMaxStages = 12;
 
 struct ChainArgs {
@@ -117,7 +118,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
-  s.x_full = reinterpret_cast<uint64_t*>(p), p += 64;   // one barrier per M tile (= K-chunk pair) of X, MT <= 8
+  s.x_full = reinterpret_cast<uint64_t*>(p), p += 72;   // one barrier per M tile (= K-chunk pair) of X, MT <= 8, + kPeerBar
   s.x0_full = reinterpret_cast<uint64_t*>(p), p += 8;   // layer-0 / cond_mlp operands (written as a whole)
   s.can_send = reinterpret_cast<uint64_t*>(p), p += 16;  // two barriers, used alternately (see wait_layer)
   s.ln_bar = reinterpret_cast<uint64_t*>(p), p += 8;
@@ -129,7 +130,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
 
 static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
   const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
-  return xb + x0b + 16 * kMaxStages + 160 + kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 + 1024 /* alignment slack */;
+  return xb + x0b + 16 * kMaxStages + 176 + kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 + 1024 /* alignment slack */;
 }
 
 // ============================================================================================== the kernel
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       mbar_init(&s.empty[i], 1);
     }
     mbar_init(s.layer_done, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&s.x_full[i], 1);
+    for (int i = 0; i < 9; ++i) mbar_init(&s.x_full[i], 1);
     mbar_init(s.x0_full, 1);
     mbar_init(&s.can_send[0], C > 1 ? C - 1 : 1);
     mbar_init(&s.can_send[1], C > 1 ? C - 1 : 1);
@@ -180,11 +181,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // `rot`: the K chunks are visited starting at chunk `rot` (wrapping): layers that read X start with the chunks this
     // CTA produced itself, which are ready first (see the MMA warp)
     auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot) {
-      for (int mt = m_begin; mt < m_end; ++mt) {
-        const uint8_t* src = base + size_t(mt) * KCl * a.nsplit * kTile;
-        for (int j = 0; j < KCl; ++j) {
-          int kc = j + rot;
-          if (kc >= KCl) kc -= KCl;
+      // chunk-major: every output tile consumes K chunk kc before anybody touches the next chunk, so one arrived tile of
+      // X feeds (m_end - m_begin) x 2 tile-MMAs before the next one is needed
+      for (int j = 0; j < KCl; ++j) {
+        int kc = j + rot;
+        if (kc >= KCl) kc -= KCl;
+        for (int mt = m_begin; mt < m_end; ++mt) {
+          const uint8_t* src = base + size_t(mt) * KCl * a.nsplit * kTile;
           for (int h = 0; h < a.nsplit; ++h) {
             const long long tw = clock64();
             mbar_wait(&s.empty[stage], phase ^ 1);
@@ -241,23 +244,24 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       m_wait_x += clock64() - tw;
       uint32_t waited = 0;
       const uint32_t bh = umma_desc_lo(smem_u32(b_hi)), bl = umma_desc_lo(smem_u32(b_lo));
-      for (int mt = 0; mt < MTl; ++mt) {
-        const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
-        for (int j = 0; j < KCl; ++j) {
-          int kc = j;
-          if (tiled) {
-            kc = j + rot;
-            if (kc >= KCl) kc -= KCl;
-            const uint32_t t = uint32_t(kc) >> 1;
-            if (!((waited >> t) & 1u)) {
-              tw = clock64();
-              mbar_wait(&s.x_full[t], (xf_phase >> t) & 1u);
-              m_wait_x += clock64() - tw;
-              tc_fence_after();
-              waited |= 1u << t;
-            }
+      for (int j = 0; j < KCl; ++j) {
+        int kc = j;
+        if (tiled) {
+          kc = j + rot;
+          if (kc >= KCl) kc -= KCl;
+          uint32_t t = uint32_t(kc) >> 1;
+          if (MTo == 1 && int(t) != mt0) t = kPeerBar;  // one tile per CTA: all the peers' tiles share one barrier
+          if (!((waited >> t) & 1u)) {
+            tw = clock64();
+            mbar_wait(&s.x_full[t], (xf_phase >> t) & 1u);
+            m_wait_x += clock64() - tw;
+            tc_fence_after();
+            waited |= 1u << t;
           }
-          const uint32_t boff = uint32_t(kc) * (NE * 128 / 16);
+        }
+        const uint32_t boff = uint32_t(kc) * (NE * 128 / 16);
+        for (int mt = 0; mt < MTl; ++mt) {
+          const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
           tw = clock64();
           mbar_wait(&s.full[stage], phase);
           m_wait_full += clock64() - tw;
@@ -366,8 +370,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // (the bytes may land first: the transaction count is signed)
     auto expect_peer_tiles = [&]() {
       if (C > 1 && et == 0) {
-        for (int t = 0; t < a.MT; ++t)
-          if (t < mt0 || t >= mt0 + MTo) mbar_arrive_expect_tx(&s.x_full[t], 2u * NE * 128u * uint32_t(a.nsplit));
+        if (MTo == 1) {  // (C - 1) single-tile blocks land on the shared barrier: one wait instead of C - 1
+          mbar_arrive_expect_tx(&s.x_full[kPeerBar], uint32_t(C - 1) * 2u * NE * 128u * uint32_t(a.nsplit));
+        } else {
+          for (int t = 0; t < a.MT; ++t)
+            if (t < mt0 || t >= mt0 + MTo) mbar_arrive_expect_tx(&s.x_full[t], 2u * NE * 128u * uint32_t(a.nsplit));
+        }
       }
     };
     // hand the operand written by this epilogue over to the MMA warp (and, for an exchange layer, to the peers)
@@ -382,10 +390,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     auto publish_tile = [&](int mt) {
       const uint32_t off = blk_off + uint32_t(mt) * tile_bytes;
       uint64_t* bar = &s.x_full[mt0 + mt];
+      uint64_t* peer_bar = MTo == 1 ? &s.x_full[kPeerBar] : bar;  // where this tile is accounted at the receivers
       for (uint32_t p = 0; p < uint32_t(C); ++p) {
         if (p == rank) continue;
-        bulk_s2peer(s.x_hi + off, s.x_hi + off, tile_bytes, bar, p);
-        if (split) bulk_s2peer(s.x_lo + off, s.x_lo + off, tile_bytes, bar, p);
+        bulk_s2peer(s.x_hi + off, s.x_hi + off, tile_bytes, peer_bar, p);
+        if (split) bulk_s2peer(s.x_lo + off, s.x_lo + off, tile_bytes, peer_bar, p);
       }
       mbar_arrive(bar);
     };
