@@ -333,6 +333,39 @@ def bench_update(args, w, model, dev, E, rank, world):
         for s in range(0, N, chunk):
             logprobs_k[s:s + chunk] = model.get_logprobs({"state": obs_k[s:s + chunk]}, chains_k[s:s + chunk]).view(-1, ft, Ta, Da)
         values_k = model.critic({"state": obs_k}).view(-1)
+    # ---- once-per-iteration prologue (reference train_ppo_diffusion_agent.py:197-279): old log-probs of every stored
+    # chain (dppo_chain_logprobs, teacher-forced chain kernel), running reward scaling + GAE (float64 scan kernels)
+    from dppo_b200 import engine as E_
+    from dppo_b200.util.reward_scaling import RunningRewardScalerCUDA
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    def all_logprobs():
+        with torch.no_grad():
+            for s0 in range(0, N, chunk):
+                model.get_logprobs({"state": obs_k[s0:s0 + chunk]}, chains_k[s0:s0 + chunk])
+
+    lp_ms = timed(all_logprobs)
+    scaler = RunningRewardScalerCUDA(E, dev)
+    rew = torch.randn((n_steps, E), dtype=torch.float64, device=dev, generator=g)
+    firsts = (torch.rand((n_steps, E), device=dev, generator=g) < 0.01).double()
+    term = (torch.rand((n_steps, E), device=dev, generator=g) < 0.01).double()
+    vals = values_k.view(n_steps, E).double()
+    nxt = torch.randn(E, dtype=torch.float64, device=dev, generator=g)
+    gae_ms = timed(lambda: E_.gae(scaler(reward=rew, first=firsts), term, vals, nxt, 0.99, 0.95, 1.0), reps=10)
+    prologue = {"logprob_rows_per_s": N * ft / (lp_ms * 1e-3), "logprob_ms": lp_ms, "rows": N * ft,
+                "reward_scaling_plus_gae_ms": gae_ms, "gae_elements": n_steps * E,
+                "gae_GBps_algorithmic": 20.0 * n_steps * E / (gae_ms * 1e-3) / 1e9,
+                "path": "dppo_chain_logprobs (chain kernel, teacher-forced over the ft window); dppo_reward_scale_f64 + dppo_gae_f64"}
     adv_k = torch.randn(N, device=dev, generator=g)
     ret_k = adv_k + values_k
     from dppo_b200 import distributed as D
@@ -393,7 +426,7 @@ def bench_update(args, w, model, dev, E, rank, world):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
-            "minibatch_rows": per_rank * world, "buffer_rows": N * ft,
+            "minibatch_rows": per_rank * world, "buffer_rows": N * ft, "prologue_per_gpu": prologue,
             "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
                      "Linear layers as 3-product bf16-split tensor-core GEMMs (dppo_split3_pack + cuBLASLt bf16, fp32 accumulate) under "
                      "torch autograd; fused flat AdamW kernel per network; "

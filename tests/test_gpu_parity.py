@@ -241,3 +241,24 @@ def test_zero_copy_pinned_io_matches_device_io(case):
     torch.cuda.synchronize()
     assert got.trajectories.data_ptr() == h_traj.data_ptr() and not got.chains.is_cuda
     assert torch.equal(h_traj, want.trajectories.cpu()) and torch.equal(h_chain, want.chains.cpu())
+
+
+@pytest.mark.parametrize("workload,n_envs,tile_envs,cluster,launches", [
+    ("walker2d", 4096, 64, 2, 3000), ("walker2d", 2048, 32, 4, 3000), ("furniture", 500, 32, 4, 2000),
+    ("transport_k20", 50, 16, 8, 2000), ("square_unet", 512, 16, 2, 1500), ("hopper", 40, 0, -1, 5000),
+])
+def test_back_to_back_launch_stress(workload, n_envs, tile_envs, cluster, launches):
+    """Protocol stress: thousands of back-to-back launches of every cluster protocol (a handshake race once hung one launch
+    in ~3000; the bounded mbarrier waits turn such a hang into a trapped launch, i.e. a CUDA error here)."""
+    w = get_workload(workload)
+    model = build_model(w, "cuda:0", our_classes())
+    eng = model.engine()
+    eng.set_launch_shape(tile_envs, cluster)
+    state = torch.rand(n_envs, 1, w["obs_dim"], device="cuda") * 2 - 1
+    first = eng.sample(state, seed=3, offset=1)[0].clone()
+    for i in range(launches):
+        traj, _ = eng.sample(state, seed=3, offset=1)
+        if i % 256 == 255:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(traj, first)  # same Philox keys -> bit-identical results on every launch
