@@ -12,12 +12,16 @@
 // The residual add is free: the second Linear of a block accumulates straight onto h in TMEM.
 //
 // Feature-split clusters: the kernel is bound by how fast ONE SM can pull weight tiles out of L2 (~35 B/cycle/SM measured,
-// profiles/r1a_microbench.txt), and a CTA that owns all features of its environments must pull the whole network every
+// profiles/earlier/r1a_microbench.txt), and a CTA that owns all features of its environments must pull the whole network every
 // step.  A cluster of C CTAs therefore shares one tile of NE environments: CTA r computes the M-tiles
 // [r*MT/C, (r+1)*MT/C) of every hidden layer (streaming only 1/C of the weights), writes its activations into its own
 // copy of X and pushes that column block into the peers' copies with one bulk shared::cta -> shared::cluster copy per
-// peer and operand half (the copy completes on the peer's x_full mbarrier).  The tiny output layer, the posterior step
-// and the layer-0 operand are computed redundantly by every CTA, so nothing else crosses CTAs.
+// peer, operand half and M tile (the copy completes on the peer's x_full[tile] mbarrier).  The tiny output layer, the
+// posterior step and the layer-0 operand are computed redundantly by every CTA, so nothing else crosses CTAs.
+//
+// Layer pipelining: X is handed over M tile by M tile (x_full[t]); layers that read X visit the K chunks
+// own-tiles-first and chunk-major, and consecutive layers alternate between the two TMEM regions, so the MMAs of layer
+// l+1 start while the epilogue of layer l is still writing its later tiles and the peers' blocks are in flight.
 //
 // Warp roles (320 threads): warp 0 = weight-tile producer, warp 1 = MMA issuer (+ TMEM allocator),
 // warps 2..9 = epilogue (TMEM -> registers -> bias / LayerNorm / activation -> bf16 split -> shared memory, and the
@@ -379,11 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       }
     };
     // hand the operand written by this epilogue over to the MMA warp (and, for an exchange layer, to the peers)
-    const uint32_t blk_chunks = 2u * uint32_t(MTo), blk_bytes = blk_chunks * NE * 128u;  // this CTA's column block of X
-    const uint32_t blk_off = uint32_t(mt0) * 2u * NE * 128u;
-    // The block is pushed M tile by M tile: the epilogue pushes tile mt as soon as its columns are written (the copy of
-    // the first tiles overlaps the arithmetic of the later ones), signal_x pushes the last tile and posts the expected
-    // byte count (peers' bytes may land before it: the transaction count is signed).
+    const uint32_t blk_off = uint32_t(mt0) * 2u * NE * 128u;  // this CTA's column block of X starts here
+    // The block is published M tile by M tile: the epilogue releases tile mt as soon as its columns are written (its copy
+    // into the peers overlaps the arithmetic of the later tiles), signal_x releases the last one.
     const uint32_t tile_bytes = 2u * NE * 128u;  // one M tile = two 64-feature chunks of X
     // tile `mt` of this CTA's block is complete in shared memory: copy it into the peers (completing on THEIR barrier of
     // that tile) and release it to this CTA's MMA warp
