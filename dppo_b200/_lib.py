@@ -53,7 +53,8 @@ class ULayer(C.Structure):
     _fields_ = [("n_gemm", C.c_int32), ("g", UGemm * 2)] + [(n, C.c_int32) for n in (
         "kind", "acc_tile", "mt", "nf", "bias_off", "bias_tstride", "gn_size", "gamma_off", "beta_off")] + [
         ("gn_eps", C.c_float)] + [(n, C.c_int32) for n in (
-            "act", "film", "film_c", "film_tshift", "res", "res_acc_tile", "res_bias_off", "res_chunk", "dst_chunk", "track")]
+            "act", "film", "film_c", "film_tshift", "res", "res_acc_tile", "res_bias_off", "res_chunk", "dst_chunk", "track",
+            "wait_chunk", "wait_tiles")]
 
 
 class SchedDesc(C.Structure):

@@ -87,7 +87,7 @@ __device__ __forceinline__ float act_f(float x) {
 struct USmem {
   uint8_t *op_hi, *op_lo, *ring;
   float *film, *eps;
-  uint64_t *full, *empty, *layer_done, *x_full, *film_full, *film_free;
+  uint64_t *full, *empty, *layer_done, *x_full, *xt_full, *film_full, *film_free;
   uint32_t* tmem_slot;
   uint32_t film_stride;  // floats between the two FiLM buffers
 };
@@ -96,7 +96,7 @@ __host__ __device__ inline size_t usmem_fixed_bytes(int NE, int total_chunks, in
   const size_t op = size_t(total_chunks) * NE * 128 * nsplit;
   const size_t film = C * ((size_t(NE) * film_dim * 4 + 127) & ~size_t(127));
   const size_t eps = (size_t(NE) * D * 4 + 127) & ~size_t(127);
-  return op + film + eps + 16 * kMaxStages + 96 + 1024 /* alignment slack */;
+  return op + film + eps + 16 * kMaxStages + 160 + 1024 /* alignment slack */;
 }
 
 template <int NE>
@@ -115,6 +115,7 @@ __device__ __forceinline__ USmem ucarve(uint8_t* base, const UArgs& a) {
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
   s.x_full = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.xt_full = reinterpret_cast<uint64_t*>(p), p += 64;  // per-M-tile hand-off of the main path (track-split pairs)
   s.film_full = reinterpret_cast<uint64_t*>(p), p += 16;
   s.film_free = reinterpret_cast<uint64_t*>(p), p += 16;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p);
@@ -134,6 +135,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
   const int rank = C > 1 ? int(cluster_ctarank()) : 0;
   const int my_track = C > 1 ? rank : -1;  // -1: this CTA runs every layer
   const int env0 = (blockIdx.x / C) * NE;
+  // Main-path CTA of a pair: its layers form a strict chain (every layer consumes its predecessor's output), so the
+  // operand is handed over M tile by M tile (xt_full[t]) and consecutive layers use different accumulator sets
+  // (unet_plan.cu): the MMAs of layer l+1 start on tile 0 while the epilogue of layer l is still writing tile 1.
+  // The encoder CTA and the single-CTA mode keep the whole-operand hand-off (x_full): their layers are not a chain.
+  const bool tiled = C > 1 && rank == 0;
   constexpr uint32_t kChunk = NE * 128u;  // bytes of one 64-feature operand chunk (one half)
 
   if (threadIdx.x == 0) {
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     }
     mbar_init(s.layer_done, 1);
     mbar_init(s.x_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&s.xt_full[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.film_full[i], kEpiThreads);  // every epilogue thread of the encoder CTA arrives after its own stores
       mbar_init(&s.film_free[i], 1);
@@ -171,18 +178,22 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         for (int gi = 0; gi < n_gemm; ++gi) {
           const UGemm G = L->g[gi];
           const uint8_t* src = a.tiles[net] + size_t(G.tile_off) * kTile;
-          const uint32_t n = uint32_t(G.mt) * G.kc * uint32_t(a.nsplit);
-          for (uint32_t i = 0; i < n; ++i) {
-            const long long tw = clock64();
-            mbar_wait(&s.empty[stage], phase ^ 1);
-            p_wait += clock64() - tw;
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&s.full[stage], kTile);
-              bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(i) * kTile, kTile, &s.full[stage]);
-            }
-            __syncwarp();
-            if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
-          }
+          // chunk-major (every output tile consumes K chunk kc before the next chunk is touched); in memory the tiles of
+          // a GEMM are m-tile major, k-chunk minor, hi then lo
+          for (uint32_t kc = 0; kc < uint32_t(G.kc); ++kc)
+            for (uint32_t mt = 0; mt < uint32_t(G.mt); ++mt)
+              for (uint32_t h = 0; h < uint32_t(a.nsplit); ++h) {
+                const size_t i = (size_t(mt) * G.kc + kc) * a.nsplit + h;
+                const long long tw = clock64();
+                mbar_wait(&s.empty[stage], phase ^ 1);
+                p_wait += clock64() - tw;
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&s.full[stage], kTile);
+                  bulk_g2s(s.ring + size_t(stage) * kTile, src + i * kTile, kTile, &s.full[stage]);
+                }
+                __syncwarp();
+                if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
+              }
         }
       }
     }
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, NE);
-    uint32_t stage = 0, phase = 0, xr_phase = 0;
+    uint32_t stage = 0, phase = 0, xr_phase = 0, xt_phase = 0;
     const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
     const uint32_t op_hi = umma_desc_lo(smem_u32(s.op_hi)), op_lo = umma_desc_lo(smem_u32(s.op_lo));
     long long m_wait_x = 0, m_wait_full = 0;
@@ -201,20 +212,34 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         if (my_track >= 0 && L->track != my_track) continue;
         const int n_gemm = L->n_gemm;
         const UGemm G0 = L->g[0], G1 = L->g[1];  // fetched while the previous epilogue is still running
+        const uint32_t wait_chunk = uint32_t(L->wait_chunk), wait_tiles = uint32_t(L->wait_tiles);
+        uint32_t waited = 0;
         long long tw = clock64();
-        mbar_wait(s.x_full, xr_phase);
+        if (!tiled) {
+          mbar_wait(s.x_full, xr_phase);
+          xr_phase ^= 1;
+          tc_fence_after();
+        }
         m_wait_x += clock64() - tw;
-        xr_phase ^= 1;
-        tc_fence_after();
         for (int gi = 0; gi < n_gemm; ++gi) {
           const UGemm G = gi == 0 ? G0 : G1;
-          for (int mt = 0; mt < int(G.mt); ++mt) {
-            const uint32_t d = tmem + uint32_t(G.acc_tile + mt) * NE;
-            for (int kc = 0; kc < int(G.kc); ++kc) {
-              const uint32_t chunk = kc < int(G.src_n[0]) ? uint32_t(G.src_chunk[0]) + kc
-                                                          : uint32_t(G.src_chunk[1]) + (kc - int(G.src_n[0]));
-              const uint32_t boff = chunk * (kChunk / 16);
-              const uint32_t bh = op_hi + boff, bl = op_lo + boff;
+          for (int kc = 0; kc < int(G.kc); ++kc) {
+            const uint32_t chunk = kc < int(G.src_n[0]) ? uint32_t(G.src_chunk[0]) + kc
+                                                        : uint32_t(G.src_chunk[1]) + (kc - int(G.src_n[0]));
+            if (tiled && chunk >= wait_chunk && chunk < wait_chunk + 2 * wait_tiles) {
+              const uint32_t t = (chunk - wait_chunk) >> 1;  // tile of the predecessor's output this chunk belongs to
+              if (!((waited >> t) & 1u)) {
+                tw = clock64();
+                mbar_wait(&s.xt_full[t], (xt_phase >> t) & 1u);
+                m_wait_x += clock64() - tw;
+                tc_fence_after();
+                waited |= 1u << t;
+              }
+            }
+            const uint32_t boff = chunk * (kChunk / 16);
+            const uint32_t bh = op_hi + boff, bl = op_lo + boff;
+            for (int mt = 0; mt < int(G.mt); ++mt) {
+              const uint32_t d = tmem + uint32_t(G.acc_tile + mt) * NE;
               tw = clock64();
               mbar_wait(&s.full[stage], phase);
               m_wait_full += clock64() - tw;
@@ -253,6 +278,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             }
           }
         }
+        if (tiled) {
+          // keep the tile barriers in step even if this layer did not read every tile of its predecessor's output
+          for (uint32_t t = 0; t < wait_tiles; ++t)
+            if (!((waited >> t) & 1u)) {
+              mbar_wait(&s.xt_full[t], (xt_phase >> t) & 1u);
+              waited |= 1u << t;
+            }
+          xt_phase ^= waited;
+        }
         if (elect_one()) umma_commit(s.layer_done);
         __syncwarp();
       }
@@ -284,11 +318,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
       ld_phase ^= 1;
       tc_fence_after();
     };
-    auto signal_x = [&]() {
+    // whole-operand hand-off, or (main path of a pair) release of tile `t` of this layer's output
+    auto signal_x = [&](int t) {
       tc_fence_before();
       fence_proxy_async_smem();
       named_bar_sync(1, kEpiThreads);
-      if (et == 0) mbar_arrive(s.x_full);
+      if (et == 0) mbar_arrive(tiled ? &s.xt_full[t] : s.x_full);
     };
     // operand store of one value (prologue / posterior; the layer epilogues use packed pairs)
     auto store_op = [&](int chunk0, int row, int k, float v) {
@@ -335,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         }
         xreg[j] = x;
       }
-      signal_x();
+      signal_x(0);
     }
 
     // ------------------------------------------------------------------------------------ step loop
@@ -449,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
                 *reinterpret_cast<__nv_bfloat162*>(s.op_lo + dst_base + off) =
                     __floats2bfloat162_rn(fa - __low2float(h2), fb - __high2float(h2));
             }
+            if (tiled && mt + 1 < MTl) signal_x(mt);  // tile mt is complete: the next layer's MMAs may consume it
           }
           if (film && C > 1) {
             // every epilogue thread is done reading the buffer: hand it back to the encoder CTA
@@ -554,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             store_op(a.chunk_x, e, x_feature(f), xn);
           }
         }
-        signal_x();
+        signal_x(kind == U_EPI_OPERAND ? MTl - 1 : 0);
       }
     }
     if (a.prof && et == 0) a.prof[blockIdx.x * 16 + 5] = e_wait, a.prof[blockIdx.x * 16 + 6] = clock64() - e_t0, a.prof[blockIdx.x * 16 + 7] = e_film;

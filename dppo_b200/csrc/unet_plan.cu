@@ -233,10 +233,13 @@ int unet_build_plan(const dppo_unet_desc& d, int K, int precision, UnetPlan* out
   P.MTmax = P.KA / 2;
   P.film_dim = fdmax;
   P.KX = cdiv(P.D, 64), P.KS = cdiv(d.cond_dim, 64);
+  // every slot a layer epilogue writes starts on an even chunk: an M tile of 128 features is a chunk PAIR, the unit of
+  // the tile hand-off (the sample / observation slots are written element-wise and only need to come first)
   int c = 0;
   P.chunk_x = c, c += P.KX;
   P.chunk_state = c, c += P.KS;
   if (!d.larger_encoder) P.chunk_state_act = c, c += P.KS;
+  c = round_up(c, 2);
   P.n_condh = round_up(cdiv(fdmax, 64), 2);
   P.chunk_condh = c, c += P.n_condh;
   const int chunk_h = c;
@@ -321,11 +324,38 @@ int unet_build_plan(const dppo_unet_desc& d, int K, int precision, UnetPlan* out
   P.n_params = B.pc;
   P.n_side = B.side;
   P.n_tiles = B.tile;
+  // Main-path layers alternate between two accumulator sets (TMEM tiles [0, 2 MTmax) and [2 MTmax, 4 MTmax)): the MMAs
+  // of layer l+1 may then start while the epilogue of layer l is still reading its accumulators.  Each main-path layer
+  // also records which chunks its predecessor writes.
+  {
+    int n_main = 0, prev = -1, last_main = -1;
+    for (size_t i = 0; i < P.layers.size(); ++i)
+      if (P.layers[i].track == 0) last_main = int(i);
+    prev = last_main;  // cyclic: the output layer (posterior) precedes the first layer of the next step
+    for (size_t i = 0; i < P.layers.size(); ++i) {
+      ULayer& L = P.layers[i];
+      if (L.track != 0) continue;
+      if (n_main & 1) {
+        const int base = 2 * P.MTmax;
+        L.acc_tile += base;
+        if (L.res == U_RES_ACC) L.res_acc_tile += base;
+        for (int gi = 0; gi < L.n_gemm; ++gi) L.g[gi].acc_tile = uint16_t(L.g[gi].acc_tile + base);
+      }
+      const ULayer& Q = P.layers[prev];
+      if (Q.kind == U_EPI_EPS) {
+        L.wait_chunk = P.chunk_x, L.wait_tiles = 1;
+      } else {
+        L.wait_chunk = Q.dst_chunk, L.wait_tiles = Q.mt;
+      }
+      prev = int(i);
+      ++n_main;
+    }
+  }
   for (const ULayer& L : P.layers) {
     ++P.track_layers[L.track];
     for (int gi = 0; gi < L.n_gemm; ++gi) P.track_tiles[L.track] += size_t(L.g[gi].mt) * L.g[gi].kc * P.nsplit;
   }
-  if (2 * P.MTmax * 16 > 512) return set_error("unet: %d features per activation exceed the TMEM budget", P.MTmax * 128), DPPO_ERR_UNSUPPORTED;
+  if (4 * P.MTmax * 16 > 512) return set_error("unet: %d features per activation exceed the TMEM budget", P.MTmax * 128), DPPO_ERR_UNSUPPORTED;
   return DPPO_OK;
 }
 

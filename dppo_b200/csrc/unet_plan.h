@@ -44,6 +44,9 @@ struct ULayer {
   int32_t res_acc_tile, res_bias_off, res_chunk;
   int32_t dst_chunk;               // operand chunk the result is written to (U_EPI_OPERAND)
   int32_t track;                   // 0 = main path (x -> eps), 1 = FiLM conditioning encoders (depend on t and obs only)
+  // main path only: the operand chunks written by the PREVIOUS main-path layer (cyclically: the first layer of a step
+  // waits for the sample x written by the posterior).  The track-split kernel hands those over M tile by M tile.
+  int32_t wait_chunk, wait_tiles;
 };
 
 enum : int32_t { U_PACK_LINEAR = 0, U_PACK_CONV = 1, U_PACK_CONVT = 2 };

@@ -65,7 +65,7 @@ def run_program(plan, x, t, state, act="Mish"):
     if plan.chunk_state_act >= 0:
         op[:, plan.chunk_state_act * 64: plan.chunk_state_act * 64 + state.shape[1]] = actf(state)
     film = np.zeros((B, plan.film_dim), dtype=np.float64)
-    acc = np.zeros((B, 2 * plan.MTmax * 128), dtype=np.float64)
+    acc = np.zeros((B, 4 * plan.MTmax * 128), dtype=np.float64)
     side = plan.side.astype(np.float64)
     job = 0
     eps = None
@@ -106,6 +106,20 @@ def run_program(plan, x, t, state, act="Mish"):
         else:
             eps = v[:, :D].reshape(B, Ta, Da)  # rows are time-major: flat index t * Da + d
     assert job == plan.n_jobs
+    # main-path bookkeeping of the tile hand-off: consecutive main layers use different accumulator sets and every one of
+    # them names the chunks its (cyclic) predecessor writes
+    main = [L for L in plan.layers if L.track == 0]
+    for prev, cur in zip([main[-1]] + main[:-1], main):
+        assert (prev.acc_tile >= 2 * plan.MTmax) != (cur.acc_tile >= 2 * plan.MTmax)
+        if prev.kind == EPI_EPS:
+            assert (cur.wait_chunk, cur.wait_tiles) == (plan.chunk_x, 1)
+        else:
+            assert (cur.wait_chunk, cur.wait_tiles) == (prev.dst_chunk, prev.mt)
+        srcs = set()
+        for gi in range(cur.n_gemm):
+            G = cur.g[gi]
+            srcs |= set(range(G.src_chunk[0], G.src_chunk[0] + G.src_n[0])) | set(range(G.src_chunk[1], G.src_chunk[1] + G.src_n[1]))
+        assert cur.wait_chunk in srcs  # a main-path layer always consumes its predecessor's output
     return eps
 
 
