@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-1e evidence: default bench (plain), ncu launch list of the same command, full captures of the three chain kernels
+# evidence recipe of a round: default bench (both arms), ncu launch list of the same command, one full capture per chain kernel and of the update kernels.  usage: gpurun -- bash scripts/gpu_evidence.sh (edit the r1h tag)
 mkdir -p gpurun_out
 timeout 600 python bench.py > gpurun_out/bench_r1h.json 2> gpurun_out/bench_r1h.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1h_ref.json 2>/dev/null; echo "ref rc=$?"
