@@ -312,3 +312,10 @@ def test_dense_lowered_convs_match_float64_convs(kind, cin, cout, ks, stride, pa
                        ("db", mod.bias.grad, bd.grad)):
         err = float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
         assert err < 5e-5, (name, err)
+
+
+def test_graft_entry_smoke_runs():
+    """The driver's smoke() entry point (one Hopper chain + log-probs against the CPU oracle)."""
+    import __graft_entry__ as g
+
+    g.smoke()
