@@ -119,3 +119,32 @@ def test_flat_grad_buffer_pads_every_tensor_to_16_bytes():
     assert offs == [0, 16, 24] and all(o % 4 == 0 for o in offs)
     a[1].grad.fill_(2.0)
     assert float(buf.flat[16:23].sum()) == 14.0 and float(buf.flat[23]) == 0.0
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines committed under profiles/ (written by bench.py on the GPU box) have every key the contract names."""
+    import glob
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = sorted(glob.glob(os.path.join(root, "profiles", "r1*_bench*.json")))
+    assert lines, "no bench lines under profiles/"
+    for path in lines:
+        d = json.load(open(path))
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"):
+            assert k in d, (path, k)
+        assert d["config"].get("workload") and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+        if d.get("impl") == "reference":
+            assert d["gpu_launches"] == 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+            continue
+        assert d["gpu_launches"] == d["steps"] and d["steps"] > 0 and d["warmup"] >= 3
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["clocks"]["samples"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert d["e2e"]["value"] < d["value"]  # the end-to-end number is never the device-timed one
