@@ -2,7 +2,7 @@
 //   gae_kernel            per-env reverse scan, float64           reference train_ppo_diffusion_agent.py:255-279
 //   logprob_rows_kernel   Gaussian log-density of (x_prev -> x_next) given the network output eps
 //                                                                  reference diffusion_vpg.py:165-224,453-458
-//   adv_stats_kernel      minibatch advantage mean / unbiased std / min / max          diffusion_ppo.py:129-136
+//   adv_partial/finalize  minibatch advantage mean / unbiased std / min / max          diffusion_ppo.py:129-136
 //   ppo_loss_kernel       fused gather + log-prob + clipped-ratio loss + value loss, forward and closed-form backward
 //                         (one group of G lanes per minibatch row, float4 loads, shuffle reductions)
 //                                                                  reference diffusion_ppo.py:57-199, SURVEY.md §3.3
@@ -98,50 +98,47 @@ __global__ void logprob_rows_kernel(const float* __restrict__ eps, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ advantage stats
-// one block; ws[0..3] (double) = mean, unbiased std, min, max of advantages[inds[i] / ft]
-__global__ void adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ inds, int n, int ft,
-                                 double* __restrict__ ws) {  // inds == nullptr: advantages are already per row
-  __shared__ double sh[32];
-  __shared__ double s_mean;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  double acc = 0.0;
+// ws[0..3] (double) = mean, unbiased std, min, max of advantages[inds[i] / ft].  Grid-wide: every block adds its partial
+// sum / sum of squares (double) and its min / max (order-preserving integer keys) into ws[4..7]; a one-thread kernel
+// turns them into the four statistics.  (inds == nullptr: advantages are already per row.)
+__device__ __forceinline__ int float_order_key(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;  // signed-integer order == float order
+}
+__device__ __forceinline__ float float_from_key(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+__global__ void adv_partial_kernel(const float* __restrict__ adv, const int64_t* __restrict__ inds, int n, int ft,
+                                   double* __restrict__ ws) {
+  double s1 = 0.0, s2 = 0.0;
   float mn = INFINITY, mx = -INFINITY;
-  for (int i = tid; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float a = adv[inds ? inds[i] / ft : i];
-    acc += a;
+    s1 += a, s2 += double(a) * double(a);
     mn = fminf(mn, a), mx = fmaxf(mx, a);
   }
   for (int o = 16; o > 0; o >>= 1) {
-    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
-  __shared__ float smn[32], smx[32];
-  if (lane == 0) sh[wid] = acc, smn[wid] = mn, smx[wid] = mx;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    float a = INFINITY, b = -INFINITY;
-    for (int w = 0; w < nw; ++w) t += sh[w], a = fminf(a, smn[w]), b = fmaxf(b, smx[w]);
-    s_mean = t / n;
-    ws[0] = s_mean, ws[2] = a, ws[3] = b;
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&ws[4], s1);
+    atomicAdd(&ws[5], s2);
+    int* keys = reinterpret_cast<int*>(&ws[6]);
+    atomicMin(&keys[0], float_order_key(mn));
+    atomicMax(&keys[1], float_order_key(mx));
   }
-  __syncthreads();
-  const double mean = s_mean;
-  acc = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) {
-    const double d = double(adv[inds ? inds[i] / ft : i]) - mean;
-    acc += d * d;
-  }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __syncthreads();
-  if (lane == 0) sh[wid] = acc;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += sh[w];
-    ws[1] = n > 1 ? sqrt(t / (n - 1)) : NAN;
-  }
+}
+
+__global__ void adv_finalize_kernel(int n, double* __restrict__ ws) {
+  const double mean = ws[4] / n;
+  const double ss = fmax(ws[5] - double(n) * mean * mean, 0.0);
+  const int* keys = reinterpret_cast<const int*>(&ws[6]);
+  ws[0] = mean;
+  ws[1] = n > 1 ? sqrt(ss / (n - 1)) : NAN;
+  ws[2] = float_from_key(keys[0]);
+  ws[3] = float_from_key(keys[1]);
 }
 
 // ------------------------------------------------------------------------------------------------ fused loss
@@ -598,7 +595,14 @@ static int loss_impl(dppo_ctx* ctx, LossArgs a, const int64_t* stat_inds, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* ws = static_cast<double*>(workspace);
   DPPO_CUDA(cudaMemsetAsync(ws, 0, 16 * sizeof(double), st));
-  adv_stats_kernel<<<1, 1024, 0, st>>>(a.adv, stat_inds, a.global_rows, ctx->ft, ws);
+  DPPO_CUDA(cudaMemsetAsync(reinterpret_cast<int*>(ws + 6), 0x7F, sizeof(int), st));      // min key: +3.4e38
+  DPPO_CUDA(cudaMemsetAsync(reinterpret_cast<int*>(ws + 6) + 1, 0x80, sizeof(int), st));  // max key: below every float
+  {
+    int blocks = (a.global_rows + 255) / 256;
+    blocks = blocks > 296 ? 296 : blocks;
+    adv_partial_kernel<<<blocks, 256, 0, st>>>(a.adv, stat_inds, a.global_rows, ctx->ft, ws);
+    adv_finalize_kernel<<<1, 1, 0, st>>>(a.global_rows, ws);
+  }
   a.rows = ctx->d_rows, a.row0 = ctx->S - ctx->ft;
   a.D = D, a.ft = ctx->ft, a.ddim = ctx->use_ddim;
   a.horizon_elems = hp->reward_horizon * hp->action_dim, a.norm_adv = hp->norm_adv;
