@@ -15,10 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libdppo_b200.so")
 SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "umma_selftest.cu", "microbench.cu"]
 HEADERS = ["common.cuh", "internal.h", "unet_plan.h", os.path.join("..", "..", "include", "dppo_b200.h")]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-    "-Xcompiler", "-fPIC",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _stale():
@@ -29,20 +26,32 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources; returns the path."""
+    """Compile the library if it is missing or older than its sources; returns the path.
+    One `nvcc -c` per translation unit, run concurrently, then one link step."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
+
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(os.path.dirname(LIB), "obj")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [o for o, _ in results] + ["-o", LIB]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(out for _, out in results) + res.stdout + res.stderr)
     return LIB
 
 
