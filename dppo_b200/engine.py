@@ -230,6 +230,8 @@ class ChainEngine:
         for name, t, shape in (("out_traj", out_traj, E * self.D), ("out_chain", out_chain, E * (self.ft + 1) * self.D)):
             if t is not None and (t.dtype != torch.float32 or t.numel() != shape):
                 raise RuntimeError(f"{name}: expected {shape} float32 elements")
+        if E == 0:  # nothing to launch (empty tensors have no storage to point at)
+            return traj, chain
         if noise is not None:
             noise = noise.reshape(self.S + 1, E, self.D).contiguous().float()
         _lib.check(
@@ -244,6 +246,8 @@ class ChainEngine:
         state = state.reshape(B, -1).contiguous().float()
         chains = chains.reshape(B, self.ft + 1, self.D).contiguous().float()
         logp = torch.empty((B * self.ft, self.D), dtype=torch.float32, device=chains.device)
+        if B == 0 or self.ft == 0:
+            return logp
         _lib.check(self.lib.dppo_chain_logprobs(self.ctx, _lib.ptr(state), _lib.ptr(chains), B, int(use_base_policy),
                                                 _lib.ptr(logp), _lib.stream_ptr()), "dppo_chain_logprobs")
         return logp

@@ -262,3 +262,30 @@ def test_back_to_back_launch_stress(workload, n_envs, tile_envs, cluster, launch
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     assert torch.equal(traj, first)  # same Philox keys -> bit-identical results on every launch
+
+
+def test_empty_and_multi_wave_batches():
+    """E = 0 is a no-op; E = 20 011 (ragged, several waves of CTAs) matches the oracle on the first / last rows."""
+    from oracle import dppo_oracle as O
+
+    w = get_workload("hopper")
+    model = build_model(w, "cuda:0", our_classes())
+    ft, Ta, Da = w["ft_denoising_steps"], w["horizon_steps"], w["action_dim"]
+    out = model(cond={"state": torch.zeros(0, 1, w["obs_dim"], device="cuda")})
+    assert out.trajectories.shape == (0, Ta, Da) and out.chains.shape == (0, ft + 1, Ta, Da)
+    E = 20011
+    inp = make_inputs(w, E, 8, seed=11)
+    out = model(cond={"state": inp["state"].cuda()}, noise=inp["noise"].cuda())
+    with torch.no_grad():
+        lp = model.get_logprobs({"state": inp["state"].cuda()}, out.chains)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.chains).all() and torch.isfinite(lp).all()
+    nc, dc = oracle_cfgs(w)
+    p = oracle_params(model)
+    for rows in (slice(0, 48), slice(E - 37, E)):
+        _, chains_o = O.sample_chain(p, nc, dc, inp["state"][rows], inp["noise"][:, rows], faithful_cost=False)
+        assert_close(out.chains[rows].cpu().numpy(), chains_o.numpy(), 1e-3, f"rows {rows}", max_frac=2e-3)
+        lp_o = O.get_logprobs(p, nc, dc, inp["state"][rows], chains_o, faithful_cost=False)
+        n = chains_o.shape[0]
+        got = lp.view(E, ft, Ta, Da)[rows].reshape(n * ft, Ta, Da)
+        assert_close(got.cpu().numpy(), lp_o.numpy(), 2e-3, f"log-probs rows {rows}", max_frac=5e-3)
