@@ -286,6 +286,6 @@ def test_empty_and_multi_wave_batches():
         _, chains_o = O.sample_chain(p, nc, dc, inp["state"][rows], inp["noise"][:, rows], faithful_cost=False)
         assert_close(out.chains[rows].cpu().numpy(), chains_o.numpy(), 1e-3, f"rows {rows}", max_frac=2e-3)
         lp_o = O.get_logprobs(p, nc, dc, inp["state"][rows], chains_o, faithful_cost=False)
-        n = chains_o.shape[0]
-        got = lp.view(E, ft, Ta, Da)[rows].reshape(n * ft, Ta, Da)
-        assert_close(got.cpu().numpy(), lp_o.numpy(), 2e-3, f"log-probs rows {rows}", max_frac=5e-3)
+        with torch.no_grad():  # same chains on both sides (log-probs amplify chain differences by 1 / sigma^2)
+            got = model.get_logprobs({"state": inp["state"][rows].cuda()}, chains_o.cuda())
+        assert_close(got.cpu().numpy(), lp_o.numpy(), 1e-3, f"log-probs rows {rows}", max_frac=2e-3)
