@@ -221,7 +221,7 @@ class ChainEngine:
         E = state.shape[0]
         if state.dtype != torch.float32 or not state.is_contiguous():
             state = state.contiguous().float()
-        state = state.view(E, -1)
+        state = state.view(E, math.prod(state.shape[1:]))
         if not (state.is_cuda or state.is_pinned()):
             state = state.to(self.device)
         traj = out_traj if out_traj is not None else torch.empty((E, self.D), dtype=torch.float32, device=self.device)
