@@ -213,6 +213,24 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uin
   }
 }
 
+// Accumulating MMA with an explicit A-collector policy: FILL keeps the A operand (128 x 16) in the tensor core's collector
+// buffer, LASTUSE consumes it from there - the next MMA with the SAME A descriptor skips its shared-memory read of A.
+__device__ __forceinline__ void umma_bf16_lo_fill(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  const uint64_t a = (uint64_t(kDescHi32) << 32) | a_lo, b = (uint64_t(kDescHi32) << 32) | b_lo;
+  if (accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc) : "memory");
+  }
+}
+__device__ __forceinline__ void umma_bf16_lo_lastuse(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  const uint64_t a = (uint64_t(kDescHi32) << 32) | a_lo, b = (uint64_t(kDescHi32) << 32) | b_lo;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -9,7 +9,7 @@
 
 namespace dppo {
 
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int n_b, unsigned long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int n_b, int reuse, unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -37,8 +37,18 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int 
       if (elect_one()) {
         const uint32_t d = tmem + acc * N;
         const uint32_t aa = a0 + at * (16384 / 16), bb = b0 + bt * (uint32_t(N) * 128 / 16);
+        if (reuse) {
+          // pairs that share their A operand (the chain kernel's w_hi * x_hi, w_hi * x_lo): second one reads A from the collector
+          const uint32_t b2 = b0 + ((bt + 1) % uint32_t(n_b)) * (uint32_t(N) * 128 / 16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_lo(d, aa + 2 * k, bb + 2 * k, idesc, true);
+          for (int k = 0; k < 2; ++k) {
+            umma_bf16_lo_fill(d, aa + 2 * k, bb + 2 * k, idesc, true);
+            umma_bf16_lo_lastuse(d, aa + 2 * k, b2 + 2 * k, idesc);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_lo(d, aa + 2 * k, bb + 2 * k, idesc, true);
+        }
       }
       __syncwarp();
       if (++at == 8) at = 0;
@@ -113,14 +123,127 @@ __global__ void __launch_bounds__(64, 1) stream_rate_kernel(const uint8_t* __res
   if (csz > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
 }
 
+
+// ---------------------------------------------------------------------------------------------------- CTA pair
+// tcgen05.mma.cta_group::2 (M = 256 over a CTA pair, each CTA holds 128 rows of A, N/2 rows of B and a 128-lane x N
+// accumulator).  First one K = 64 pass over known small-integer operands whose accumulator both CTAs write to `d`
+// ((2, 128, N) fp32) - the layout check - then the issue rate of n_mma instructions like mma_rate_kernel measures it.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  const uint64_t a = (uint64_t(kDescHi32) << 32) | a_lo, b = (uint64_t(kDescHi32) << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+
+__host__ __device__ inline int pair_a_val(int cta, int r, int k) { return (r + 3 * k + 7 * cta) % 5 - 2; }
+__host__ __device__ inline int pair_b_val(int n, int k) { return (2 * n + k) % 7 - 3; }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    mma_pair_rate_kernel(int N, int n_mma, float* d, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = int(cluster_ctarank());
+  const int Nh = N / 2;
+  // A: 8 tiles of 128 x 64 at [0, 128 KiB) (tile 0 holds the known values, the rest zeros); B: Nh x 64 at 128 KiB
+  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    *reinterpret_cast<__nv_bfloat16*>(smem + sw128_offset(r, k, 128)) = __float2bfloat16_rn(float(pair_a_val(cta, r, k)));
+  }
+  for (int i = threadIdx.x; i < Nh * 64; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    *reinterpret_cast<__nv_bfloat16*>(smem + 128 * 1024 + sw128_offset(r, k, Nh)) =
+        __float2bfloat16_rn(float(pair_b_val(cta * Nh + r, k)));
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair(&slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' operands and barriers are in place before the leader issues
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const uint32_t idesc = umma_idesc_bf16(256, N);
+  const uint32_t a0 = umma_desc_lo(smem_u32(smem)), b0 = umma_desc_lo(smem_u32(smem + 128 * 1024));
+  if (warp == 0 && cta == 0) {
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_pair(tmem, a0 + 2 * k, b0 + 2 * k, idesc, k > 0);
+      umma_commit_pair(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);
+    for (int j = 0; j < 32; ++j) d[(size_t(cta) * 128 + warp * 32 + lane) * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 0 && cta == 0) {
+    uint32_t at = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; i += 4) {
+      if (elect_one()) {
+        const uint32_t aa = a0 + at * (16384 / 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_pair(tmem, aa + 2 * k, b0 + 2 * k, idesc, 1);
+      }
+      __syncwarp();
+      if (++at == 8) at = 0;
+    }
+    if (elect_one()) umma_commit_pair(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 1);
+    if (threadIdx.x == 0) out[0] = clock64() - t0;
+  } else {
+    mbar_wait(&bar, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tmem, 256);
+}
+
 }  // namespace dppo
 
-extern "C" int dppo_debug_mma_rate(int N, int n_mma, int n_b, unsigned long long* out, void* stream) {
+extern "C" int dppo_debug_mma_rate(int N, int n_mma, int n_b, int reuse, unsigned long long* out, void* stream) {
   using namespace dppo;
   if (N < 16 || N > 256 || N % 16 || n_b < 1 || n_b * N > 512) return -1;
   const int smem = 193 * 1024 + 1024;
   if (cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
-  mma_rate_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, n_b, out);
+  mma_rate_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, n_b, reuse, out);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -141,4 +264,23 @@ extern "C" int dppo_debug_stream_rate(const void* region, int region_tiles, int 
   cudaError_t e = cudaLaunchKernelEx(&cfg, stream_rate_kernel, static_cast<const uint8_t*>(region), region_tiles, n_tiles,
                                      cluster, out);
   return e == cudaSuccess ? 0 : -3;
+}
+
+// d: (2, 128, N) fp32 device buffer, expect: same shape on the host filled with the exact result (or null)
+extern "C" int dppo_debug_mma_pair_rate(int N, int n_mma, float* d, unsigned long long* out, float* expect, void* stream) {
+  using namespace dppo;
+  if (N < 32 || N > 256 || N % 32) return -1;
+  if (expect) {
+    for (int cta = 0; cta < 2; ++cta)
+      for (int r = 0; r < 128; ++r)
+        for (int n = 0; n < N; ++n) {
+          int acc = 0;
+          for (int k = 0; k < 64; ++k) acc += pair_a_val(cta, r, k) * pair_b_val(n, k);
+          expect[(size_t(cta) * 128 + r) * N + n] = float(acc);
+        }
+  }
+  const int smem = 161 * 1024 + 1024;
+  if (cudaFuncSetAttribute(mma_pair_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
+  mma_pair_rate_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, d, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

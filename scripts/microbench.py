@@ -8,7 +8,7 @@ sys.path.insert(0, ".")
 from dppo_b200 import _lib
 
 lib = _lib.load()
-lib.dppo_debug_mma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.dppo_debug_mma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 lib.dppo_debug_stream_rate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 out = torch.zeros(256, dtype=torch.int64, device="cuda")
 n = 8192
@@ -18,9 +18,29 @@ for N in (16, 32, 48, 64, 96, 128, 256):
         if n_b * N > 512:
             continue
         for _ in range(2):
-            rc = lib.dppo_debug_mma_rate(N, n, n_b, C.c_void_p(out.data_ptr()), None)
+            rc = lib.dppo_debug_mma_rate(N, n, n_b, 0, C.c_void_p(out.data_ptr()), None)
             torch.cuda.synchronize()
-        print(f"N={N:3d} n_b={n_b} rc={rc} cycles/MMA {out[0].item() / n:7.1f}   floors tensor {N / 2:5.1f} smem {(4096 + 32 * N) / 128:5.1f}")
+        plain = out[0].item() / n
+        for _ in range(2):
+            rc2 = lib.dppo_debug_mma_rate(N, n, n_b, 1, C.c_void_p(out.data_ptr()), None)
+            torch.cuda.synchronize()
+        print(f"N={N:3d} n_b={n_b} rc={rc},{rc2} cycles/MMA {plain:7.1f}   floors tensor {N / 2:5.1f} smem {(4096 + 32 * N) / 128:5.1f}"
+              f"   | pairs sharing A through the collector (fill / lastuse): {out[0].item() / n:7.1f}  smem floor {(2048 + 32 * N) / 128:5.1f}")
+
+print("== tcgen05.mma.cta_group::2 M=256 K=16 bf16 SS over a CTA pair: cycles per MMA, layout check of the accumulator")
+lib.dppo_debug_mma_pair_rate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+for N in (64, 128, 256):
+    d = torch.zeros(2, 128, N, device="cuda")
+    exp = torch.zeros(2, 128, N)
+    for _ in range(2):
+        rc = lib.dppo_debug_mma_pair_rate(N, n, C.c_void_p(d.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(exp.data_ptr()), None)
+        torch.cuda.synchronize()
+    ok = torch.equal(d.cpu(), exp)
+    print(f"N={N:3d} (N/2={N // 2} rows of B per CTA) rc={rc} layout {'ok' if ok else 'MISMATCH'} cycles/MMA {out[0].item() / n:7.1f}"
+          f"   floors per SM: tensor {N / 2:5.1f} smem {(4096 + 16 * N) / 128:5.1f}")
+    if not ok:
+        bad = (d.cpu() != exp).nonzero()
+        print("   first mismatches", bad[:4].tolist(), "got", d.cpu()[tuple(bad[0])].item(), "want", exp[tuple(bad[0])].item())
 
 print("== L2 -> smem streaming of one shared region, 16 KiB tiles, 8-stage ring: bytes/cycle/SM")
 region_tiles = 140  # ~2.2 MiB, the hi+lo tile stream of one 512-wide denoiser step
