@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        prof = ["-DDPPO_CHAIN_PROF"] if os.environ.get("DPPO_B200_CHAIN_PROF") == "1" else []  # MMA-warp wait counters
+        cmd = [nvcc] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

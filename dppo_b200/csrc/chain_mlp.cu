@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // hi tile then lo tile)
     // `rot`: the K chunks are visited starting at chunk `rot` (wrapping): layers that read X start with the chunks this
     // CTA produced itself, which are ready first (see the MMA warp)
-    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot) {
+    // `bytes`: leading part of every 16 KiB tile that is fetched (a tile is 128 rows of 128 bytes, row-major: its first R
+    // rows are its first R * 128 bytes).  The output layer has only D <= 128 real rows; the rows behind them keep whatever
+    // the ring slot held before (finite or not - they only reach accumulator lanes >= D, which nobody reads).
+    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot, uint32_t bytes) {
       // chunk-major: every output tile consumes K chunk kc before anybody touches the next chunk, so one arrived tile of
       // X feeds (m_end - m_begin) x 2 tile-MMAs before the next one is needed
       for (int j = 0; j < KCl; ++j) {
@@ -197,8 +200,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             mbar_wait(&s.empty[stage], phase ^ 1);
             p_wait += clock64() - tw;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&s.full[stage], kTile);
-              bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(kc * a.nsplit + h) * kTile, kTile, &s.full[stage]);
+              mbar_arrive_expect_tx(&s.full[stage], bytes);
+              bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(kc * a.nsplit + h) * kTile, bytes, &s.full[stage]);
             }
             __syncwarp();
             if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
@@ -207,19 +210,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       }
     };
     const int rot = mt0 * 2;
+    const uint32_t out_bytes = uint32_t((a.D + 7) / 8) * 8u * 128u;  // D <= 128
     const size_t lin0 = size_t(a.MT) * a.KC0 * a.nsplit * kTile, linh = size_t(a.MT) * a.KCH * a.nsplit * kTile;
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
       if (a.CH && net != cur_net) {
-        stream(a.tiles[net], 0, a.MTc, a.KCc, 0);
-        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64, 0);
+        stream(a.tiles[net], 0, a.MTc, a.KCc, 0, kTile);
+        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64, 0, kTile);
       }
       cur_net = net;
       const uint8_t* base = a.tiles[net] + a.off_step_tiles;
-      stream(base, mt0, mt0 + MTo, a.KC0, 0);
+      stream(base, mt0, mt0 + MTo, a.KC0, 0, kTile);
       base += lin0;
-      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH, rot);
-      stream(base, 0, 1, a.KCH, rot);
+      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH, rot, kTile);
+      stream(base, 0, 1, a.KCH, rot, out_bytes);
     }
     if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = p_wait, a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0;
   } else if (warp == 1) {
@@ -238,14 +242,27 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     long long m_wait_x = 0, m_wait_full = 0;
     const long long m_t0 = clock64();
     const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
+    // The issue loop is ONE warp's dependent instruction stream on a scheduler it shares with two epilogue warps, and it
+    // is on the kernel's critical path (measured: a handful of extra instructions per tile cost 7 % of the launch).  So:
+    // no branch around the MMAs (predicated on the lane elected once, here), and the wait counters of the role profile
+    // are compiled in only with -DDPPO_CHAIN_PROF (scripts/chain_prof.py needs a build with DPPO_B200_CHAIN_PROF=1).
+    const uint32_t leader = elect_one() ? 1u : 0u;
+#ifdef DPPO_CHAIN_PROF
+#define DPPO_MMA_T0() tw = clock64()
+#define DPPO_MMA_T1(acc_) acc_ += clock64() - tw
+#else
+#define DPPO_MMA_T0()
+#define DPPO_MMA_T1(acc_)
+#endif
     auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc, bool tiled) {
-      long long tw = clock64();
+      [[maybe_unused]] long long tw = 0;
+      DPPO_MMA_T0();
       if (!tiled) {
         mbar_wait(s.x0_full, x0_phase);
         x0_phase ^= 1;
         tc_fence_after();
       }
-      m_wait_x += clock64() - tw;
+      DPPO_MMA_T1(m_wait_x);
       uint32_t waited = 0;
       const uint32_t bh = umma_desc_lo(smem_u32(b_hi)), bl = umma_desc_lo(smem_u32(b_lo));
       for (int j = 0; j < KCl; ++j) {
@@ -256,56 +273,48 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           uint32_t t = uint32_t(kc) >> 1;
           if (MTo == 1 && int(t) != mt0) t = kPeerBar;  // one tile per CTA: all the peers' tiles share one barrier
           if (!((waited >> t) & 1u)) {
-            tw = clock64();
+            DPPO_MMA_T0();
             mbar_wait(&s.x_full[t], (xf_phase >> t) & 1u);
-            m_wait_x += clock64() - tw;
+            DPPO_MMA_T1(m_wait_x);
             tc_fence_after();
             waited |= 1u << t;
           }
         }
         const uint32_t boff = uint32_t(kc) * (NE * 128 / 16);
+        const uint32_t first_acc = (acc || j > 0) ? 1u : 0u;
         for (int mt = 0; mt < MTl; ++mt) {
           const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
-          tw = clock64();
+          DPPO_MMA_T0();
           mbar_wait(&s.full[stage], phase);
-          m_wait_full += clock64() - tw;
+          DPPO_MMA_T1(m_wait_full);
           tc_fence_after();
-          if (elect_one()) {
+          {
             const uint32_t wa = ring_lo + stage * (kTile / 16);
-            if (acc || j > 0) {
-              umma_bf16_lo(d, wa, bh + boff, idesc, true);
-            } else {
-              umma_bf16_lo(d, wa, bh + boff, idesc, false);
-            }
+            umma_bf16_lo_p(d, wa, bh + boff, idesc, first_acc, leader);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + boff + 2 * k, idesc, true);
+            for (int k = 1; k < 4; ++k) umma_bf16_lo_p(d, wa + 2 * k, bh + boff + 2 * k, idesc, 1u, leader);
             if (split) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bl + boff + 2 * k, idesc, true);
+              for (int k = 0; k < 4; ++k) umma_bf16_lo_p(d, wa + 2 * k, bl + boff + 2 * k, idesc, 1u, leader);
             }
-            umma_commit(&s.empty[stage]);
+            umma_commit_p(&s.empty[stage], leader);
           }
-          __syncwarp();
           if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           if (split) {
-            tw = clock64();
+            DPPO_MMA_T0();
             mbar_wait(&s.full[stage], phase);
-            m_wait_full += clock64() - tw;
+            DPPO_MMA_T1(m_wait_full);
             tc_fence_after();
-            if (elect_one()) {
-              const uint32_t wa = ring_lo + stage * (kTile / 16);
+            const uint32_t wa = ring_lo + stage * (kTile / 16);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + boff + 2 * k, idesc, true);
-              umma_commit(&s.empty[stage]);
-            }
-            __syncwarp();
+            for (int k = 0; k < 4; ++k) umma_bf16_lo_p(d, wa + 2 * k, bh + boff + 2 * k, idesc, 1u, leader);
+            umma_commit_p(&s.empty[stage], leader);
             if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           }
         }
       }
       xf_phase ^= waited;
-      if (elect_one()) umma_commit(s.layer_done);
-      __syncwarp();
+      umma_commit_p(s.layer_done, leader);
     };
     int cur_net = -1;
     for (int step = a.first_step; step < a.S; ++step) {
@@ -886,6 +895,12 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   if (fixed + 2 * kTile > budget) return set_error("chain kernel: geometry needs %zu B of shared memory", fixed), DPPO_ERR_INVALID;
   int nstage = int((budget - fixed) / kTile);
   if (nstage > kMaxStages) nstage = kMaxStages;
+  static int env_stages = -1;  // bring-up: cap the ring depth (sensitivity measurements)
+  if (env_stages < 0) {
+    const char* e = getenv("DPPO_B200_STAGES");
+    env_stages = e ? atoi(e) : 0;
+  }
+  if (env_stages >= 2 && env_stages < nstage) nstage = env_stages;
   a.nstage = nstage;
   const size_t smem_bytes = fixed + size_t(nstage) * kTile;
 

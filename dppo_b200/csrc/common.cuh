@@ -231,6 +231,26 @@ __device__ __forceinline__ void umma_bf16_lo_lastuse(uint32_t d_tmem, uint32_t a
                ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc) : "memory");
 }
 
+// Predicated forms for an issue loop whose control flow stays warp-uniform: every lane executes the statement, only the
+// lane with `leader != 0` (elected once, in front of the loop) issues.  No branch around the MMAs, so the compiler
+// keeps one convergent instruction stream (a single vote -> uniform predicate) instead of a divergent region per tile.
+__device__ __forceinline__ void umma_bf16_lo_p(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t leader) {
+  const uint64_t a = (uint64_t(kDescHi32) << 32) | a_lo, b = (uint64_t(kDescHi32) << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {

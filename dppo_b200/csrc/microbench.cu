@@ -9,16 +9,25 @@
 
 namespace dppo {
 
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int n_b, int reuse, unsigned long long* out) {
+// `load` adds what runs next to the MMA stream in the chain kernel (bit mask):
+//   1  warp 1 keeps 4 x 16 KiB bulk copies global -> shared in flight (weight ingest; `region` = 64 KiB of global memory)
+//   2  warps 2, 3 read the accumulator region back with tcgen05.ld in a loop (epilogue TMEM reads)
+//   4  warps 2, 3 store 4-byte words to shared memory in a loop (epilogue operand stores)
+// out[0] = cycles of the MMA stream, out[1] = bytes ingested meanwhile, out[2] = tcgen05.ld / store iterations
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int n_b, int reuse, int load,
+                                                          const uint8_t* __restrict__ region, unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, ring_bar[4];
   __shared__ uint32_t slot;
+  __shared__ volatile int done;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (192 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&ring_bar[i], 1);
     fence_mbar_init();
+    done = 0;
   }
   if (warp == 0) tmem_alloc(&slot, 512);
   fence_proxy_async_smem();
@@ -26,10 +35,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = slot;
+  // A: 6 tiles of 128 x 64 (16 KiB each) at [0, 96 KiB); B: n_b operands of N x 64 at 96 KiB (<= 32 KiB);
+  // ingest ring: 4 x 16 KiB at 128 KiB; store scratch at 192 KiB - 8 KiB .. (inside the ring's last stage when load & 4 only)
   if (warp == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, N);
-    // A: 8 tiles of 128 x 64 (16 KiB each) at [0, 128 KiB); B: n_b operands of N x 64 at 128 KiB (n_b * N <= 512 rows)
-    const uint32_t a0 = umma_desc_lo(smem_u32(smem)), b0 = umma_desc_lo(smem_u32(smem + 128 * 1024));
+    const uint32_t a0 = umma_desc_lo(smem_u32(smem)), b0 = umma_desc_lo(smem_u32(smem + 96 * 1024));
     const uint32_t n_acc = 512 / N >= 4 ? 4 : 512 / N;
     uint32_t at = 0, acc = 0, bt = 0;
     const long long t0 = clock64();
@@ -51,7 +61,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int 
         }
       }
       __syncwarp();
-      if (++at == 8) at = 0;
+      if (++at == 6) at = 0;
       if (++acc == n_acc) acc = 0;
       if (++bt == uint32_t(n_b)) bt = 0;
     }
@@ -59,6 +69,48 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int n_mma, int 
     __syncwarp();
     mbar_wait(&bar, 0);
     if (threadIdx.x == 0) out[0] = clock64() - t0;
+    done = 1;
+  } else if (warp == 1) {
+    if ((load & 1) && (threadIdx.x & 31) == 0) {
+      unsigned long long bytes = 0;
+      uint32_t ph[4] = {0, 0, 0, 0};
+      for (int st = 0; st < 4; ++st) {
+        mbar_arrive_expect_tx(&ring_bar[st], 16384);
+        bulk_g2s(smem + 128 * 1024 + st * 16384, region + st * 16384, 16384, &ring_bar[st]);
+      }
+      int st = 0;
+      while (!done) {
+        mbar_wait(&ring_bar[st], ph[st]);
+        ph[st] ^= 1;
+        bytes += 16384;
+        mbar_arrive_expect_tx(&ring_bar[st], 16384);
+        bulk_g2s(smem + 128 * 1024 + st * 16384, region + st * 16384, 16384, &ring_bar[st]);
+        st = (st + 1) & 3;
+      }
+      for (int i = 0; i < 4; ++i, st = (st + 1) & 3) mbar_wait(&ring_bar[st], ph[st]);  // drain before exit
+      out[1] = bytes;
+    }
+  } else {
+    unsigned long long it = 0;
+    if (load & 2) {
+      float sink = 0.f;
+      while (!__shfl_sync(0xffffffffu, int(done), 0)) {  // warp-uniform exit: tcgen05.ld is .sync.aligned
+        float v[32];
+        tmem_ld32(tmem + (uint32_t(warp * 32) << 16) + uint32_t((it & 7) * 32), v);
+        sink += v[0] + v[31];
+        ++it;
+      }
+      if (sink == 12345.f) out[3] = 1;
+    }
+    if (load & 4) {
+      uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + 120 * 1024);  // 8 KiB behind the B operands, nobody reads it
+      while (!__shfl_sync(0xffffffffu, int(done), 0)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scratch[((it * 8 + j) & 31) * 64 + (warp - 2) * 32 + (threadIdx.x & 31)] = uint32_t(it);
+        ++it;
+      }
+    }
+    if ((threadIdx.x & 31) == 0 && warp == 2) out[2] = it;
   }
   tc_fence_before();
   __syncthreads();
@@ -238,12 +290,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 
 }  // namespace dppo
 
-extern "C" int dppo_debug_mma_rate(int N, int n_mma, int n_b, int reuse, unsigned long long* out, void* stream) {
+extern "C" int dppo_debug_mma_rate(int N, int n_mma, int n_b, int reuse, int load, const void* region,
+                                   unsigned long long* out, void* stream) {
   using namespace dppo;
-  if (N < 16 || N > 256 || N % 16 || n_b < 1 || n_b * N > 512) return -1;
+  if (N < 16 || N > 256 || N % 16 || n_b < 1 || n_b * N > 256) return -1;
+  if ((load & 1) && region == nullptr) return -1;
   const int smem = 193 * 1024 + 1024;
   if (cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
-  mma_rate_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, n_b, reuse, out);
+  mma_rate_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, n_b, reuse, load, static_cast<const uint8_t*>(region), out);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
