@@ -290,14 +290,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           tc_fence_after();
           {
             const uint32_t wa = ring_lo + stage * (kTile / 16);
-            umma_bf16_lo_p(d, wa, bh + boff, idesc, first_acc, leader);
-#pragma unroll
-            for (int k = 1; k < 4; ++k) umma_bf16_lo_p(d, wa + 2 * k, bh + boff + 2 * k, idesc, 1u, leader);
-            if (split) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_lo_p(d, wa + 2 * k, bl + boff + 2 * k, idesc, 1u, leader);
-            }
-            umma_commit_p(&s.empty[stage], leader);
+            const uint32_t rel = smem_u32(&s.empty[stage]);
+            umma_bf16_lo_x4_p(d, wa, bh + boff, idesc, first_acc, leader, split ? 0u : rel);
+            if (split) umma_bf16_lo_x4_p(d, wa, bl + boff, idesc, 1u, leader, rel);
           }
           if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           if (split) {
@@ -305,10 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             mbar_wait(&s.full[stage], phase);
             DPPO_MMA_T1(m_wait_full);
             tc_fence_after();
-            const uint32_t wa = ring_lo + stage * (kTile / 16);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_lo_p(d, wa + 2 * k, bh + boff + 2 * k, idesc, 1u, leader);
-            umma_commit_p(&s.empty[stage], leader);
+            umma_bf16_lo_x4_p(d, ring_lo + stage * (kTile / 16), bh + boff, idesc, 1u, leader, smem_u32(&s.empty[stage]));
             if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           }
         }

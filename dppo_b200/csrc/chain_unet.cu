@@ -206,6 +206,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     const uint32_t op_hi = umma_desc_lo(smem_u32(s.op_hi)), op_lo = umma_desc_lo(smem_u32(s.op_lo));
     long long m_wait_x = 0, m_wait_full = 0;
     const long long m_t0 = clock64();
+    // Same issue discipline as chain_mlp.cu: no divergent region around the MMAs (they are predicated on the lane
+    // elected once, here) and the wait counters exist only in a -DDPPO_CHAIN_PROF build.
+    const uint32_t leader = elect_one() ? 1u : 0u;
+#ifdef DPPO_CHAIN_PROF
+#define DPPO_UMMA_T0() tw = clock64()
+#define DPPO_UMMA_T1(acc_) acc_ += clock64() - tw
+#else
+#define DPPO_UMMA_T0()
+#define DPPO_UMMA_T1(acc_)
+#endif
     for (int step = a.first_step; step < a.S; ++step) {
       for (int li = 0; li < a.n_layers; ++li) {
         const ULayer* L = a.layers + li;
@@ -214,13 +224,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         const UGemm G0 = L->g[0], G1 = L->g[1];  // fetched while the previous epilogue is still running
         const uint32_t wait_chunk = uint32_t(L->wait_chunk), wait_tiles = uint32_t(L->wait_tiles);
         uint32_t waited = 0;
-        long long tw = clock64();
+        [[maybe_unused]] long long tw = 0;
+        DPPO_UMMA_T0();
         if (!tiled) {
           mbar_wait(s.x_full, xr_phase);
           xr_phase ^= 1;
           tc_fence_after();
         }
-        m_wait_x += clock64() - tw;
+        DPPO_UMMA_T1(m_wait_x);
         for (int gi = 0; gi < n_gemm; ++gi) {
           const UGemm G = gi == 0 ? G0 : G1;
           for (int kc = 0; kc < int(G.kc); ++kc) {
@@ -229,9 +240,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             if (tiled && chunk >= wait_chunk && chunk < wait_chunk + 2 * wait_tiles) {
               const uint32_t t = (chunk - wait_chunk) >> 1;  // tile of the predecessor's output this chunk belongs to
               if (!((waited >> t) & 1u)) {
-                tw = clock64();
+                DPPO_UMMA_T0();
                 mbar_wait(&s.xt_full[t], (xt_phase >> t) & 1u);
-                m_wait_x += clock64() - tw;
+                DPPO_UMMA_T1(m_wait_x);
                 tc_fence_after();
                 waited |= 1u << t;
               }
@@ -240,39 +251,23 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             const uint32_t bh = op_hi + boff, bl = op_lo + boff;
             for (int mt = 0; mt < int(G.mt); ++mt) {
               const uint32_t d = tmem + uint32_t(G.acc_tile + mt) * NE;
-              tw = clock64();
+              DPPO_UMMA_T0();
               mbar_wait(&s.full[stage], phase);
-              m_wait_full += clock64() - tw;
+              DPPO_UMMA_T1(m_wait_full);
               tc_fence_after();
-              if (elect_one()) {
+              {
                 const uint32_t wa = ring_lo + stage * (kTile / 16);
-                if (kc > 0) {
-                  umma_bf16_lo(d, wa, bh, idesc, true);
-                } else {
-                  umma_bf16_lo(d, wa, bh, idesc, false);
-                }
-#pragma unroll
-                for (int k = 1; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + 2 * k, idesc, true);
-                if (split) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bl + 2 * k, idesc, true);
-                }
-                umma_commit(&s.empty[stage]);
+                const uint32_t rel = smem_u32(&s.empty[stage]);
+                umma_bf16_lo_x4_p(d, wa, bh, idesc, kc > 0 ? 1u : 0u, leader, split ? 0u : rel);
+                if (split) umma_bf16_lo_x4_p(d, wa, bl, idesc, 1u, leader, rel);
               }
-              __syncwarp();
               if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
               if (split) {
-                tw = clock64();
+                DPPO_UMMA_T0();
                 mbar_wait(&s.full[stage], phase);
-                m_wait_full += clock64() - tw;
+                DPPO_UMMA_T1(m_wait_full);
                 tc_fence_after();
-                if (elect_one()) {
-                  const uint32_t wa = ring_lo + stage * (kTile / 16);
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_bf16_lo(d, wa + 2 * k, bh + 2 * k, idesc, true);
-                  umma_commit(&s.empty[stage]);
-                }
-                __syncwarp();
+                umma_bf16_lo_x4_p(d, ring_lo + stage * (kTile / 16), bh, idesc, 1u, leader, smem_u32(&s.empty[stage]));
                 if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
               }
             }
@@ -287,8 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             }
           xt_phase ^= waited;
         }
-        if (elect_one()) umma_commit(s.layer_done);
-        __syncwarp();
+        umma_commit_p(s.layer_done, leader);
       }
     }
     if (a.prof && lane == 0) {

@@ -251,6 +251,26 @@ __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
       : "memory");
 }
 
+// The four K = 16 steps of one 64-wide swizzle atom (descriptor start address + 32 bytes each) in ONE statement: one
+// predicate set-up for four MMAs, and, with `commit_bar != 0`, the ring release behind them.
+__device__ __forceinline__ void umma_bf16_lo_x4_p(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                  uint32_t accumulate_first, uint32_t leader, uint32_t commit_bar) {
+  const uint64_t a = (uint64_t(kDescHi32) << 32) | a_lo, b = (uint64_t(kDescHi32) << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p, q, t, c;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\tsetp.eq.u32 t, 1, 1;\n\t"
+      "setp.ne.and.b32 c, %6, 0, q;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
+      "@c tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate_first), "r"(leader), "r"(commit_bar)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
