@@ -127,14 +127,15 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.can_send = reinterpret_cast<uint64_t*>(p), p += 16;  // two barriers, used alternately (see wait_layer)
   s.ln_bar = reinterpret_cast<uint64_t*>(p), p += 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
-  s.ln_part = reinterpret_cast<float*>(p), p += kEpiWarps * 2 * 32 * 4;
-  s.ln_x = reinterpret_cast<float*>(p);
+  s.ln_part = reinterpret_cast<float*>(p), p += a.ln ? kEpiWarps * 2 * 32 * 4 : 0;  // LayerNorm scratch only when used:
+  s.ln_x = reinterpret_cast<float*>(p);                                             // 6 KiB decide about a ring stage
   return s;
 }
 
 static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
   const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
-  return xb + x0b + 16 * kMaxStages + 176 + kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 + 1024 /* alignment slack */;
+  const size_t ln_bytes = g.ln ? kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 : 0;
+  return xb + x0b + 16 * kMaxStages + 176 + ln_bytes + 1024 /* alignment slack */;
 }
 
 // ============================================================================================== the kernel
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint32_t ld_phase = 0;
     float xreg[CPT];
+    float zreg[CPT];  // the step's injected noise, drawn while the output-layer MMAs run (see the step loop)
     const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
 
     long long e_wait = 0, e_hand = 0;
@@ -672,6 +674,29 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       // the completed output-layer MMAs no longer read), then ALL epilogue threads run the posterior on the flat mapping.
       // Every CTA of a cluster does this redundantly (same inputs, same noise); rank 0 alone writes to global memory.
       const float bo = fl < a.D ? side[a.off_bout + fl] : 0.f;  // fetched while the output-layer MMAs run
+      // The posterior is a serial stretch of the chain (output-layer MMAs -> posterior -> layer 0), and most of its
+      // per-element latency is the Philox + Box-Muller draw, which depends on nothing the MMAs produce: draw now, while
+      // this warp would otherwise sit in wait_layer.
+      {
+#pragma unroll 1
+        for (int j = 0; j < CPT; ++j) {
+          const int i = et + j * kEpiThreads;
+          if (i >= nxe) break;
+          const int e = i / a.D, f = i - e * a.D;
+          const int env = env0 + e;
+          float z = 0.f;
+          if (env < a.E && a.eval_mode) {
+            z = a.chains_in[(size_t(env) * (a.ft + 1) + (step - a.first_step) + 1) * a.D + f];  // the stored next sample
+          } else if (env < a.E) {
+            if (a.noise)
+              z = a.noise[(size_t(step + 1) * a.E + env) * a.D + f];
+            else
+              z = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, uint32_t(step + 1));
+            z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
+          }
+          zreg[j] = z;
+        }
+      }
       wait_layer(true);
       {
         float* s_eps = reinterpret_cast<float*>(s.x_hi);
@@ -722,17 +747,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             float xn = 0.f;
             if (env < a.E) {
               if (a.eval_mode) {
-                xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + f];
+                xn = zreg[j];
                 const float diff = xn - mu;
                 if (rank == 0) a.logp[(size_t(env) * a.ft + d_eval) * a.D + f] = -(diff * diff) * inv_2var - log_std - 0.91893853320467274f;
               } else {
-                float z;
-                if (a.noise)
-                  z = a.noise[(size_t(step + 1) * a.E + env) * a.D + f];
-                else
-                  z = philox_normal(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, uint32_t(step + 1));
-                z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
-                xn = mu + stdv * z;
+                xn = mu + stdv * zreg[j];
                 if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
                 if (rank == 0) {
                   if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;

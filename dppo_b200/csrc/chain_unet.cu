@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     uint32_t ld_phase = 0;
     uint32_t film_n = 0;  // FiLM blocks produced (encoder CTA) / consumed (main CTA) so far; buffer = film_n & 1
     float xreg[CPT];
+    float zreg[CPT];  // the step's injected noise / stored next sample, fetched while the output layer's MMAs run
     const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
 
     long long e_wait = 0, e_film = 0;
@@ -389,6 +390,28 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
         for (int i = 0; i < 2; ++i) {
           const int f = (i < MTl ? i : 0) * 128 + fl;
           pb[i] = bias[f], pg[i] = gamma[f], pbe[i] = beta[f], prb[i] = res_bias[f];
+        }
+        if (kind != U_EPI_OPERAND) {
+          // the posterior is a serial stretch of the chain; its Philox + Box-Muller draws depend on nothing the MMAs
+          // produce, so they happen here, where this warp would otherwise wait
+#pragma unroll 1
+          for (int j = 0; j < CPT; ++j) {
+            const int i = et + j * kEpiThreads;
+            if (i >= nxe) break;
+            const int e = i / a.D, f = i - e * a.D;
+            const int env = env0 + e;
+            float z = 0.f;
+            if (env < a.E && a.eval_mode) {
+              z = a.chains_in[(size_t(env) * (a.ft + 1) + (step - a.first_step) + 1) * a.D + f];
+            } else if (env < a.E) {
+              if (a.noise)
+                z = a.noise[(size_t(step + 1) * a.E + env) * a.D + f];
+              else
+                z = philox_normal_u(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, uint32_t(step + 1));
+              z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
+            }
+            zreg[j] = z;
+          }
         }
         wait_layer();
         if (kind == U_EPI_OPERAND) {
@@ -564,17 +587,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             float xn = 0.f;
             if (env < a.E) {
               if (a.eval_mode) {
-                xn = a.chains_in[(size_t(env) * (a.ft + 1) + d_eval + 1) * a.D + f];
+                xn = zreg[j];
                 const float diff = xn - mu;
                 a.logp[(size_t(env) * a.ft + d_eval) * a.D + f] = -(diff * diff) * inv_2var - log_std - 0.91893853320467274f;
               } else {
-                float z;
-                if (a.noise)
-                  z = a.noise[(size_t(step + 1) * a.E + env) * a.D + f];
-                else
-                  z = philox_normal_u(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + f, uint32_t(step + 1));
-                z = fminf(fmaxf(z, -a.randn_clip), a.randn_clip);
-                xn = mu + stdv * z;
+                xn = mu + stdv * zreg[j];
                 if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
                 if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
                 if (last) a.traj[size_t(env) * a.D + f] = xn;
