@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // `bytes`: leading part of every 16 KiB tile that is fetched (a tile is 128 rows of 128 bytes, row-major: its first R
     // rows are its first R * 128 bytes).  The output layer has only D <= 128 real rows; the rows behind them keep whatever
     // the ring slot held before (finite or not - they only reach accumulator lanes >= D, which nobody reads).
+    const uint32_t p_leader = elect_one() ? 1u : 0u;  // same issue discipline as the MMA warp: no divergent region per tile
     auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot, uint32_t bytes) {
       // chunk-major: every output tile consumes K chunk kc before anybody touches the next chunk, so one arrived tile of
       // X feeds (m_end - m_begin) x 2 tile-MMAs before the next one is needed
@@ -197,14 +198,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         for (int mt = m_begin; mt < m_end; ++mt) {
           const uint8_t* src = base + size_t(mt) * KCl * a.nsplit * kTile;
           for (int h = 0; h < a.nsplit; ++h) {
+#ifdef DPPO_CHAIN_PROF
             const long long tw = clock64();
+#endif
             mbar_wait(&s.empty[stage], phase ^ 1);
+#ifdef DPPO_CHAIN_PROF
             p_wait += clock64() - tw;
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&s.full[stage], bytes);
-              bulk_g2s(s.ring + size_t(stage) * kTile, src + size_t(kc * a.nsplit + h) * kTile, bytes, &s.full[stage]);
-            }
-            __syncwarp();
+#endif
+            bulk_g2s_expect_p(s.ring + size_t(stage) * kTile, src + size_t(kc * a.nsplit + h) * kTile, bytes,
+                              &s.full[stage], p_leader);
             if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
           }
         }

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     uint32_t stage = 0, phase = 0;
     long long p_wait = 0;
     const long long p_t0 = clock64();
+    const uint32_t p_leader = elect_one() ? 1u : 0u;  // copies are predicated on it: no divergent region per tile
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
       for (int li = 0; li < a.n_layers; ++li) {
@@ -184,14 +185,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             for (uint32_t mt = 0; mt < uint32_t(G.mt); ++mt)
               for (uint32_t h = 0; h < uint32_t(a.nsplit); ++h) {
                 const size_t i = (size_t(mt) * G.kc + kc) * a.nsplit + h;
+#ifdef DPPO_CHAIN_PROF
                 const long long tw = clock64();
+#endif
                 mbar_wait(&s.empty[stage], phase ^ 1);
+#ifdef DPPO_CHAIN_PROF
                 p_wait += clock64() - tw;
-                if (elect_one()) {
-                  mbar_arrive_expect_tx(&s.full[stage], kTile);
-                  bulk_g2s(s.ring + size_t(stage) * kTile, src + i * kTile, kTile, &s.full[stage]);
-                }
-                __syncwarp();
+#endif
+                bulk_g2s_expect_p(s.ring + size_t(stage) * kTile, src + i * kTile, kTile, &s.full[stage], p_leader);
                 if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
               }
         }

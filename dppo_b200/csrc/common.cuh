@@ -86,6 +86,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// expect-tx arrive + bulk copy, predicated on `leader` (issue loops without a divergent region, see chain_mlp.cu)
+__device__ __forceinline__ void bulk_g2s_expect_p(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                  uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ thread-block clusters / distributed shared memory
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
