@@ -1,4 +1,8 @@
-"""Per-role cycle counters of the chain kernel (bring-up aid).  python scripts/chain_prof.py [workload] [envs] [precision]"""
+"""Per-role cycle counters of the chain kernel (bring-up aid).  python scripts/chain_prof.py [workload] [envs] [precision]
+
+The wait counters of the producer and MMA warps (prod_wait_empty, mma_wait_x, mma_wait_full) are compiled in only when the
+library is built with DPPO_B200_CHAIN_PROF=1 (python -c "from dppo_b200 import build; build.build(force=True)" under that
+environment variable); the default build reports 0 for them - the clock reads cost 7 % of the launch."""
 import ctypes as C
 import sys
 
