@@ -20,6 +20,8 @@ EXPORTS = [
     "dppo_last_error", "dppo_version", "dppo_ctx_create", "dppo_ctx_destroy", "dppo_pack_mlp", "dppo_ctx_create_unet",
     "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain",
     "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64", "dppo_split3_pack", "dppo_reward_scale_f64", "dppo_adamw_flat",
+    "dppo_update_create", "dppo_update_destroy", "dppo_update_bind", "dppo_update_forward", "dppo_update_backward",
+    "dppo_update_minibatch", "dppo_update_buffers",
     "dppo_selftest_umma",
 ]
 
@@ -80,6 +82,16 @@ class LossHp(C.Structure):
     ]
 
 
+class ResMlpDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_dim", "hidden_dim", "n_blocks", "out_dim", "activation", "use_layernorm")]
+
+
+class UpdateBatch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "chains", "x_next", "old_logprobs", "returns", "old_values", "advantages",
+                                          "inds_all", "denoising_inds")] + [
+        (n, C.c_int32) for n in ("row_begin", "n_rows", "global_rows")]
+
+
 _lib = None
 
 
@@ -126,6 +138,19 @@ def load(build_if_missing=True):
     lib.dppo_reward_scale_f64.argtypes = [vp, vp, i32, i32, C.c_longlong, f64, f64, f64, vp, vp, vp, vp, vp, i32, vp]
     lib.dppo_adamw_flat.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp]
     lib.dppo_selftest_umma.argtypes = [vp, vp, vp, vp, i32, i32, u64, C.c_uint32, vp]
+    lib.dppo_update_create.argtypes = [C.POINTER(vp), vp, C.POINTER(ResMlpDesc), i32]
+    lib.dppo_update_destroy.argtypes = [vp]
+    lib.dppo_update_bind.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp), i32]
+    lib.dppo_update_forward.argtypes = [vp, C.POINTER(UpdateBatch), vp, vp, vp]
+    lib.dppo_update_backward.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, vp]
+    lib.dppo_update_minibatch.argtypes = [vp, C.POINTER(UpdateBatch), C.POINTER(LossHp), f32, i32, vp, vp, vp]
+    lib.dppo_update_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    # bring-up / unit-test hooks (not part of the public header)
+    lib.dppo_debug_linear.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, vp, vp]
+    lib.dppo_debug_wgrad.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.dppo_debug_set_mn_desc.argtypes = [C.c_uint, C.c_uint]
+    for name in ("dppo_debug_linear", "dppo_debug_wgrad", "dppo_debug_set_mn_desc"):
+        getattr(lib, name).restype = i32
     for name in EXPORTS:
         if name not in ("dppo_last_error",):
             getattr(lib, name).restype = i32

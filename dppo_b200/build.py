@@ -13,8 +13,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libdppo_b200.so")
-SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "umma_selftest.cu", "microbench.cu"]
-HEADERS = ["common.cuh", "internal.h", "unet_plan.h", os.path.join("..", "..", "include", "dppo_b200.h")]
+SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "update_gemm.cu", "update_plan.cu", "umma_selftest.cu", "microbench.cu"]
+HEADERS = ["common.cuh", "internal.h", "unet_plan.h", "update_gemm.h", os.path.join("..", "..", "include", "dppo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

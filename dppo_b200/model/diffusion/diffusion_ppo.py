@@ -10,6 +10,7 @@ B200 agent uses it so the rollout buffers are indexed in place.
 """
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -92,10 +93,81 @@ class PPODiffusion(VPGDiffusion):
         host = scalars.tolist()  # the one device->host read of the call (the reference does four .item()s)
         return pg_loss, entropy_loss, v_loss, host[3], host[2], host[4], bc_loss, eta_mean
 
+    # ------------------------------------------------------------------ tensor-core update path
+    def fused_update_reason(self):
+        """None when actor_ft / critic forward + backward run on the hand-written tcgen05 kernels (dppo_update_*), else
+        the reason the torch-autograd path is used (Unet1D actors, non-residual critics, DPPO_B200_UPDATE=autograd)."""
+        if os.environ.get("DPPO_B200_UPDATE", "fused") == "autograd":
+            return "DPPO_B200_UPDATE=autograd"
+        from dppo_b200.update_engine import unsupported_reason
+
+        return unsupported_reason(self)
+
+    def update_plan(self, rows):
+        """The dppo_update workspace for minibatches of up to `rows` rows (rebuilt when it has to grow or the kernel
+        context changed, e.g. after the fine-tuning window was annealed)."""
+        from dppo_b200.update_engine import UpdatePlan
+
+        eng = self.engine(sync=False)
+        plan = getattr(self, "_update_plan", None)
+        if plan is None or plan.engine is not eng or plan.max_rows < rows:
+            self._update_plan = plan = UpdatePlan(self, rows)
+        return plan
+
+    def _loss_fused(self, obs, chains_prev, chains_next, denoising_inds, returns, oldvalues, advantages, oldlogprobs,
+                    reward_horizon):
+        from dppo_b200.engine import _mlp_param_list
+        from dppo_b200.update_engine import FusedLoss, _c32, critic_param_list
+
+        eng = self.engine(sync=False)
+        B = denoising_inds.shape[0]
+        plan = self.update_plan(B)
+        lo, hi = self._adv_bounds(advantages)
+        hp = eng.make_hp(self, reward_horizon, lo, hi)
+        tensors = dict(obs=_c32(obs["state"], (B, -1)), chains=_c32(chains_prev, (B, -1)), x_next=_c32(chains_next, (B, -1)),
+                       old_logprobs=_c32(oldlogprobs, (B, -1)), returns=_c32(returns, (B,)), old_values=_c32(oldvalues, (B,)),
+                       advantages=_c32(advantages, (B,)), denoising_inds=denoising_inds.detach().contiguous().to(torch.int64))
+        ap, cp = _mlp_param_list(self.actor_ft), critic_param_list(self.critic)
+        pg_loss, v_loss, scalars = FusedLoss.apply(self, plan, hp, tensors, len(ap), *ap, *cp)
+        eta_mean = self._eta_value()
+        entropy_loss = torch.full((), -eta_mean, device=pg_loss.device)
+        host = scalars.tolist()  # the one device->host read of the call (the reference does four .item()s)
+        return pg_loss, entropy_loss, v_loss, host[3], host[2], host[4], 0, eta_mean
+
+    def update_minibatch(self, obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k, inds_all, row_begin=0,
+                         row_count=None, reward_horizon=4, vf_coef=0.5, with_actor=True, scalars_out=None):
+        """
+        One PPO minibatch (slice) entirely inside libdppo_b200: gather -> actor_ft / critic forward -> fused loss ->
+        backward of pg_loss + vf_coef * v_loss, gradients ACCUMULATED into the parameters' .grad tensors (the views of
+        the agent's flat all-reduce buffer; the caller zeroes them).  Arguments as loss_gathered.  `scalars_out`
+        (8 floats, device) receives the partial means [pg, v, kl, clipfrac, ratio, -, adv mean, adv std]; nothing is
+        read back to the host.  reference: train_ppo_diffusion_agent.py:316-364.
+        """
+        eng = self.engine(sync=False)
+        row_count = inds_all.numel() - row_begin if row_count is None else row_count
+        plan = self.update_plan(row_count)
+        plan.bind_model(self)
+        lo, hi = self._adv_bounds(advantages_k[inds_all // self.ft_denoising_steps]) if (
+            self.clip_advantage_lower_quantile > 0 or self.clip_advantage_upper_quantile < 1) else (-math.inf, math.inf)
+        hp = eng.make_hp(self, reward_horizon, lo, hi)
+        from dppo_b200.update_engine import UpdatePlan
+
+        for t in (obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("rollout buffers must be contiguous fp32")
+        batch = UpdatePlan._batch(row_count, inds_all.numel(), row_begin, obs=obs_k, chains=chains_k, old_logprobs=logprobs_k,
+                                  returns=returns_k, old_values=values_k, advantages=advantages_k, inds_all=inds_all)
+        scalars = scalars_out if scalars_out is not None else torch.empty(8, dtype=torch.float32, device=obs_k.device)
+        plan.minibatch(batch, hp, vf_coef, with_actor, scalars, eng._ws)
+        return scalars
+
     # ------------------------------------------------------------------ reference signature
     def loss(self, obs, chains_prev, chains_next, denoising_inds, returns, oldvalues, advantages, oldlogprobs,
              use_bc_loss=False, reward_horizon=4):
         """Returns (pg_loss, entropy_loss, v_loss, clipfrac, approx_kl, ratio, bc_loss, eta)."""
+        if not use_bc_loss and self.fused_update_reason() is None:
+            return self._loss_fused(obs, chains_prev, chains_next, denoising_inds, returns, oldvalues, advantages,
+                                    oldlogprobs, reward_horizon)
         eng = self.engine()
         eps = self.actor_ft(chains_prev, self._ft_timesteps(denoising_inds), cond=obs)
         vpred = self.critic(obs).view(-1)

@@ -199,6 +199,69 @@ int dppo_ppo_loss_rows(dppo_ctx* ctx, const float* x_prev, const float* x_next, 
                        const dppo_loss_hp* hp, float* grad_eps, float* grad_vpred, float* scalars, void* workspace,
                        void* stream);
 
+/* ---- update: the PPO minibatch on hand-written tensor-core kernels ------------------------------------------------- */
+/* Replaces torch autograd (cuBLAS GEMMs + elementwise kernels) for the update of a DiffusionMLP actor_ft and a
+ * residual-MLP critic: PPODiffusion.loss -> get_logprobs_subsample -> actor_ft forward (diffusion_vpg.py:398-461,
+ * mlp_diffusion.py:218-250, common/mlp.py:84-154), CriticObs.forward (common/critic.py:40-54) and loss.backward()
+ * (train_ppo_diffusion_agent.py:360-364).  Every Linear is one tcgen05 GEMM launch (forward, dgrad, wgrad) with the
+ * activation / residual / bf16 hi-lo split fused into its epilogue; gradients are ACCUMULATED (+=) straight into the
+ * caller's gradient tensors (e.g. the views of one flat all-reduce buffer), which the caller zeroes.              */
+typedef struct dppo_update dppo_update;
+
+/* Residual MLP of the critic: Linear(in, H), n_blocks x [h + l2(act(l1(act(h))))], Linear(H, out).
+ * reference dppo/model/common/critic.py:15-54, dppo/model/common/mlp.py:84-154 */
+typedef struct dppo_resmlp_desc {
+  int32_t in_dim;        /* To * Do */
+  int32_t hidden_dim;
+  int32_t n_blocks;
+  int32_t out_dim;       /* 1 */
+  int32_t activation;    /* DPPO_ACT_* */
+  int32_t use_layernorm;
+} dppo_resmlp_desc;
+
+/* One minibatch (slice).  Gather mode (inds_all != NULL): obs / chains / old_logprobs / returns / old_values /
+ * advantages are the whole rollout buffers ([N, cond_dim], [N, ft+1, D], [N, ft, D], [N] x 3) and inds_all the
+ * minibatch's flat indices into (N, ft) (train_ppo_diffusion_agent.py:316-327); this rank evaluates rows
+ * [row_begin, row_begin + n_rows) and every mean divides by global_rows.  Direct mode (inds_all == NULL): the
+ * arguments of PPODiffusion.loss, already gathered per row (chains = chains_prev [n_rows, D], x_next, old_logprobs
+ * [n_rows, D], per-row scalars, denoising_inds [n_rows]); global_rows = n_rows.                                    */
+typedef struct dppo_update_batch {
+  const float* obs;
+  const float* chains;
+  const float* x_next;
+  const float* old_logprobs;
+  const float* returns;
+  const float* old_values;
+  const float* advantages;
+  const int64_t* inds_all;
+  const int64_t* denoising_inds;
+  int32_t row_begin, n_rows, global_rows;
+} dppo_update_batch;
+
+/* Workspace for up to max_rows minibatch rows per call (activations, operand images, packed weights).            */
+int dppo_update_create(dppo_update** out, dppo_ctx* ctx, const dppo_resmlp_desc* critic, int max_rows);
+int dppo_update_destroy(dppo_update* up);
+/* HOST arrays of DEVICE pointers to the fp32 parameters and to their gradient tensors: actor_ft in dppo_pack_mlp
+ * order; critic as layers.0.{weight,bias}, per block l1.{weight,bias}, l2.{weight,bias} [, norm1.{weight,bias},
+ * norm2.{weight,bias}], layers.last.{weight,bias}.  The current parameter VALUES are re-read on every call.      */
+int dppo_update_bind(dppo_update* up, const float* const* actor_params, float* const* actor_grads, int n_actor,
+                     const float* const* critic_params, float* const* critic_grads, int n_critic);
+/* actor_ft(x_prev, t_d, obs) -> eps_out [n_rows, D] and critic(obs) -> vpred_out [n_rows]; NULL = library-owned
+ * buffers (dppo_update_buffers).                                                                                   */
+int dppo_update_forward(dppo_update* up, const dppo_update_batch* batch, float* eps_out, float* vpred_out,
+                        void* stream);
+/* Back-propagate grad_eps [n_rows, D] / grad_vpred [n_rows] of the last forward into the bound gradient tensors.
+ * scale_pg / scale_v: optional DEVICE scalars multiplied into the two gradients (autograd's incoming factors),
+ * vf_coef an immediate factor on grad_vpred.  with_actor = 0 skips actor_ft (critic warm-up iterations).          */
+int dppo_update_backward(dppo_update* up, const float* grad_eps, const float* grad_vpred, const float* scale_pg,
+                         const float* scale_v, float vf_coef, int with_actor, int with_critic, void* stream);
+/* forward + fused PPO loss (dppo_ppo_loss_fwd_bwd / dppo_ppo_loss_rows) + backward of pg_loss + vf_coef * v_loss.
+ * scalars[8] as in dppo_ppo_loss_fwd_bwd; workspace >= 128 bytes.                                                 */
+int dppo_update_minibatch(dppo_update* up, const dppo_update_batch* batch, const dppo_loss_hp* hp, float vf_coef,
+                          int with_actor, float* scalars, void* workspace, void* stream);
+/* the library-owned buffers of the last forward: eps, vpred, and the gradient buffers dppo_update_minibatch fills   */
+int dppo_update_buffers(dppo_update* up, float** eps, float** vpred, float** grad_eps, float** grad_vpred);
+
 /* ---- GAE ------------------------------------------------------------------------------------------------------ */
 /* Reverse scan of train_ppo_diffusion_agent.py:255-279, one thread per env, float64 like the reference's numpy.
  *   reward, terminated, values: [n_steps, n_envs] float64; next_value [n_envs] float64 (critic of the post-rollout
