@@ -42,10 +42,11 @@ log = logging.getLogger(__name__)
 
 
 def cosine_warmup_lr(step, first_cycle_steps, max_lr, min_lr, warmup_steps):
-    """Learning rate after `step` scheduler steps: linear warm-up from min_lr, then cosine to min_lr, restarting every
-    first_cycle_steps (what util/scheduler.py's CosineAnnealingWarmupRestarts yields with cycle_mult = gamma = 1;
-    before the first scheduler step the optimiser sits at min_lr)."""
-    if step < 0:
+    """Learning rate after `step` >= 1 calls of CosineAnnealingWarmupRestarts.step() (reference dppo/util/scheduler.py:
+    _LRScheduler's constructor already takes one step, so the scheduler sits at step_in_cycle = 0 when the agent starts
+    and at step_in_cycle = n after n calls; cycle_mult = gamma = 1): linear warm-up from min_lr, then cosine to min_lr,
+    restarting every first_cycle_steps.  Before the first call the optimiser sits at min_lr (init_lr()), step = 0."""
+    if step <= 0:
         return min_lr
     s = step % first_cycle_steps
     if s < warmup_steps:
@@ -103,7 +104,7 @@ class TrainPPODiffusionAgent:
                                          weight_decay=cfg.train.actor_weight_decay)
         self.critic_optimizer = FlatAdamW(self.model.critic.parameters(), lr=cfg.train.critic_lr,
                                           weight_decay=cfg.train.critic_weight_decay)
-        self._sched = {"actor": -1, "critic": -1}
+        self._sched = {"actor": 0, "critic": 0}  # scheduler.step() calls so far (the reference's step_in_cycle)
         self._apply_lr()
         self.gae_lambda = cfg.train.get("gae_lambda", 0.95)
         self.target_kl = cfg.train.target_kl
