@@ -379,11 +379,18 @@ def bench_update(args, w, model, dev, E, rank, world):
     lo, hi = D.minibatch_slice(bs, rank, world)
     per_rank = bs // world
 
+    fused = model.fused_update_reason() is None
+
     def fwd_bwd(inds):
         grads.zero()
-        res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo,
-                                  row_count=hi - lo, reward_horizon=w["act_steps"], scalars_out=grads.scalars)
-        (res[0] + w["train"]["vf_coef"] * res[2]).backward()
+        if fused:  # the whole minibatch inside libdppo_b200 (hand-written tcgen05 forward / dgrad / wgrad kernels)
+            model.update_minibatch(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo, row_count=hi - lo,
+                                   reward_horizon=w["act_steps"], vf_coef=w["train"]["vf_coef"], with_actor=True,
+                                   scalars_out=grads.scalars)
+        else:
+            res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo,
+                                      row_count=hi - lo, reward_horizon=w["act_steps"], scalars_out=grads.scalars)
+            (res[0] + w["train"]["vf_coef"] * res[2]).backward()
         grads.allreduce()  # gradients of both networks + loss diagnostics: one NCCL all-reduce
 
     graphed = None
@@ -428,8 +435,12 @@ def bench_update(args, w, model, dev, E, rank, world):
     return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
             "minibatch_rows": per_rank * world, "buffer_rows": N * ft, "prologue_per_gpu": prologue,
             "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
-                     "Linear layers as 3-product bf16-split tensor-core GEMMs (dppo_split3_pack + cuBLASLt bf16, fp32 accumulate) under "
-                     "torch autograd; fused flat AdamW kernel per network; "
+                     + ("actor_ft / critic forward, dgrad and wgrad as hand-written tcgen05 GEMM kernels on bf16 hi/lo operand images "
+                        "(dppo_update_minibatch, 3-product split, fp32 accumulate), gradients accumulated straight into the flat buffer; "
+                        if fused else
+                        "Linear layers as 3-product bf16-split tensor-core GEMMs (dppo_split3_pack + cuBLASLt bf16, fp32 accumulate) under "
+                        "torch autograd (" + str(model.fused_update_reason()) + "); ")
+                     + "fused flat AdamW kernel per network; "
                      + ("forward + loss + backward + all-reduce replayed as ONE CUDA graph per minibatch" if graphed
                         else "eager launches"))}
 

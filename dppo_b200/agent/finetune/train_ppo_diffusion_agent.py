@@ -225,9 +225,20 @@ class TrainPPODiffusionAgent:
         eta_mean = self.model._eta_value()
         ent_const = -eta_mean  # the entropy term of a fixed-eta policy is a constant (diffusion_ppo.py:183-187)
 
+        fused = not self.use_bc_loss and self.model.fused_update_reason() is None
+        with_actor = self.itr >= self.n_critic_warmup_itr
+
         def fwd_bwd(inds_b):
             """zero grads -> actor_ft / critic forward -> fused loss kernel -> backward -> one all-reduce (no host sync)"""
             self.grads.zero()
+            if fused:
+                # the whole minibatch inside libdppo_b200 (tcgen05 forward / dgrad / wgrad kernels, dppo_update_minibatch):
+                # gradients are accumulated straight into the views of the flat all-reduce buffer
+                self.model.update_minibatch(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
+                                            row_count=hi - lo, reward_horizon=self.reward_horizon, vf_coef=self.vf_coef,
+                                            with_actor=with_actor, scalars_out=self.grads.scalars)
+                self.grads.allreduce()
+                return None
             res = self.model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
                                            row_count=hi - lo, use_bc_loss=self.use_bc_loss,
                                            reward_horizon=self.reward_horizon, scalars_out=self.grads.scalars)
@@ -241,7 +252,8 @@ class TrainPPODiffusionAgent:
         # amortise the capture (the rollout buffers get new addresses every iteration, so the graph is per iteration)
         step_fn = fwd_bwd
         n_minibatches = self.update_epochs * num_batch
-        if (self.cuda_graph_update and not self.use_bc_loss and n_minibatches >= 16
+        quantile_clip = self.model.clip_advantage_lower_quantile > 0 or self.model.clip_advantage_upper_quantile < 1
+        if (self.cuda_graph_update and not self.use_bc_loss and not quantile_clip and n_minibatches >= 16
                 and total_steps >= self.batch_size):
             try:
                 step_fn = GraphedMinibatch(fwd_bwd, self.batch_size, self.device)

@@ -338,3 +338,149 @@ extern "C" int dppo_debug_mma_pair_rate(int N, int n_mma, float* d, unsigned lon
   mma_pair_rate_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(N, n_mma, d, out);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
+
+// ------------------------------------------------------------------------------------------------ TMEM read rate
+// 8 warps read a 128-lane x `cols`-column fp32 accumulator region back with tcgen05.ld in different shapes / batching
+// (what an epilogue does), optionally next to a stream of N = 256 MMAs into the other half of TMEM.
+//   variant 0: x16 + wait per load     1: x32 + wait per load     2: two x32 loads, one wait     3: four x32 loads, one wait
+//   variant 4: x16 x 4 loads, one wait
+// out[0] = cycles (max over warps is taken on the host: out[w]), out[8] = MMA cycles
+namespace dppo {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(320, 1) tmem_read_rate_kernel(int variant, int iters, int with_mma, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (96 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    done = 0;
+  }
+  if (warp == 1) tmem_alloc(&slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1) {
+    if (with_mma) {
+      const uint32_t idesc = umma_idesc_bf16(128, 256);
+      const uint32_t a0 = umma_desc_lo(smem_u32(smem)), b0 = umma_desc_lo(smem_u32(smem + 32 * 1024));
+      const long long t0 = clock64();
+      long long n = 0;
+      while (!done) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_lo(tmem + 256, a0 + 2 * k, b0 + 2 * k, idesc, true);
+          umma_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, uint32_t(n) & 1u);
+        ++n;
+      }
+      if (lane == 0) out[8] = clock64() - t0, out[9] = n * 4;
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t base = tmem + (uint32_t(q * 32) << 16) + uint32_t(half * 128);
+    uint32_t acc = 0;
+    named_bar_sync(1, 256);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (variant == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[16];
+          tmem_ld16_nowait(base + c * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc += r[i];
+        }
+      } else if (variant == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32_nowait(base + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc += r[i];
+        }
+      } else if (variant == 2) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(base + c * 64, r0);
+          tmem_ld32_nowait(base + c * 64 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc += r0[i] + r1[i];
+        }
+      } else if (variant == 3) {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32_nowait(base, r0);
+        tmem_ld32_nowait(base + 32, r1);
+        tmem_ld32_nowait(base + 64, r2);
+        tmem_ld32_nowait(base + 96, r3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += r0[i] + r1[i] + r2[i] + r3[i];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          tmem_ld16_nowait(base + c * 64, r0);
+          tmem_ld16_nowait(base + c * 64 + 16, r1);
+          tmem_ld16_nowait(base + c * 64 + 32, r2);
+          tmem_ld16_nowait(base + c * 64 + 48, r3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc += r0[i] + r1[i] + r2[i] + r3[i];
+        }
+      }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) out[warp - 2] = t1 - t0;
+    if (acc == 0x12345678u) out[15] = acc;
+    named_bar_sync(1, 256);
+    if (threadIdx.x == 64) done = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+}  // namespace dppo
+
+// every epilogue warp reads 128 columns of its lane quarter per iteration (the 8 warps together: 128 lanes x 256 columns)
+extern "C" int dppo_debug_tmem_read_rate(int variant, int iters, int with_mma, unsigned long long* out, void* stream) {
+  using namespace dppo;
+  const int smem = 97 * 1024;
+  if (cudaFuncSetAttribute(tmem_read_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
+  tmem_read_rate_kernel<<<1, 320, smem, static_cast<cudaStream_t>(stream)>>>(variant, iters, with_mma, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

@@ -14,6 +14,8 @@
 //   pack_weight_kernel  fp32 weights -> K-major B tiles (optionally transposed: dgrad)
 //   ln_fwd / ln_bwd     LayerNorm + activation around the GEMMs (row statistics need the whole feature row)
 // Warp roles of the two GEMM kernels (320 threads): warp 0 producer, warp 1 MMA issuer + TMEM allocator, warps 2..9 epilogue.
+#include <set>
+
 #include "common.cuh"
 #include "internal.h"
 #include "update_gemm.h"
@@ -120,72 +122,250 @@ __device__ __forceinline__ UBars carve_bars(uint8_t* p) {
 }
 constexpr uint32_t kUBarBytes = (2 * kUMaxStages + 4) * 8 + 16;
 
-template <int CW>
+// address of the 8 floats (row, features n .. n+7) of an fp32 side tensor
+__device__ __forceinline__ size_t side_off(int mode, int ld, int row, int n) {
+  return mode ? ((size_t(row >> 7) * (ld >> 3) + (n >> 3)) * 128 + (row & 127)) * 8 : size_t(row) * ld + n;
+}
+
+// One 128 x NTILE accumulator tile.  Thread = one row (TMEM lane) x 32 columns of each 64-column chunk; the operand
+// images of a chunk are assembled in shared memory (`stage`, 32 KiB: hi image then lo image, the global tile layout) and
+// copied out with fully coalesced 16-byte stores by all 256 epilogue threads.
 __device__ __forceinline__ void rows_epilogue(const RowGemmArgs& a, uint32_t tmem_d, int rt, int nt, int warp, int lane,
-                                              bool vec_pre, bool vec_res, bool vec_out) {
+                                              uint8_t* stage, long long (&pc)[4]) {
   const int q = warp & 3, half = (warp - 2) >> 2;
   const uint32_t rloc = uint32_t(q * 32 + lane);
   const int row = rt * 128 + int(rloc);
   const bool valid = row < a.R;
-  const int nchunks = a.NTILE / CW;
+  const int et = int(threadIdx.x) - 64;
+  const int ncc = (a.NTILE + 63) >> 6;
   float mean = 0.f, rstd = 1.f;
   if (a.ln_stats && valid) mean = a.ln_stats[2 * size_t(row)], rstd = a.ln_stats[2 * size_t(row) + 1];
-  for (int c = half; c < nchunks; c += 2) {
-    float v[CW];
-    tmem_ld(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c * CW), v);
+  const bool vec_pre = a.pre_mode || ((reinterpret_cast<uintptr_t>(a.pre) & 15) == 0 && (a.ld_pre & 3) == 0);
+  const bool vec_res = a.res_mode || ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0 && (a.ld_res & 3) == 0);
+  const bool vec_out = a.out_mode || ((reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0 && (a.ld_out & 3) == 0);
+  for (int cc = 0; cc < ncc; ++cc) {
+    const int cb = cc * 64 + half * 32;  // first column (within the tile) of this thread's 32
+    float v[32];
+    const long long tp0 = clock64();
+    if (cb < a.NTILE) {
+      float lo16[16];
+      tmem_ld16(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(cb), lo16);
 #pragma unroll
-    for (int g = 0; g < CW / 8; ++g) {
-      const int n = nt * a.NTILE + c * CW + g * 8;  // first output feature of this group
+      for (int i = 0; i < 16; ++i) v[i] = lo16[i];
+    }
+    if (cb + 16 < a.NTILE) {
+      float hi16[16];
+      tmem_ld16(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(cb + 16), hi16);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[16 + i] = hi16[i];
+    }
+    const int n0 = nt * a.NTILE + cb;
+    const long long tp1 = clock64();
+    pc[0] += tp1 - tp0;
+    uint32_t mword = 0, mout = 0;
+    if (a.mask_in && valid && n0 < a.N) mword = a.mask_in[(size_t(rt) * a.mask_words + (n0 >> 5)) * 128 + rloc];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = n0 + g * 8;  // first output feature of this group
+      const bool live = cb + g * 8 < a.NTILE && n < a.N;
       float x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = v[g * 8 + i];
-      if (a.bias) {
+      for (int i = 0; i < 8; ++i) x[i] = live ? v[g * 8 + i] : 0.f;
+      if (live) {
+        if (a.bias) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (n + i < a.N) x[i] += __ldg(a.bias + n + i);
-      }
-      if (a.pre) {
-        float p[8];
-        if (valid) load8(a.pre + size_t(row) * a.ld_pre + n, vec_pre, n, a.N, p);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) p[i] = 0.f;
+          for (int i = 0; i < 8; ++i)
+            if (n + i < a.N) x[i] += __ldg(a.bias + n + i);
         }
-        if (a.ln_stats) {
+        if (a.mask_in) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int nn = n + i < a.N ? n + i : a.N - 1;
-            p[i] = (p[i] - mean) * rstd * __ldg(a.ln_g + nn) + __ldg(a.ln_b + nn);
+          for (int i = 0; i < 8; ++i) x[i] = ((mword >> (g * 8 + i)) & 1u) ? x[i] : 0.f;
+        } else if (a.pre) {
+          float p[8];
+          if (valid) load8(a.pre + side_off(a.pre_mode, a.ld_pre, row, n), vec_pre, n, a.N, p);
+          else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[i] = 0.f;
           }
+          if (a.ln_stats) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int nn = n + i < a.N ? n + i : a.N - 1;
+              p[i] = (p[i] - mean) * rstd * __ldg(a.ln_g + nn) + __ldg(a.ln_b + nn);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] *= act_grad(a.act_grad, p[i]);
         }
+        if (a.res && valid) {
+          float r8[8];
+          load8(a.res + side_off(a.res_mode, a.ld_res, row, n), vec_res, n, a.N, r8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] *= act_grad(a.act_grad, p[i]);
-      }
-      if (a.res && valid) {
-        float r8[8];
-        load8(a.res + size_t(row) * a.ld_res + n, vec_res, n, a.N, r8);
+          for (int i = 0; i < 8; ++i) x[i] += r8[i];
+        }
+        if (a.out_f32 && valid) store8(a.out_f32 + side_off(a.out_mode, a.ld_out, row, n), vec_out, n, a.N, x);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] += r8[i];
+        for (int i = 0; i < 8; ++i) mout |= (valid && n + i < a.N && x[i] > 0.f) ? (1u << (g * 8 + i)) : 0u;
       }
-      if (a.out_f32 && valid && n < a.N) store8(a.out_f32 + size_t(row) * a.ld_out + n, vec_out, n, a.N, x);
       if (a.out_op) {
         float y[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = (valid && n + i < a.N) ? act_apply(a.act_out, x[i]) : 0.f;
-        const int col = a.op_col0 + n;
-        uint8_t* img = a.out_op + (size_t(rt) * a.FCo + (col >> 6)) * 2 * kImg;
-        store_op8(img, rloc, uint32_t(col & 63), y);
+        for (int i = 0; i < 8; ++i) y[i] = (live && valid && n + i < a.N) ? act_apply(a.act_out, x[i]) : 0.f;
+        store_op8(stage, rloc, uint32_t(half * 32 + g * 8), y);
       }
+    }
+    if (a.mask_out && n0 < a.N && cb < a.NTILE) a.mask_out[(size_t(rt) * a.mask_words + (n0 >> 5)) * 128 + rloc] = mout;
+    const long long tp2 = clock64();
+    pc[1] += tp2 - tp1;
+    if (a.out_op) {
+      named_bar_sync(1, kUEpiThreads);  // the chunk's two images are complete in shared memory
+      const long long tp3 = clock64();
+      pc[2] += tp3 - tp2;
+      const int fc = ((a.op_col0 + nt * a.NTILE) >> 6) + cc;
+      uint4* dst = reinterpret_cast<uint4*>(a.out_op + (size_t(rt) * a.FCo + fc) * 2 * kImg);
+      const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[et + i * kUEpiThreads] = src[et + i * kUEpiThreads];
+      named_bar_sync(1, kUEpiThreads);  // everybody has read the staging buffer before the next chunk overwrites it
+      pc[3] += clock64() - tp3;
     }
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- specialised epilogue
+// The epilogue is instruction-issue bound (8 warps on 4 schedulers, 32 accumulator values per thread and chunk): the
+// generic version above spends ~2.5 k cycles per 64-column chunk on run-time flag checks alone (role counters in
+// profiles/r2).  The variants the update program actually launches are therefore compiled as straight-line code:
+//   V & 1        bias            (V >> 1) & 3   0 none | 1 ReLU bit mask in | 2 relu'(pre) | 3 mish'(pre)   (pre: tiled fp32)
+//   (V >> 3) & 1 residual in     (V >> 4) & 1   fp32 out (tiled)       (V >> 5) & 3   activation of the operand output
+//   (V >> 7) & 1 bit mask out
+// Preconditions (checked by the launcher): NTILE and N multiples of 64, operand output present, side tensors tiled.
+constexpr int kEpiGeneric = -1;
+constexpr int epi_variant(bool bias, int pre, bool res, bool outf, int acto, bool masko) {
+  return (bias ? 1 : 0) | (pre << 1) | ((res ? 1 : 0) << 3) | ((outf ? 1 : 0) << 4) | (acto << 5) | ((masko ? 1 : 0) << 7);
+}
+
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int V>
+__device__ __forceinline__ void rows_epilogue_fast(const RowGemmArgs& a, uint32_t tmem_d, int rt, int nt, int warp, int lane,
+                                                   uint8_t* stage) {
+  constexpr bool BIAS = V & 1, RES = (V >> 3) & 1, OUTF = (V >> 4) & 1, MASKO = (V >> 7) & 1;
+  constexpr int PRE = (V >> 1) & 3, ACTO = (V >> 5) & 3;
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  const uint32_t rloc = uint32_t(q * 32 + lane);
+  const int row = rt * 128 + int(rloc);
+  const bool valid = row < a.R;
+  const int et = int(threadIdx.x) - 64;
+  const int ncc = a.NTILE >> 6;
+  const int G = a.N >> 3;  // 8-feature groups per row of the tiled side tensors (all of width N)
+  for (int cc = 0; cc < ncc; ++cc) {
+    const int cb = cc * 64 + half * 32;
+    const int n0 = nt * a.NTILE + cb;
+    uint32_t raw[32];
+    tmem_ld32_issue(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(cb), raw);
+    // side inputs are requested before the accumulator is needed
+    const size_t side = ((size_t(rt) * G + (n0 >> 3)) * 128 + rloc) * 8;  // group g of this chunk: + g * 1024 floats
+    float4 pr[8], rs[8];
+    uint32_t mword = 0;
+    if (valid) {
+      if (PRE == 1) mword = a.mask_in[(size_t(rt) * a.mask_words + (n0 >> 5)) * 128 + rloc];
+      if (PRE >= 2) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          pr[2 * g] = *reinterpret_cast<const float4*>(a.pre + side + g * 1024);
+          pr[2 * g + 1] = *reinterpret_cast<const float4*>(a.pre + side + g * 1024 + 4);
+        }
+      }
+      if (RES) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          rs[2 * g] = *reinterpret_cast<const float4*>(a.res + side + g * 1024);
+          rs[2 * g + 1] = *reinterpret_cast<const float4*>(a.res + side + g * 1024 + 4);
+        }
+      }
+    }
+    float x[32];
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
+    if (BIAS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + j);
+        x[4 * j] += b4.x, x[4 * j + 1] += b4.y, x[4 * j + 2] += b4.z, x[4 * j + 3] += b4.w;
+      }
+    }
+    uint32_t mout = 0;
+    if (valid) {
+      if (PRE == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = (mword & (1u << i)) ? x[i] : 0.f;
+      } else if (PRE >= 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float p4[4] = {pr[j].x, pr[j].y, pr[j].z, pr[j].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[4 * j + i] = PRE == 2 ? (p4[i] > 0.f ? x[4 * j + i] : 0.f) : x[4 * j + i] * mish_grad_f(p4[i]);
+        }
+      }
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[4 * j] += rs[j].x, x[4 * j + 1] += rs[j].y, x[4 * j + 2] += rs[j].z, x[4 * j + 3] += rs[j].w;
+      }
+      if (OUTF) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<float4*>(a.out_f32 + side + g * 1024) = make_float4(x[8 * g], x[8 * g + 1], x[8 * g + 2], x[8 * g + 3]);
+          *reinterpret_cast<float4*>(a.out_f32 + side + g * 1024 + 4) = make_float4(x[8 * g + 4], x[8 * g + 5], x[8 * g + 6], x[8 * g + 7]);
+        }
+      }
+      if (MASKO) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mout |= x[i] > 0.f ? (1u << i) : 0u;
+        a.mask_out[(size_t(rt) * a.mask_words + (n0 >> 5)) * 128 + rloc] = mout;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = ACTO == kUActRelu ? fmaxf(x[i], 0.f) : (ACTO == kUActMish ? mish_f(x[i]) : x[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float y[8] = {x[8 * g], x[8 * g + 1], x[8 * g + 2], x[8 * g + 3], x[8 * g + 4], x[8 * g + 5], x[8 * g + 6], x[8 * g + 7]};
+      store_op8(stage, rloc, uint32_t(half * 32 + g * 8), y);
+    }
+    named_bar_sync(1, kUEpiThreads);
+    const int fc = ((a.op_col0 + nt * a.NTILE) >> 6) + cc;
+    uint4* dst = reinterpret_cast<uint4*>(a.out_op + (size_t(rt) * a.FCo + fc) * 2 * kImg);
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[et + i * kUEpiThreads] = src[et + i * kUEpiThreads];
+    named_bar_sync(1, kUEpiThreads);
+  }
+}
+
+template <int V>
 __global__ void __launch_bounds__(kUThreads, 1) ugemm_rows_kernel(const RowGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t b_plane = uint32_t(a.NTILE) * 128u;
   const uint32_t stage_bytes = 2 * kImg + 2 * b_plane;
-  const UBars bar = carve_bars(smem + size_t(a.nstage) * stage_bytes);
+  uint8_t* epi_stage = smem + size_t(a.nstage) * stage_bytes;  // 32 KiB: operand images of one output chunk
+  const UBars bar = carve_bars(epi_stage + 2 * kImg);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.nstage; ++i) mbar_init(&bar.full[i], 1), mbar_init(&bar.empty[i], 1);
@@ -202,12 +382,16 @@ __global__ void __launch_bounds__(kUThreads, 1) ugemm_rows_kernel(const RowGemmA
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ producer
     uint32_t stage = 0, phase = 0;
+    long long w_empty = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int rt = t / a.NT, nt = t - rt * a.NT;
       const uint8_t* a_src = a.A + size_t(rt) * a.FCa * 2 * kImg;
       const uint8_t* b_src = a.B + size_t(nt) * a.KC * 2 * b_plane;
       for (int kc = 0; kc < a.KC; ++kc) {
+        const long long tw = clock64();
         mbar_wait(&bar.empty[stage], phase ^ 1);
+        w_empty += clock64() - tw;
         if (lane == 0) {
           uint8_t* dst = smem + size_t(stage) * stage_bytes;
           mbar_arrive_expect_tx(&bar.full[stage], stage_bytes);
@@ -218,19 +402,26 @@ __global__ void __launch_bounds__(kUThreads, 1) ugemm_rows_kernel(const RowGemmA
         if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
       }
     }
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = w_empty, a.prof[blockIdx.x * 16 + 1] = clock64() - t_begin;
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
+    long long w_full = 0, w_tempty = 0;
+    const long long t_begin = clock64();
     const uint32_t idesc = umma_idesc_bf16(128, a.NTILE);
     const uint32_t leader = elect_one() ? 1u : 0u;
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const uint32_t buf = uint32_t(it) & 1u, use = uint32_t(it) >> 1;
+      long long tw = clock64();
       mbar_wait(&bar.tempty[buf], (use & 1u) ^ 1u);  // the epilogue drained this accumulator
+      w_tempty += clock64() - tw;
       tc_fence_after();
       const uint32_t d = tmem + buf * 256u;
       for (int kc = 0; kc < a.KC; ++kc) {
+        tw = clock64();
         mbar_wait(&bar.full[stage], phase);
+        w_full += clock64() - tw;
         tc_fence_after();
         const uint32_t base = smem_u32(smem + size_t(stage) * stage_bytes);
         const uint64_t a_hi = umma_desc(base), a_lo = umma_desc(base + kImg);
@@ -242,23 +433,32 @@ __global__ void __launch_bounds__(kUThreads, 1) ugemm_rows_kernel(const RowGemmA
       }
       umma_commit_p(&bar.tfull[buf], leader);
     }
+    if (a.prof && lane == 0)
+      a.prof[blockIdx.x * 16 + 2] = w_full, a.prof[blockIdx.x * 16 + 3] = w_tempty, a.prof[blockIdx.x * 16 + 4] = clock64() - t_begin;
   } else {
     // ------------------------------------------------------------------------------------------ epilogue
-    const bool vec_pre = a.pre && (reinterpret_cast<uintptr_t>(a.pre) & 15) == 0 && (a.ld_pre & 3) == 0;
-    const bool vec_res = a.res && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 && (a.ld_res & 3) == 0;
-    const bool vec_out = a.out_f32 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0 && (a.ld_out & 3) == 0;
+    long long w_tfull = 0, w_arrive = 0;
+    long long pc[4] = {0, 0, 0, 0};
+    const long long t_begin = clock64();
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int rt = t / a.NT, nt = t - rt * a.NT;
       const uint32_t buf = uint32_t(it) & 1u, use = uint32_t(it) >> 1;
+      const long long tw = clock64();
       mbar_wait(&bar.tfull[buf], use & 1u);
+      w_tfull += clock64() - tw;
       tc_fence_after();
-      if (a.NTILE % 64 == 0)
-        rows_epilogue<32>(a, tmem + buf * 256u, rt, nt, warp, lane, vec_pre, vec_res, vec_out);
-      else
-        rows_epilogue<16>(a, tmem + buf * 256u, rt, nt, warp, lane, vec_pre, vec_res, vec_out);
+      if (V == kEpiGeneric) rows_epilogue(a, tmem + buf * 256u, rt, nt, warp, lane, epi_stage, pc);
+      else rows_epilogue_fast<V>(a, tmem + buf * 256u, rt, nt, warp, lane, epi_stage);
+      const long long ta = clock64();
       tc_fence_before();
       mbar_arrive(&bar.tempty[buf]);
+      w_arrive += clock64() - ta;
+    }
+    if (a.prof && threadIdx.x == 64) {
+      unsigned long long* o = a.prof + blockIdx.x * 16;
+      o[5] = w_tfull, o[6] = clock64() - t_begin, o[7] = w_arrive;
+      o[8] = pc[0], o[9] = pc[1], o[10] = pc[2], o[11] = pc[3];
     }
   }
   tc_fence_before();
@@ -668,7 +868,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 // ============================================================================================== launchers
-int row_gemm_ntile(int N) { return N >= 256 ? 256 : (N + 15) / 16 * 16; }
+static int g_ntile_cap = 256, g_max_stages = 0;
+static bool g_fast_epilogue = true;
+void set_row_gemm_fast_epilogue(bool on) { g_fast_epilogue = on; }
+void set_row_gemm_tuning(int ntile_cap, int max_stages) {
+  g_ntile_cap = (ntile_cap >= 64 && ntile_cap <= 256 && ntile_cap % 64 == 0) ? ntile_cap : 256;
+  g_max_stages = max_stages;
+}
+int row_gemm_ntile_cap() { return g_ntile_cap; }
+int row_gemm_ntile(int N) { return N >= g_ntile_cap ? g_ntile_cap : (N + 15) / 16 * 16; }
 
 size_t packed_weight_bytes(int rows, int K, int NTILE) {
   const int NT = (rows + NTILE - 1) / NTILE, KC = (K + 63) / 64;
@@ -720,24 +928,67 @@ int launch_row_gemm(const RowGemmArgs& a0, int sm_count, cudaStream_t st) {
   if (a.R <= 0) return DPPO_OK;
   if (a.NTILE < 16 || a.NTILE > 256 || a.NTILE % 16 || a.KC < 1 || a.NT < 1)
     return set_error("row gemm: bad tile geometry NTILE=%d KC=%d NT=%d", a.NTILE, a.KC, a.NT), DPPO_ERR_INVALID;
-  if (a.out_op && ((a.op_col0 & 7) || (a.op_col0 + a.NT * a.NTILE + 63) / 64 > a.FCo))
-    return set_error("row gemm: operand output columns [%d, %d) do not fit %d chunks", a.op_col0, a.op_col0 + a.NT * a.NTILE, a.FCo),
-           DPPO_ERR_INVALID;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ugemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUSmemBudget));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ugemm_rows_kernel)");
-    configured = true;
+  if (a.out_op && ((a.op_col0 & 63) || (a.NT > 1 && (a.NTILE & 63)) || (a.op_col0 + a.NT * a.NTILE + 63) / 64 > a.FCo))
+    return set_error("row gemm: operand output columns [%d, %d) must cover whole 64-feature chunks of %d", a.op_col0,
+                     a.op_col0 + a.NT * a.NTILE, a.FCo), DPPO_ERR_INVALID;
+  if ((a.pre && a.pre_mode && (a.ld_pre & 7)) || (a.res && a.res_mode && (a.ld_res & 7)) || (a.out_f32 && a.out_mode && (a.ld_out & 7)))
+    return set_error("row gemm: tiled fp32 tensors need a feature count that is a multiple of 8"), DPPO_ERR_INVALID;
+  // straight-line epilogue variants (see rows_epilogue_fast); anything else runs the generic epilogue
+  int variant = kEpiGeneric;
+  const bool fast_ok = a.out_op && a.NTILE % 64 == 0 && a.N % 64 == 0 && a.N == a.NT * a.NTILE && !a.ln_stats && g_fast_epilogue &&
+                       (!a.pre || a.pre_mode == 1) && (!a.res || a.res_mode == 1) && (!a.out_f32 || a.out_mode == 1) &&
+                       (!a.pre || a.ld_pre == a.N) && (!a.res || a.ld_res == a.N) && (!a.out_f32 || a.ld_out == a.N) &&
+                       (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) && !(a.pre && a.mask_in) &&
+                       (!(a.mask_in || a.mask_out) || a.mask_words * 32 == a.N);
+  if (fast_ok) {
+    const int pre = a.mask_in ? 1 : (a.pre ? (a.act_grad == kUActRelu ? 2 : (a.act_grad == kUActMish ? 3 : -1)) : 0);
+    if (pre >= 0) variant = epi_variant(a.bias != nullptr, pre, a.res != nullptr, a.out_f32 != nullptr, a.act_out, a.mask_out != nullptr);
+  }
+  void (*kfn)(const RowGemmArgs) = nullptr;
+  switch (variant) {
+#define DPPO_EPI_CASE(...)                        \
+  case epi_variant(__VA_ARGS__):                  \
+    kfn = ugemm_rows_kernel<epi_variant(__VA_ARGS__)>; \
+    break;
+    //            bias   pre res    outf   act        mask-out
+    DPPO_EPI_CASE(false, 0, false, true, kUActRelu, true)    // layer 0, ReLU actor
+    DPPO_EPI_CASE(false, 0, false, true, kUActMish, false)   // layer 0, Mish actor
+    DPPO_EPI_CASE(true, 0, false, true, kUActRelu, true)     // layer 0 with bias (critic), ReLU
+    DPPO_EPI_CASE(true, 0, false, true, kUActMish, false)    // layer 0 with bias (critic), Mish; l1, Mish
+    DPPO_EPI_CASE(true, 0, false, false, kUActRelu, true)    // l1, ReLU
+    DPPO_EPI_CASE(true, 0, true, false, kUActNone, false)    // l2 of the last block
+    DPPO_EPI_CASE(true, 0, true, true, kUActRelu, true)      // l2, ReLU
+    DPPO_EPI_CASE(true, 0, true, true, kUActMish, false)     // l2, Mish
+    DPPO_EPI_CASE(false, 0, false, true, kUActNone, false)   // dgrad of the output layer
+    DPPO_EPI_CASE(false, 1, false, false, kUActNone, false)  // dgrad l2, ReLU mask
+    DPPO_EPI_CASE(false, 3, false, false, kUActNone, false)  // dgrad l2, Mish
+    DPPO_EPI_CASE(false, 1, true, true, kUActNone, false)    // dgrad l1, ReLU mask
+    DPPO_EPI_CASE(false, 3, true, true, kUActNone, false)    // dgrad l1, Mish
+    DPPO_EPI_CASE(false, 2, false, false, kUActNone, false)  // dgrad with relu'(fp32 pre)
+    DPPO_EPI_CASE(false, 2, true, true, kUActNone, false)
+#undef DPPO_EPI_CASE
+    default:
+      variant = kEpiGeneric;
+      kfn = ugemm_rows_kernel<kEpiGeneric>;
+  }
+  {
+    static std::set<const void*> configured;
+    if (!configured.count(reinterpret_cast<const void*>(kfn))) {
+      cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUSmemBudget));
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ugemm_rows_kernel)");
+      configured.insert(reinterpret_cast<const void*>(kfn));
+    }
   }
   const size_t stage_bytes = 2 * size_t(kImg) + size_t(a.NTILE) * 256;
-  int nstage = int((kUSmemBudget - 1024 - kUBarBytes) / stage_bytes);
+  int nstage = int((kUSmemBudget - 1024 - kUBarBytes - 2 * kImg) / stage_bytes);
   if (nstage > kUMaxStages) nstage = kUMaxStages;
+  if (g_max_stages >= 1 && nstage > g_max_stages) nstage = g_max_stages;
   a.nstage = nstage;
   a.RT = (a.R + 127) / 128;
   const int n_tiles = a.RT * a.NT;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  const size_t smem = size_t(nstage) * stage_bytes + kUBarBytes + 1024;
-  ugemm_rows_kernel<<<grid, kUThreads, smem, st>>>(a);
+  const size_t smem = size_t(nstage) * stage_bytes + 2 * kImg + kUBarBytes + 1024;
+  kfn<<<grid, kUThreads, smem, st>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ugemm_rows_kernel launch");
 }

@@ -37,21 +37,29 @@ struct RowGemmArgs {
   int R, RT;          // rows, row tiles of 128
   int KC;             // 64-wide contraction chunks
   int N, NTILE, NT;   // real output features; tile width (multiple of 16, <= 256); number of column tiles
-  // ---- epilogue, per element v = acc[r][n]
+  // ---- epilogue, per element v = acc[r][n].  fp32 side tensors are row-major [R][ld] (mode 0) or "tiled" (mode 1):
+  // [row tile][n / 8][128 rows][8 floats], ld = feature count (multiple of 8) - the layout in which a warp of the
+  // epilogue (lane = row, 8 consecutive features per access) reads / writes 1 KiB contiguous.
   const float* bias;  // [N] or null:                 v += bias[n]
-  const float* pre;   // fp32 [R][ld_pre] or null:     v *= act'(p), p = pre[r][n] (or its LayerNorm, below)
-  int ld_pre, act_grad;
+  const float* pre;   // fp32 or null:                 v *= act'(p), p = pre[r][n] (or its LayerNorm, below)
+  int ld_pre, pre_mode, act_grad;
+  const uint32_t* mask_in;  // ReLU derivative as bits (written by a forward epilogue) instead of `pre`, or null
   const float* ln_stats;  // [R][2] (mean, rstd) or null: p = (pre - mean) * rstd * ln_g[n] + ln_b[n]
   const float* ln_g;
   const float* ln_b;
-  const float* res;   // fp32 [R][ld_res] or null:     v += res[r][n]
-  int ld_res;
-  float* out_f32;     // fp32 [R][ld_out] or null
-  int ld_out;
+  const float* res;   // fp32 or null:                 v += res[r][n]
+  int ld_res, res_mode;
+  float* out_f32;     // fp32 or null
+  int ld_out, out_mode;
   uint8_t* out_op;    // operand images of act_out(v) or null, feature n lands at column op_col0 + n
   int FCo, op_col0, act_out;
+  uint32_t* mask_out; // bit (n % 32) of word [row tile][n / 32][row] = (v > 0), or null
+  int mask_words;     // 32-feature words per row of the mask tensors
   int nstage;
+  unsigned long long* prof;  // optional [grid][8] role cycle counters (bring-up), null in production
 };
+inline size_t f32_tiled_floats(int rows, int features) { return size_t((rows + 127) / 128) * 128 * ((features + 7) / 8 * 8); }
+inline size_t mask_words_total(int rows, int features) { return size_t((rows + 127) / 128) * 128 * ((features + 31) / 32); }
 
 // dW[n][k] += sum_r G[r][n] * X[r][k];  db[n] += sum_r G[r][n]
 struct WgradArgs {
@@ -108,6 +116,9 @@ struct PackWJob {
 };
 int launch_pack_weights(const PackWJob* d_jobs, int n_jobs, long long max_total, cudaStream_t st);
 void set_mn_desc_override(uint32_t lbo_bytes, uint32_t sbo_bytes);
+void set_row_gemm_tuning(int ntile_cap, int max_stages);  // bring-up: cap the column tile / ring depth (0 = default)
+int row_gemm_ntile_cap();
+void set_row_gemm_fast_epilogue(bool on);  // bring-up: force the generic epilogue
 // fp32 [rows][K] (element (j, c) at W[j * s_row + c * s_col]) -> packed B tiles [NT][KC][plane][NTILE x 128 B]
 int launch_pack_weight(const float* W, int64_t s_row, int64_t s_col, int rows, int K, int NTILE, uint8_t* out, cudaStream_t st);
 size_t packed_weight_bytes(int rows, int K, int NTILE);

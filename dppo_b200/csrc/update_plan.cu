@@ -56,6 +56,9 @@ struct ResMlp {
   std::vector<float*> Hf, Yf;       // fp32 pre-activations h_b (block inputs), y_b (l1 outputs)
   std::vector<uint8_t*> A, A1;      // operand images act(norm(h_b)), act(norm(y_b))
   std::vector<float*> st1, st2;     // LayerNorm statistics
+  std::vector<uint32_t*> MH, MY;    // ReLU nets: (h_b > 0), (y_b > 0) as bit masks instead of the fp32 pre-activations
+  int fmode = 1;                    // layout of the fp32 side tensors: 1 = tiled (update_gemm.h), 0 = row-major (LayerNorm nets)
+  bool relu_bits = false;
   uint8_t* HL = nullptr;            // raw h_nb images (input of the output layer)
   float* OUT = nullptr;             // fp32 [R][Dout]
   // backward
@@ -87,6 +90,7 @@ struct dppo_update {
   int K0p = 0;
   int* d_ts = nullptr;  // [ft] timestep of every denoising index
   float *t_emb = nullptr, *t_hpre = nullptr, *t_temb = nullptr, *TB = nullptr, *t_dtemb = nullptr, *t_dpre = nullptr;
+  float *t_G = nullptr, *t_hid = nullptr;
   // weight-pack job table
   PackWJob* d_jobs = nullptr;
   int n_jobs_actor = 0, n_jobs = 0;
@@ -122,9 +126,18 @@ static int alloc_resmlp(dppo_update* u, ResMlp& m, int R) {
   if (m.own_x0) UALLOC(m.X0, opmat_bytes(R, m.K0));
   m.Hf.assign(m.nb, nullptr), m.Yf.assign(m.nb, nullptr), m.A.assign(m.nb, nullptr), m.A1.assign(m.nb, nullptr);
   m.st1.assign(m.nb, nullptr), m.st2.assign(m.nb, nullptr);
+  m.MH.assign(m.nb, nullptr), m.MY.assign(m.nb, nullptr);
+  m.fmode = m.ln ? 0 : 1;
+  m.relu_bits = !m.ln && m.act == kUActRelu && m.H % 32 == 0;
+  const size_t fbytes = f32_tiled_floats(R, m.H) * 4;
   for (int b = 0; b < m.nb; ++b) {
-    UALLOC(m.Hf[b], size_t(R) * m.H * 4);
-    UALLOC(m.Yf[b], size_t(R) * m.H * 4);
+    UALLOC(m.Hf[b], fbytes);
+    if (m.relu_bits) {
+      UALLOC(m.MH[b], mask_words_total(R, m.H) * 4);
+      UALLOC(m.MY[b], mask_words_total(R, m.H) * 4);
+    } else {
+      UALLOC(m.Yf[b], fbytes);
+    }
     UALLOC(m.A[b], opmat_bytes(R, m.H));
     UALLOC(m.A1[b], opmat_bytes(R, m.H));
     if (m.ln) {
@@ -135,10 +148,10 @@ static int alloc_resmlp(dppo_update* u, ResMlp& m, int R) {
   UALLOC(m.HL, opmat_bytes(R, m.H));
   UALLOC(m.OUT, size_t(R) * m.Dout * 4);
   UALLOC(m.GOUT, opmat_bytes(R, m.Dout));
-  UALLOC(m.DHf, size_t(R) * m.H * 4);
+  UALLOC(m.DHf, fbytes);
   UALLOC(m.DHop, opmat_bytes(R, m.H));
   UALLOC(m.G1op, opmat_bytes(R, m.H));
-  if (m.ln) UALLOC(m.DZf, size_t(R) * m.H * 4);
+  if (m.ln) UALLOC(m.DZf, fbytes);
   return DPPO_OK;
 }
 
@@ -244,38 +257,42 @@ __global__ void scatter_dw0_kernel(const float* __restrict__ dW0p, int H, int in
   else dW0[size_t(f) * in0 + c - Dc] += g;
 }
 
-// one block: G[d][f] = dW0p[f][Dc + D + d] is the gradient w.r.t. TB[d][f]; back through TB = b0 + W0_time temb and
-// the time MLP.  All outputs are accumulated (+=) into the parameter gradients.
-__global__ void __launch_bounds__(256) time_table_bwd_kernel(const float* __restrict__ dW0p, int K0p, int gcol, int ft, int H,
-                                                             int td, int D, int in0, const float* __restrict__ W0,
-                                                             const float* __restrict__ tw2, const float* __restrict__ emb,
-                                                             const float* __restrict__ hpre, const float* __restrict__ temb,
-                                                             float* __restrict__ dtemb, float* __restrict__ dpre,
-                                                             float* __restrict__ dW0, float* __restrict__ db0,
-                                                             float* __restrict__ dtw1, float* __restrict__ dtb1,
-                                                             float* __restrict__ dtw2, float* __restrict__ dtb2) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  // db0, dW0[:, time]
-  for (int f = tid; f < H; f += nt) {
-    float sb = 0.f;
-    for (int d = 0; d < ft; ++d) sb += dW0p[size_t(f) * K0p + gcol + d];
-    db0[f] += sb;
-    for (int j = 0; j < td; ++j) {
-      float s = 0.f;
-      for (int d = 0; d < ft; ++d) s += dW0p[size_t(f) * K0p + gcol + d] * temb[d * td + j];
-      dW0[size_t(f) * in0 + D + j] += s;
-    }
+// G[d][f] = dW0p[f][Dc + D + d] is the gradient w.r.t. TB[d][f] = b0[f] + W0[f, D:D+td] . temb[d]; three small kernels
+// carry it back through the time MLP.  All outputs are accumulated (+=) into the parameter gradients.
+// (a) grid = ft blocks: dtemb[d][j] = sum_f G[d][f] W0[f][D + j] (one warp per j, lanes over f); G is also copied to a
+//     contiguous [ft][H] scratch for (c)
+__global__ void __launch_bounds__(256) time_bwd_a_kernel(const float* __restrict__ dW0p, int K0p, int gcol, int H, int td, int D,
+                                                         int in0, const float* __restrict__ W0, float* __restrict__ Gs,
+                                                         float* __restrict__ dtemb) {
+  extern __shared__ float s_g[];
+  const int d = blockIdx.x;
+  for (int f = threadIdx.x; f < H; f += blockDim.x) {
+    const float v = dW0p[size_t(f) * K0p + gcol + d];
+    s_g[f] = v;
+    Gs[size_t(d) * H + f] = v;
   }
-  // dtemb[d][j] = sum_f G[d][f] W0[f][D + j]
-  for (int i = tid; i < ft * td; i += nt) {
-    const int d = i / td, j = i - d * td;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < td; j += nw) {
     float s = 0.f;
-    for (int f = 0; f < H; ++f) s += dW0p[size_t(f) * K0p + gcol + d] * W0[size_t(f) * in0 + D + j];
-    dtemb[i] = s;
+    for (int f = lane; f < H; f += 32) s += s_g[f] * W0[size_t(f) * in0 + D + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dtemb[d * td + j] = s;
   }
+}
+
+// (b) one block: the two Linear layers of the time MLP (ft x td x 2td work)
+__global__ void __launch_bounds__(256) time_bwd_b_kernel(int ft, int td, const float* __restrict__ tw2,
+                                                         const float* __restrict__ emb, const float* __restrict__ hpre,
+                                                         const float* __restrict__ dtemb, float* __restrict__ hid,
+                                                         float* __restrict__ dpre, float* __restrict__ dtw1,
+                                                         float* __restrict__ dtb1, float* __restrict__ dtw2,
+                                                         float* __restrict__ dtb2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < ft * 2 * td; i += nt) hid[i] = mish_exact_u(hpre[i]);
   __threadfence_block();
   __syncthreads();
-  // second Linear: temb = tw2 hid + tb2
   for (int j = tid; j < td; j += nt) {
     float s = 0.f;
     for (int d = 0; d < ft; ++d) s += dtemb[d * td + j];
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(256) time_table_bwd_kernel(const float* __rest
   for (int i = tid; i < td * 2 * td; i += nt) {
     const int j = i / (2 * td), k = i - j * 2 * td;
     float s = 0.f;
-    for (int d = 0; d < ft; ++d) s += dtemb[d * td + j] * mish_exact_u(hpre[d * 2 * td + k]);
+    for (int d = 0; d < ft; ++d) s += dtemb[d * td + j] * hid[d * 2 * td + k];
     dtw2[i] += s;
   }
   for (int i = tid; i < ft * 2 * td; i += nt) {
@@ -295,7 +312,6 @@ __global__ void __launch_bounds__(256) time_table_bwd_kernel(const float* __rest
   }
   __threadfence_block();
   __syncthreads();
-  // first Linear: hpre = tw1 emb + tb1
   for (int k = tid; k < 2 * td; k += nt) {
     float s = 0.f;
     for (int d = 0; d < ft; ++d) s += dpre[d * 2 * td + k];
@@ -306,6 +322,21 @@ __global__ void __launch_bounds__(256) time_table_bwd_kernel(const float* __rest
     float s = 0.f;
     for (int d = 0; d < ft; ++d) s += dpre[d * 2 * td + k] * emb[d * td + j];
     dtw1[i] += s;
+  }
+}
+
+// (c) one thread per feature: db0[f] += sum_d G[d][f], dW0[f][D + j] += sum_d G[d][f] temb[d][j]
+__global__ void time_bwd_c_kernel(const float* __restrict__ Gs, int ft, int H, int td, int D, int in0,
+                                  const float* __restrict__ temb, float* __restrict__ dW0, float* __restrict__ db0) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= H) return;
+  float sb = 0.f;
+  for (int d = 0; d < ft; ++d) sb += Gs[size_t(d) * H + f];
+  db0[f] += sb;
+  for (int j = 0; j < td; ++j) {
+    float s = 0.f;
+    for (int d = 0; d < ft; ++d) s += Gs[size_t(d) * H + f] * temb[d * td + j];
+    dW0[size_t(f) * in0 + D + j] += s;
   }
 }
 
@@ -342,8 +373,9 @@ static int resmlp_forward(const dppo_update* u, ResMlp& m, int R, float* out_ove
   {
     RowGemmArgs g = gemm_args(m.X0, m.FC0, m.L0, false, R);
     g.bias = m.L0.b;
-    g.out_f32 = m.Hf[0], g.ld_out = m.H;
+    g.out_f32 = m.Hf[0], g.ld_out = m.H, g.out_mode = m.fmode;
     if (!m.ln) g.out_op = m.A[0], g.FCo = m.FCH, g.act_out = m.act;
+    if (m.relu_bits) g.mask_out = m.MH[0], g.mask_words = m.H / 32;
     URUN(launch_row_gemm(g, sm, st));
     if (m.ln) URUN(launch_ln_fwd(m.Hf[0], m.H, R, m.H, m.blk[0].g1, m.blk[0].be1, eps, m.act, m.st1[0], m.A[0], m.FCH, st));
   }
@@ -352,7 +384,8 @@ static int resmlp_forward(const dppo_update* u, ResMlp& m, int R, float* out_ove
     {
       RowGemmArgs g = gemm_args(m.A[b], m.FCH, B.l1, false, R);
       g.bias = B.l1.b;
-      g.out_f32 = m.Yf[b], g.ld_out = m.H;
+      if (m.relu_bits) g.mask_out = m.MY[b], g.mask_words = m.H / 32;
+      else g.out_f32 = m.Yf[b], g.ld_out = m.H, g.out_mode = m.fmode;
       if (!m.ln) g.out_op = m.A1[b], g.FCo = m.FCH, g.act_out = m.act;
       URUN(launch_row_gemm(g, sm, st));
       if (m.ln) URUN(launch_ln_fwd(m.Yf[b], m.H, R, m.H, B.g2, B.be2, eps, m.act, m.st2[b], m.A1[b], m.FCH, st));
@@ -361,12 +394,13 @@ static int resmlp_forward(const dppo_update* u, ResMlp& m, int R, float* out_ove
       const bool last = b + 1 == m.nb;
       RowGemmArgs g = gemm_args(m.A1[b], m.FCH, B.l2, false, R);
       g.bias = B.l2.b;
-      g.res = m.Hf[b], g.ld_res = m.H;
+      g.res = m.Hf[b], g.ld_res = m.H, g.res_mode = m.fmode;
       if (last) {
         g.out_op = m.HL, g.FCo = m.FCH, g.act_out = kUActNone;  // no activation between the last block and the output layer
       } else {
-        g.out_f32 = m.Hf[b + 1], g.ld_out = m.H;
+        g.out_f32 = m.Hf[b + 1], g.ld_out = m.H, g.out_mode = m.fmode;
         if (!m.ln) g.out_op = m.A[b + 1], g.FCo = m.FCH, g.act_out = m.act;
+        if (m.relu_bits) g.mask_out = m.MH[b + 1], g.mask_words = m.H / 32;
       }
       URUN(launch_row_gemm(g, sm, st));
       if (!last && m.ln)
@@ -389,7 +423,7 @@ static int resmlp_backward(const dppo_update* u, ResMlp& m, int R, bool need_dh0
   URUN(launch_wgrad(wgrad_args(m.GOUT, m.FCout, m.HL, m.FCH, m.out, R), sm, st));
   {
     RowGemmArgs g = gemm_args(m.GOUT, m.FCout, m.out, true, R);
-    g.out_f32 = m.DHf, g.ld_out = m.H;
+    g.out_f32 = m.DHf, g.ld_out = m.H, g.out_mode = m.fmode;
     g.out_op = m.DHop, g.FCo = m.FCH, g.act_out = kUActNone;
     URUN(launch_row_gemm(g, sm, st));
   }
@@ -398,10 +432,11 @@ static int resmlp_backward(const dppo_update* u, ResMlp& m, int R, bool need_dh0
     URUN(launch_wgrad(wgrad_args(m.DHop, m.FCH, m.A1[b], m.FCH, B.l2, R), sm, st));
     {
       RowGemmArgs g = gemm_args(m.DHop, m.FCH, B.l2, true, R);
-      g.pre = m.Yf[b], g.ld_pre = m.H, g.act_grad = m.act;
+      if (m.relu_bits) g.mask_in = m.MY[b], g.mask_words = m.H / 32;
+      else g.pre = m.Yf[b], g.ld_pre = m.H, g.pre_mode = m.fmode, g.act_grad = m.act;
       if (m.ln) {
         g.ln_stats = m.st2[b], g.ln_g = B.g2, g.ln_b = B.be2;
-        g.out_f32 = m.DZf, g.ld_out = m.H;
+        g.out_f32 = m.DZf, g.ld_out = m.H, g.out_mode = m.fmode;
       } else {
         g.out_op = m.G1op, g.FCo = m.FCH, g.act_out = kUActNone;
       }
@@ -412,13 +447,14 @@ static int resmlp_backward(const dppo_update* u, ResMlp& m, int R, bool need_dh0
     URUN(launch_wgrad(wgrad_args(m.G1op, m.FCH, m.A[b], m.FCH, B.l1, R), sm, st));
     {
       RowGemmArgs g = gemm_args(m.G1op, m.FCH, B.l1, true, R);
-      g.pre = m.Hf[b], g.ld_pre = m.H, g.act_grad = m.act;
+      if (m.relu_bits) g.mask_in = m.MH[b], g.mask_words = m.H / 32;
+      else g.pre = m.Hf[b], g.ld_pre = m.H, g.pre_mode = m.fmode, g.act_grad = m.act;
       if (m.ln) {
         g.ln_stats = m.st1[b], g.ln_g = B.g1, g.ln_b = B.be1;
-        g.out_f32 = m.DZf, g.ld_out = m.H;
+        g.out_f32 = m.DZf, g.ld_out = m.H, g.out_mode = m.fmode;
       } else {
-        g.res = m.DHf, g.ld_res = m.H;
-        g.out_f32 = m.DHf, g.ld_out = m.H;
+        g.res = m.DHf, g.ld_res = m.H, g.res_mode = m.fmode;
+        g.out_f32 = m.DHf, g.ld_out = m.H, g.out_mode = m.fmode;
         g.out_op = m.DHop, g.FCo = m.FCH, g.act_out = kUActNone;
       }
       URUN(launch_row_gemm(g, sm, st));
@@ -454,7 +490,10 @@ extern "C" int dppo_update_create(dppo_update** out, dppo_ctx* ctx, const dppo_r
       critic->in_dim != g.Dc_in)
     return set_error("dppo_update_create: critic geometry (%d -> %d x %d -> %d) unsupported", critic->in_dim, critic->hidden_dim,
                      critic->n_blocks, critic->out_dim), DPPO_ERR_UNSUPPORTED;
-  if (g.CH && (g.CO % 8)) return set_error("dppo_update_create: cond_mlp output %d must be a multiple of 8", g.CO), DPPO_ERR_UNSUPPORTED;
+  if (g.CH && (g.CO % 64 || g.CH % 64))
+    return set_error("dppo_update_create: cond_mlp widths (%d, %d) must be multiples of 64", g.CH, g.CO), DPPO_ERR_UNSUPPORTED;
+  if (g.H % 64 || critic->hidden_dim % 64)
+    return set_error("dppo_update_create: hidden widths (%d, %d) must be multiples of 64", g.H, critic->hidden_dim), DPPO_ERR_UNSUPPORTED;
   if (ctx->ft < 1 || ctx->ft > 128) return set_error("dppo_update_create: ft_denoising_steps %d", ctx->ft), DPPO_ERR_UNSUPPORTED;
   DPPO_CUDA(cudaSetDevice(ctx->device));
   dppo_update* u = new dppo_update();
@@ -480,6 +519,8 @@ extern "C" int dppo_update_create(dppo_update** out, dppo_ctx* ctx, const dppo_r
     UALLOC(u->TB, size_t(ctx->ft) * g.H * 4);
     UALLOC(u->t_dtemb, size_t(ctx->ft) * g.td * 4);
     UALLOC(u->t_dpre, size_t(ctx->ft) * 2 * g.td * 4);
+    UALLOC(u->t_hid, size_t(ctx->ft) * 2 * g.td * 4);
+    UALLOC(u->t_G, size_t(ctx->ft) * g.H * 4);
     // layer 0 runs on the assembled matrix; its wgrad lands in dW0p
     a.L0.W = u->W0p, a.L0.dW = u->dW0p, a.L0.N = g.H, a.L0.K = u->K0p, a.L0.ld = u->K0p;
     if (g.CH) a.L0.bd_rows = g.CO, a.L0.bd_col0 = 0;
@@ -500,7 +541,7 @@ extern "C" int dppo_update_create(dppo_update** out, dppo_ctx* ctx, const dppo_r
       u->c1.N = g.CO, u->c1.K = g.CH, u->c1.ld = g.CH;
       URUN(alloc_layer_tiles(u, u->c0, false));
       URUN(alloc_layer_tiles(u, u->c1, true));
-      UALLOC(u->YC0f, size_t(R) * g.CH * 4);
+      UALLOC(u->YC0f, f32_tiled_floats(R, g.CH) * 4);
       UALLOC(u->AC0, opmat_bytes(R, g.CH));
       UALLOC(u->GC1, opmat_bytes(R, g.CO));
       UALLOC(u->GC0, opmat_bytes(R, g.CH));
@@ -636,7 +677,7 @@ static int actor_forward(dppo_update* u, int R, float* eps_out, cudaStream_t st)
     {
       RowGemmArgs a = gemm_args(u->OBS, u->FCobs, u->c0, false, R);
       a.bias = u->c0.b;
-      a.out_f32 = u->YC0f, a.ld_out = g.CH;
+      a.out_f32 = u->YC0f, a.ld_out = g.CH, a.out_mode = 1;
       a.out_op = u->AC0, a.FCo = opmat_chunks(g.CH), a.act_out = u->actor.act;
       URUN(launch_row_gemm(a, u->sm_count, st));
     }
@@ -667,16 +708,18 @@ static int actor_backward(dppo_update* u, int R, cudaStream_t st) {
     URUN(launch_wgrad(wgrad_args(u->GC1, opmat_chunks(g.CO), u->AC0, opmat_chunks(g.CH), u->c1, R), u->sm_count, st));
     {
       RowGemmArgs a = gemm_args(u->GC1, opmat_chunks(g.CO), u->c1, true, R);
-      a.pre = u->YC0f, a.ld_pre = g.CH, a.act_grad = u->actor.act;
+      a.pre = u->YC0f, a.ld_pre = g.CH, a.pre_mode = 1, a.act_grad = u->actor.act;
       a.out_op = u->GC0, a.FCo = opmat_chunks(g.CH), a.act_out = kUActNone;
       URUN(launch_row_gemm(a, u->sm_count, st));
     }
     URUN(launch_wgrad(wgrad_args(u->GC0, opmat_chunks(g.CH), u->OBS, u->FCobs, u->c0, R), u->sm_count, st));
   }
   scatter_dw0_kernel<<<(g.H * (g.Dc + g.D) + 255) / 256, 256, 0, st>>>(u->dW0p, g.H, in0, g.D, g.td, g.Dc, u->K0p, u->dW0);
-  time_table_bwd_kernel<<<1, 256, 0, st>>>(u->dW0p, u->K0p, g.Dc + g.D, ctx->ft, g.H, g.td, g.D, in0, u->W0, u->tw2, u->t_emb,
-                                           u->t_hpre, u->t_temb, u->t_dtemb, u->t_dpre, u->dW0, u->db0, u->dtw1, u->dtb1,
-                                           u->dtw2, u->dtb2);
+  time_bwd_a_kernel<<<ctx->ft, 256, size_t(g.H) * 4, st>>>(u->dW0p, u->K0p, g.Dc + g.D, g.H, g.td, g.D, in0, u->W0, u->t_G,
+                                                           u->t_dtemb);
+  time_bwd_b_kernel<<<1, 256, 0, st>>>(ctx->ft, g.td, u->tw2, u->t_emb, u->t_hpre, u->t_dtemb, u->t_hid, u->t_dpre, u->dtw1,
+                                       u->dtb1, u->dtw2, u->dtb2);
+  time_bwd_c_kernel<<<(g.H + 127) / 128, 128, 0, st>>>(u->t_G, ctx->ft, g.H, g.td, g.D, in0, u->t_temb, u->dW0, u->db0);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "dppo_update actor backward");
 }
@@ -790,6 +833,60 @@ extern "C" int dppo_debug_linear(const float* x, int R, int K, const float* W, i
   if (rc == DPPO_OK && out_act_f32) rc = launch_unpack_rows(oi, opmat_chunks(N), R, N, out_act_f32, N, st);
   cudaStreamSynchronize(st);
   cudaFree(xi), cudaFree(bt), cudaFree(oi);
+  return rc;
+}
+
+// times `reps` launches of one row GEMM (R x K) . (N x K)^T on resident operands; flags: 1 = fp32 output (tiled),
+// 2 = operand-image output (ReLU; 64: no activation, 128: Mish), 4 = fp32 residual input (tiled), 8 = bit-mask output,
+// 16 = bias, 32 = bit-mask input, 256 = mish'(fp32 pre) input, 512 = force the generic epilogue.  prof (optional): [grid][16] role counters
+// of the last launch.  Returns the average milliseconds per launch in *ms.
+extern "C" int dppo_debug_gemm_bench(int R, int K, int N, int flags, int ntile_cap, int max_stages, int reps, float* ms,
+                                     unsigned long long* prof, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sm = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  set_row_gemm_tuning(ntile_cap, max_stages);
+  const int NTILE = row_gemm_ntile(N);
+  uint8_t *xi = nullptr, *bt = nullptr, *oi = nullptr;
+  float *of = nullptr, *rf = nullptr;
+  uint32_t* mk = nullptr;
+  DPPO_CUDA(cudaMalloc(&xi, opmat_bytes(R, K)));
+  DPPO_CUDA(cudaMalloc(&bt, packed_weight_bytes(N, K, NTILE)));
+  DPPO_CUDA(cudaMalloc(&oi, opmat_bytes(R, N)));
+  DPPO_CUDA(cudaMalloc(&of, f32_tiled_floats(R, N) * 4));
+  DPPO_CUDA(cudaMalloc(&rf, f32_tiled_floats(R, N) * 4));
+  DPPO_CUDA(cudaMalloc(&mk, mask_words_total(R, N) * 4));
+  DPPO_CUDA(cudaMemsetAsync(xi, 0, opmat_bytes(R, K), st));
+  DPPO_CUDA(cudaMemsetAsync(bt, 0, packed_weight_bytes(N, K, NTILE), st));
+  DPPO_CUDA(cudaMemsetAsync(rf, 0, f32_tiled_floats(R, N) * 4, st));
+  RowGemmArgs g{};
+  g.A = xi, g.FCa = opmat_chunks(K), g.B = bt, g.R = R, g.KC = (K + 63) / 64, g.N = N, g.NTILE = NTILE, g.NT = (N + NTILE - 1) / NTILE;
+  if (flags & 1) g.out_f32 = of, g.ld_out = N, g.out_mode = 1;
+  if (flags & 2) g.out_op = oi, g.FCo = opmat_chunks(N), g.act_out = (flags & 64) ? kUActNone : ((flags & 128) ? kUActMish : kUActRelu);
+  if (flags & 4) g.res = rf, g.ld_res = N, g.res_mode = 1;
+  if (flags & 8) g.mask_out = mk, g.mask_words = (N + 31) / 32;
+  if (flags & 16) g.bias = rf;
+  if (flags & 32) g.mask_in = mk, g.mask_words = (N + 31) / 32;
+  if (flags & 256) g.pre = rf, g.ld_pre = N, g.pre_mode = 1, g.act_grad = kUActMish;
+  set_row_gemm_fast_epilogue(!(flags & 512));
+  int rc = launch_row_gemm(g, sm, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < reps && rc == DPPO_OK; ++i) {
+    g.prof = (i == reps - 1) ? prof : nullptr;
+    rc = launch_row_gemm(g, sm, st);
+  }
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float t = 0.f;
+  cudaEventElapsedTime(&t, e0, e1);
+  if (ms) *ms = t / reps;
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(xi), cudaFree(bt), cudaFree(oi), cudaFree(of), cudaFree(rf), cudaFree(mk);
+  set_row_gemm_tuning(0, 0);
+  set_row_gemm_fast_epilogue(true);
   return rc;
 }
 

@@ -67,8 +67,10 @@ class PPODiffusion(VPGDiffusion):
             adv = (adv - adv.mean()) / (adv.std() + 1e-8)
         return float(torch.quantile(adv, lo_q)), float(torch.quantile(adv, hi_q))
 
+    bc_noise = None  # test hook: (S+1, B, Ta, Da) draws injected into the BC branch's sampling call (parity tests)
+
     def _bc_loss(self, obs):
-        samples = self.forward(cond=obs, deterministic=False, return_chain=True, use_base_policy=True)
+        samples = self.forward(cond=obs, deterministic=False, return_chain=True, use_base_policy=True, noise=self.bc_noise)
         bc = self.get_logprobs(obs, samples.chains, get_ent=False, use_base_policy=False)
         return -bc.clamp(min=-5, max=2).mean(dim=(-1, -2)).view(-1).mean()
 

@@ -23,6 +23,16 @@ GOLDEN_CASES = {
     "square_unet": dict(workload="square_unet", n_envs=40, mb_rows=128),
 }
 
+# optional branches of the hot path (tests/golden/make_golden_variants.py): base workload + constructor overrides
+VARIANTS = {
+    "bc": dict(base="hopper", ppo={}, n_envs=24, mb_rows=64, use_bc_loss=True, bc_coeff=0.1),
+    "vclip_quant": dict(base="hopper", n_envs=24, mb_rows=96,
+                        ppo=dict(clip_vloss_coef=0.2, clip_advantage_lower_quantile=0.05, clip_advantage_upper_quantile=0.95)),
+    "epsclip": dict(base="furniture", ppo=dict(eps_clip_value=0.3), n_envs=16, mb_rows=48),
+    "finalclip": dict(base="hopper", ppo=dict(final_action_clip_value=0.5), n_envs=24, mb_rows=64, loss=False),
+    "anneal": dict(base="hopper", ppo=dict(ft_denoising_steps_d=3, ft_denoising_steps_t=1), n_envs=24, mb_rows=32, anneal=True),
+}
+
 WEIGHT_SEED = 42
 PERTURB_SEED = 1234
 PERTURB_SCALE = 1e-2
@@ -58,10 +68,25 @@ def build_model(w, device, classes, perturb=True):
     return model
 
 
-def make_inputs(w, n_envs, mb_rows, seed=0):
+def variant_workload(name):
+    spec = VARIANTS[name]
+    w = get_workload(spec["base"])
+    w["ppo"] = dict(w["ppo"], **spec["ppo"])
+    return w
+
+
+def perturb_again(model, seed=4321):
+    """Second perturbation of actor_ft (after VPGDiffusion.step() made it a copy of the new base policy)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.actor_ft.parameters():
+            p.add_((PERTURB_SCALE * torch.randn(p.shape, generator=g)).to(p.device))
+
+
+def make_inputs(w, n_envs, mb_rows, seed=0, ft=None):
     """Seeded synthetic observations U(-1,1), injected noise (S+1,E,Ta,Da), and one PPO minibatch worth of scalars."""
     rng = np.random.default_rng(seed)
-    S, ft = chain_evals(w), w["ft_denoising_steps"]
+    S, ft = chain_evals(w), (w["ft_denoising_steps"] if ft is None else ft)
     state = torch.from_numpy(rng.uniform(-1, 1, (n_envs, w["cond_steps"], w["obs_dim"])).astype(np.float32))
     noise = torch.from_numpy(rng.standard_normal((S + 1, n_envs, w["horizon_steps"], w["action_dim"])).astype(np.float32))
     noise[1:] *= 1.5  # make the +-randn_clip clamp bite on some elements
