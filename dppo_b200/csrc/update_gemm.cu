@@ -233,17 +233,23 @@ __device__ __forceinline__ void rows_epilogue(const RowGemmArgs& a, uint32_t tme
 }
 
 
+__device__ __forceinline__ bool row_valid(const RowGemmArgs& a, int rt, int warp, int lane) {
+  return rt * 128 + (warp & 3) * 32 + lane < a.R;
+}
+
 // ---------------------------------------------------------------------------------------------- specialised epilogue
 // The epilogue is instruction-issue bound (8 warps on 4 schedulers, 32 accumulator values per thread and chunk): the
 // generic version above spends ~2.5 k cycles per 64-column chunk on run-time flag checks alone (role counters in
 // profiles/r2).  The variants the update program actually launches are therefore compiled as straight-line code:
 //   V & 1        bias            (V >> 1) & 3   0 none | 1 ReLU bit mask in | 2 relu'(pre) | 3 mish'(pre)   (pre: tiled fp32)
 //   (V >> 3) & 1 residual in     (V >> 4) & 1   fp32 out (tiled)       (V >> 5) & 3   activation of the operand output
-//   (V >> 7) & 1 bit mask out
-// Preconditions (checked by the launcher): NTILE and N multiples of 64, operand output present, side tensors tiled.
+//   (V >> 7) & 1 bit mask out    (V >> 8) & 1   operand-image output   (V >> 9) & 1   pre goes through LayerNorm first
+// Preconditions (checked by the launcher): NTILE and N multiples of 64, side tensors tiled.
 constexpr int kEpiGeneric = -1;
-constexpr int epi_variant(bool bias, int pre, bool res, bool outf, int acto, bool masko) {
-  return (bias ? 1 : 0) | (pre << 1) | ((res ? 1 : 0) << 3) | ((outf ? 1 : 0) << 4) | (acto << 5) | ((masko ? 1 : 0) << 7);
+constexpr int epi_variant(bool bias, int pre, bool res, bool outf, int acto, bool masko, bool outop = true, bool ln = false,
+                          bool stats = false) {
+  return (bias ? 1 : 0) | (pre << 1) | ((res ? 1 : 0) << 3) | ((outf ? 1 : 0) << 4) | (acto << 5) | ((masko ? 1 : 0) << 7) |
+         ((outop ? 1 : 0) << 8) | ((ln ? 1 : 0) << 9) | ((stats ? 1 : 0) << 10);
 }
 
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
@@ -262,8 +268,14 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 template <int V>
 __device__ __forceinline__ void rows_epilogue_fast(const RowGemmArgs& a, uint32_t tmem_d, int rt, int nt, int warp, int lane,
                                                    uint8_t* stage) {
-  constexpr bool BIAS = V & 1, RES = (V >> 3) & 1, OUTF = (V >> 4) & 1, MASKO = (V >> 7) & 1;
+  constexpr bool BIAS = V & 1, RES = (V >> 3) & 1, OUTF = (V >> 4) & 1, MASKO = (V >> 7) & 1, OUTOP = (V >> 8) & 1, LN = (V >> 9) & 1;
+  constexpr bool STATS = (V >> 10) & 1;
   constexpr int PRE = (V >> 1) & 3, ACTO = (V >> 5) & 3;
+  float mean = 0.f, rstd = 1.f;
+  if (LN && row_valid(a, rt, warp, lane)) {
+    const int row_ = rt * 128 + (warp & 3) * 32 + lane;
+    mean = a.ln_stats[2 * size_t(row_)], rstd = a.ln_stats[2 * size_t(row_) + 1];
+  }
   const int q = warp & 3, half = (warp - 2) >> 2;
   const uint32_t rloc = uint32_t(q * 32 + lane);
   const int row = rt * 128 + int(rloc);
@@ -309,6 +321,7 @@ __device__ __forceinline__ void rows_epilogue_fast(const RowGemmArgs& a, uint32_
       }
     }
     uint32_t mout = 0;
+    float st1 = 0.f, st2 = 0.f;
     if (valid) {
       if (PRE == 1) {
 #pragma unroll
@@ -316,14 +329,37 @@ __device__ __forceinline__ void rows_epilogue_fast(const RowGemmArgs& a, uint32_
       } else if (PRE >= 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float p4[4] = {pr[j].x, pr[j].y, pr[j].z, pr[j].w};
+          float p4[4] = {pr[j].x, pr[j].y, pr[j].z, pr[j].w};
+          float xh[4] = {0.f, 0.f, 0.f, 0.f}, gm[4] = {0.f, 0.f, 0.f, 0.f};
+          if (LN) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_g + n0) + j);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + n0) + j);
+            gm[0] = g4.x, gm[1] = g4.y, gm[2] = g4.z, gm[3] = g4.w;
+            const float bt[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[4 * j + i] = PRE == 2 ? (p4[i] > 0.f ? x[4 * j + i] : 0.f) : x[4 * j + i] * mish_grad_f(p4[i]);
+            for (int i = 0; i < 4; ++i) xh[i] = (p4[i] - mean) * rstd, p4[i] = xh[i] * gm[i] + bt[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x[4 * j + i] = PRE == 2 ? (p4[i] > 0.f ? x[4 * j + i] : 0.f) : x[4 * j + i] * mish_grad_f(p4[i]);
+            if (LN && STATS) {
+              const float d = x[4 * j + i] * gm[i];
+              st1 += d, st2 += d * xh[i];
+            }
+          }
         }
       }
       if (RES) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[4 * j] += rs[j].x, x[4 * j + 1] += rs[j].y, x[4 * j + 2] += rs[j].z, x[4 * j + 3] += rs[j].w;
+      }
+      if (STATS && !LN) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) st1 += x[i], st2 += x[i] * x[i];
+      }
+      if (STATS) {
+        atomicAdd(a.stat_out + 2 * size_t(row), st1);
+        atomicAdd(a.stat_out + 2 * size_t(row) + 1, st2);
       }
       if (OUTF) {
 #pragma unroll
@@ -343,18 +379,20 @@ __device__ __forceinline__ void rows_epilogue_fast(const RowGemmArgs& a, uint32_
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = 0.f;
     }
+    if (OUTOP) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float y[8] = {x[8 * g], x[8 * g + 1], x[8 * g + 2], x[8 * g + 3], x[8 * g + 4], x[8 * g + 5], x[8 * g + 6], x[8 * g + 7]};
-      store_op8(stage, rloc, uint32_t(half * 32 + g * 8), y);
+      for (int g = 0; g < 4; ++g) {
+        const float y[8] = {x[8 * g], x[8 * g + 1], x[8 * g + 2], x[8 * g + 3], x[8 * g + 4], x[8 * g + 5], x[8 * g + 6], x[8 * g + 7]};
+        store_op8(stage, rloc, uint32_t(half * 32 + g * 8), y);
+      }
+      named_bar_sync(1, kUEpiThreads);
+      const int fc = ((a.op_col0 + nt * a.NTILE) >> 6) + cc;
+      uint4* dst = reinterpret_cast<uint4*>(a.out_op + (size_t(rt) * a.FCo + fc) * 2 * kImg);
+      const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[et + i * kUEpiThreads] = src[et + i * kUEpiThreads];
+      named_bar_sync(1, kUEpiThreads);
     }
-    named_bar_sync(1, kUEpiThreads);
-    const int fc = ((a.op_col0 + nt * a.NTILE) >> 6) + cc;
-    uint4* dst = reinterpret_cast<uint4*>(a.out_op + (size_t(rt) * a.FCo + fc) * 2 * kImg);
-    const uint4* src = reinterpret_cast<const uint4*>(stage);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dst[et + i * kUEpiThreads] = src[et + i * kUEpiThreads];
-    named_bar_sync(1, kUEpiThreads);
   }
 }
 
@@ -867,6 +905,140 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
+// ---------------------------------------------------------------------------------------------- LayerNorm, tiled fp32
+// One CTA of 256 threads per 128-row tile of a tiled fp32 tensor [row tile][F / 8][128][8]: thread = (row, half).  Every
+// global access of a warp is 1 KiB contiguous.  Pass 1: row statistics (shifted sums), pass 2: normalise + activation +
+// bf16 hi/lo split, operand images assembled in shared memory and copied out coalesced (like the GEMM epilogue).
+__global__ void __launch_bounds__(256) ln_fwd_tiled_kernel(const float* __restrict__ x, const float* __restrict__ sums, int R,
+                                                           int F, const float* __restrict__ g, const float* __restrict__ b,
+                                                           float eps, int act, float* __restrict__ stats,
+                                                           uint8_t* __restrict__ out_op, int FCo) {
+  extern __shared__ __align__(1024) uint8_t ln_smem[];
+  uint8_t* stage = ln_smem;  // 32 KiB
+  const int rt = blockIdx.x, t = threadIdx.x, r = t & 127, half = t >> 7;
+  const int row = rt * 128 + r;
+  const bool valid = row < R;
+  const int G = F >> 3;
+  const float* base = x + (size_t(rt) * G * 128 + r) * 8;  // group gi at + gi * 1024 floats
+  float mean = 0.f, rstd = 0.f;
+  if (valid) {
+    const float t1 = sums[2 * size_t(row)] / float(F), t2 = sums[2 * size_t(row) + 1] / float(F);
+    mean = t1;
+    rstd = rsqrtf(fmaxf(t2 - t1 * t1, 0.f) + eps);
+    if (half == 0 && blockIdx.y == 0) stats[2 * size_t(row)] = mean, stats[2 * size_t(row) + 1] = rstd;
+  }
+  const int ncc = F >> 6, per = (ncc + gridDim.y - 1) / gridDim.y;
+  const int cc_end = min(ncc, int(blockIdx.y + 1) * per);
+  for (int cc = blockIdx.y * per; cc < cc_end; ++cc) {
+    const int n0 = cc * 64 + half * 32;
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      float y[8];
+      if (valid) {
+        const float* p = base + size_t((n0 >> 3) + gq) * 1024;
+        const float4 a0 = *reinterpret_cast<const float4*>(p), a1 = *reinterpret_cast<const float4*>(p + 4);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + n0 + gq * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + n0 + gq * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + n0 + gq * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + n0 + gq * 8 + 4));
+        const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = act_apply(act, (v[i] - mean) * rstd * gg[i] + bb[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = 0.f;
+      }
+      store_op8(stage, uint32_t(r), uint32_t(half * 32 + gq * 8), y);
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out_op + (size_t(rt) * FCo + cc) * 2 * kImg);
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[t + i * 256] = src[t + i * 256];
+    __syncthreads();
+  }
+}
+
+// dz (tiled) = gradient w.r.t. z = xhat g + b; dx = rstd (dz g - mean(dz g) - xhat mean(dz g xhat)) [+ res] -> fp32 (tiled,
+// optional) and operand images; dg += sum_r dz xhat, db += sum_r dz (column sums over the tile through shared memory).
+__global__ void __launch_bounds__(256) ln_bwd_tiled_kernel(const float* __restrict__ dz, const float* __restrict__ sums,
+                                                           const float* __restrict__ x,
+                                                           const float* __restrict__ stats, const float* __restrict__ g, int R,
+                                                           int F, const float* __restrict__ res, float* __restrict__ out_f32,
+                                                           uint8_t* __restrict__ out_op, int FCo, float* __restrict__ dg,
+                                                           float* __restrict__ db) {
+  extern __shared__ __align__(1024) uint8_t ln_smem[];
+  uint8_t* stage = ln_smem;                                       // 32 KiB operand images of one chunk
+  float* s_p = reinterpret_cast<float*>(ln_smem + 2 * kImg);      // [128][65] dz * xhat
+  float* s_z = s_p + 128 * 65;                                    // [128][65] dz
+  const int rt = blockIdx.x, t = threadIdx.x, r = t & 127, half = t >> 7;
+  const int row = rt * 128 + r;
+  const bool valid = row < R;
+  const int G = F >> 3;
+  const size_t tbase = (size_t(rt) * G * 128 + r) * 8;
+  float mean = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
+  if (valid) {
+    mean = stats[2 * size_t(row)], rstd = stats[2 * size_t(row) + 1];
+    m1 = sums[2 * size_t(row)] / float(F), m2 = sums[2 * size_t(row) + 1] / float(F);
+  }
+  const int ncc = F >> 6, per = (ncc + gridDim.y - 1) / gridDim.y;
+  const int cc_end = min(ncc, int(blockIdx.y + 1) * per);
+  for (int cc = blockIdx.y * per; cc < cc_end; ++cc) {
+    const int n0 = cc * 64 + half * 32;
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      float y[8], pz8[8], zz8[8];
+      const size_t off = tbase + size_t((n0 >> 3) + gq) * 1024;
+      if (valid) {
+        const float4 z0 = *reinterpret_cast<const float4*>(dz + off), z1 = *reinterpret_cast<const float4*>(dz + off + 4);
+        const float4 x0 = *reinterpret_cast<const float4*>(x + off), x1 = *reinterpret_cast<const float4*>(x + off + 4);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + n0 + gq * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + n0 + gq * 8 + 4));
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = (xx[i] - mean) * rstd;
+          y[i] = rstd * (zz[i] * gg[i] - m1 - h * m2);
+          pz8[i] = zz[i] * h, zz8[i] = zz[i];
+        }
+        if (res) {
+          const float4 r0 = *reinterpret_cast<const float4*>(res + off), r1 = *reinterpret_cast<const float4*>(res + off + 4);
+          y[0] += r0.x, y[1] += r0.y, y[2] += r0.z, y[3] += r0.w, y[4] += r1.x, y[5] += r1.y, y[6] += r1.z, y[7] += r1.w;
+        }
+        if (out_f32) {
+          *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(out_f32 + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = 0.f, pz8[i] = 0.f, zz8[i] = 0.f;
+      }
+      store_op8(stage, uint32_t(r), uint32_t(half * 32 + gq * 8), y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s_p[r * 65 + half * 32 + gq * 8 + i] = pz8[i];
+        s_z[r * 65 + half * 32 + gq * 8 + i] = zz8[i];
+      }
+    }
+    __syncthreads();
+    {
+      uint4* dst = reinterpret_cast<uint4*>(out_op + (size_t(rt) * FCo + cc) * 2 * kImg);
+      const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[t + i * 256] = src[t + i * 256];
+      if (t < 128) {  // column sums of this chunk: thread = (which array, column)
+        const float* sp = (t < 64 ? s_p : s_z) + (t & 63);
+        float acc = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 128; ++rr) acc += sp[rr * 65];
+        atomicAdd((t < 64 ? dg : db) + cc * 64 + (t & 63), acc);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ============================================================================================== launchers
 static int g_ntile_cap = 256, g_max_stages = 0;
 static bool g_fast_epilogue = true;
@@ -935,15 +1107,20 @@ int launch_row_gemm(const RowGemmArgs& a0, int sm_count, cudaStream_t st) {
     return set_error("row gemm: tiled fp32 tensors need a feature count that is a multiple of 8"), DPPO_ERR_INVALID;
   // straight-line epilogue variants (see rows_epilogue_fast); anything else runs the generic epilogue
   int variant = kEpiGeneric;
-  const bool fast_ok = a.out_op && a.NTILE % 64 == 0 && a.N % 64 == 0 && a.N == a.NT * a.NTILE && !a.ln_stats && g_fast_epilogue &&
+  const bool fast_ok = a.NTILE % 64 == 0 && a.N % 64 == 0 && a.N == a.NT * a.NTILE && g_fast_epilogue &&
+                       (!a.ln_stats || ((reinterpret_cast<uintptr_t>(a.ln_g) | reinterpret_cast<uintptr_t>(a.ln_b)) & 15) == 0) &&
                        (!a.pre || a.pre_mode == 1) && (!a.res || a.res_mode == 1) && (!a.out_f32 || a.out_mode == 1) &&
                        (!a.pre || a.ld_pre == a.N) && (!a.res || a.ld_res == a.N) && (!a.out_f32 || a.ld_out == a.N) &&
                        (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) && !(a.pre && a.mask_in) &&
                        (!(a.mask_in || a.mask_out) || a.mask_words * 32 == a.N);
   if (fast_ok) {
     const int pre = a.mask_in ? 1 : (a.pre ? (a.act_grad == kUActRelu ? 2 : (a.act_grad == kUActMish ? 3 : -1)) : 0);
-    if (pre >= 0) variant = epi_variant(a.bias != nullptr, pre, a.res != nullptr, a.out_f32 != nullptr, a.act_out, a.mask_out != nullptr);
+    if (pre >= 0 && !(a.ln_stats && pre != 3))
+      variant = epi_variant(a.bias != nullptr, pre, a.res != nullptr, a.out_f32 != nullptr, a.out_op ? a.act_out : 0, a.mask_out != nullptr,
+                            a.out_op != nullptr, a.ln_stats != nullptr, a.stat_out != nullptr);
   }
+  if (a.stat_out && (variant == kEpiGeneric || !((variant >> 10) & 1)))
+    return set_error("row gemm: row statistics are only produced by the specialised epilogue variants"), DPPO_ERR_UNSUPPORTED;
   void (*kfn)(const RowGemmArgs) = nullptr;
   switch (variant) {
 #define DPPO_EPI_CASE(...)                        \
@@ -966,6 +1143,11 @@ int launch_row_gemm(const RowGemmArgs& a0, int sm_count, cudaStream_t st) {
     DPPO_EPI_CASE(false, 3, true, true, kUActNone, false)    // dgrad l1, Mish
     DPPO_EPI_CASE(false, 2, false, false, kUActNone, false)  // dgrad with relu'(fp32 pre)
     DPPO_EPI_CASE(false, 2, true, true, kUActNone, false)
+    // LayerNorm nets: the GEMMs exchange fp32 tensors with the LayerNorm kernels, no operand output
+    DPPO_EPI_CASE(false, 0, false, true, kUActNone, false, false, false, true)  // layer 0 -> h0 (+ row sums)
+    DPPO_EPI_CASE(true, 0, false, true, kUActNone, false, false, false, true)   // l1 -> y
+    DPPO_EPI_CASE(true, 0, true, true, kUActNone, false, false, false, true)    // l2 -> h + ...
+    DPPO_EPI_CASE(false, 3, false, true, kUActNone, false, false, true, true)   // dgrad -> dz = (g W) mish'(LN(pre))
 #undef DPPO_EPI_CASE
     default:
       variant = kEpiGeneric;
@@ -1036,6 +1218,35 @@ int launch_ln_fwd(const float* x, int ld, int R, int F, const float* g, const fl
   ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, ld, R, F, g, b, eps, act, stats, out_op, FCo);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ln_fwd_kernel launch");
+}
+
+int launch_ln_fwd_tiled(const float* x, const float* sums, int R, int F, const float* g, const float* b, float eps, int act,
+                        float* stats, uint8_t* out_op, int FCo, cudaStream_t st) {
+  if (F % 64 || F < 64 || ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15))
+    return set_error("ln_fwd_tiled: F=%d unsupported or unaligned parameters", F), DPPO_ERR_INVALID;
+  if (R <= 0) return DPPO_OK;
+  const int split = (F >> 6) >= 8 ? 4 : ((F >> 6) >= 2 ? 2 : 1);  // column ranges per row tile: more CTAs, more bytes in flight
+  ln_fwd_tiled_kernel<<<dim3((R + 127) / 128, split), 256, 2 * kImg, st>>>(x, sums, R, F, g, b, eps, act, stats, out_op, FCo);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ln_fwd_tiled_kernel launch");
+}
+
+int launch_ln_bwd_tiled(const float* dz, const float* sums, const float* x, const float* stats, const float* g, int R, int F,
+                        const float* res, float* out_f32, uint8_t* out_op, int FCo, float* dg, float* db, cudaStream_t st) {
+  if (F % 64 || F < 64 || (reinterpret_cast<uintptr_t>(g) & 15))
+    return set_error("ln_bwd_tiled: F=%d unsupported or unaligned parameters", F), DPPO_ERR_INVALID;
+  if (R <= 0) return DPPO_OK;
+  const size_t smem = 2 * kImg + 2 * 128 * 65 * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ln_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ln_bwd_tiled_kernel)");
+    configured = true;
+  }
+  const int split = (F >> 6) >= 8 ? 4 : ((F >> 6) >= 2 ? 2 : 1);
+  ln_bwd_tiled_kernel<<<dim3((R + 127) / 128, split), 256, smem, st>>>(dz, sums, x, stats, g, R, F, res, out_f32, out_op, FCo, dg, db);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ln_bwd_tiled_kernel launch");
 }
 
 int launch_ln_bwd(const float* dz, int ld_dz, const float* x, int ld_x, const float* stats, const float* g, int R, int F,

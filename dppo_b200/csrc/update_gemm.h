@@ -53,6 +53,8 @@ struct RowGemmArgs {
   int ld_out, out_mode;
   uint8_t* out_op;    // operand images of act_out(v) or null, feature n lands at column op_col0 + n
   int FCo, op_col0, act_out;
+  float* stat_out;    // [R][2] or null, accumulated with atomics (the caller zeroes it): (sum v, sum v^2) of the fp32 output
+                      // row; with ln_stats set: (sum dz g, sum dz g xhat) of the LayerNorm backward
   uint32_t* mask_out; // bit (n % 32) of word [row tile][n / 32][row] = (v > 0), or null
   int mask_words;     // 32-feature words per row of the mask tensors
   int nstage;
@@ -130,5 +132,12 @@ int launch_ln_fwd(const float* x, int ld, int R, int F, const float* g, const fl
 int launch_ln_bwd(const float* dz, int ld_dz, const float* x, int ld_x, const float* stats, const float* g, int R, int F,
                   const float* res, int ld_res, float* out_f32, int ld_out, uint8_t* out_op, int FCo, float* dg, float* db,
                   int sm_count, cudaStream_t st);
+
+// the same two on tiled fp32 tensors (update_gemm.h, RowGemmArgs): one CTA per 128-row tile, coalesced throughout
+// `sums`: [R][2] row sums accumulated by the producing GEMM's epilogue (RowGemmArgs.stat_out)
+int launch_ln_fwd_tiled(const float* x, const float* sums, int R, int F, const float* g, const float* b, float eps, int act,
+                        float* stats, uint8_t* out_op, int FCo, cudaStream_t st);
+int launch_ln_bwd_tiled(const float* dz, const float* sums, const float* x, const float* stats, const float* g, int R, int F,
+                        const float* res, float* out_f32, uint8_t* out_op, int FCo, float* dg, float* db, cudaStream_t st);
 
 }  // namespace dppo

@@ -55,7 +55,10 @@ struct ResMlp {
   bool own_x0 = true;
   std::vector<float*> Hf, Yf;       // fp32 pre-activations h_b (block inputs), y_b (l1 outputs)
   std::vector<uint8_t*> A, A1;      // operand images act(norm(h_b)), act(norm(y_b))
-  std::vector<float*> st1, st2;     // LayerNorm statistics
+  std::vector<float*> st1, st2;     // LayerNorm statistics (mean, rstd) of h_b, y_b
+  std::vector<float*> sf1, sf2, sb1, sb2;  // row sums accumulated by the GEMM epilogues (forward: of h_b / y_b, backward: of dz)
+  float* stat_arena = nullptr;      // sf* / sb* live here, zeroed once per minibatch
+  size_t stat_arena_bytes = 0;
   std::vector<uint32_t*> MH, MY;    // ReLU nets: (h_b > 0), (y_b > 0) as bit masks instead of the fp32 pre-activations
   int fmode = 1;                    // layout of the fp32 side tensors: 1 = tiled (update_gemm.h), 0 = row-major (LayerNorm nets)
   bool relu_bits = false;
@@ -127,7 +130,7 @@ static int alloc_resmlp(dppo_update* u, ResMlp& m, int R) {
   m.Hf.assign(m.nb, nullptr), m.Yf.assign(m.nb, nullptr), m.A.assign(m.nb, nullptr), m.A1.assign(m.nb, nullptr);
   m.st1.assign(m.nb, nullptr), m.st2.assign(m.nb, nullptr);
   m.MH.assign(m.nb, nullptr), m.MY.assign(m.nb, nullptr);
-  m.fmode = m.ln ? 0 : 1;
+  m.fmode = 1;
   m.relu_bits = !m.ln && m.act == kUActRelu && m.H % 32 == 0;
   const size_t fbytes = f32_tiled_floats(R, m.H) * 4;
   for (int b = 0; b < m.nb; ++b) {
@@ -143,6 +146,15 @@ static int alloc_resmlp(dppo_update* u, ResMlp& m, int R) {
     if (m.ln) {
       UALLOC(m.st1[b], size_t(R) * 8);
       UALLOC(m.st2[b], size_t(R) * 8);
+    }
+  }
+  m.sf1.assign(m.nb, nullptr), m.sf2.assign(m.nb, nullptr), m.sb1.assign(m.nb, nullptr), m.sb2.assign(m.nb, nullptr);
+  if (m.ln) {
+    m.stat_arena_bytes = size_t(4) * m.nb * R * 8;
+    UALLOC(m.stat_arena, m.stat_arena_bytes);
+    for (int b = 0; b < m.nb; ++b) {
+      m.sf1[b] = m.stat_arena + (size_t(4) * b + 0) * R * 2, m.sf2[b] = m.stat_arena + (size_t(4) * b + 1) * R * 2;
+      m.sb1[b] = m.stat_arena + (size_t(4) * b + 2) * R * 2, m.sb2[b] = m.stat_arena + (size_t(4) * b + 3) * R * 2;
     }
   }
   UALLOC(m.HL, opmat_bytes(R, m.H));
@@ -370,14 +382,16 @@ static WgradArgs wgrad_args(const uint8_t* G, int FCg, const uint8_t* X, int FCx
 static int resmlp_forward(const dppo_update* u, ResMlp& m, int R, float* out_override, cudaStream_t st) {
   const int sm = u->sm_count;
   const float eps = 1e-6f;
+  if (m.ln) DPPO_CUDA(cudaMemsetAsync(m.stat_arena, 0, m.stat_arena_bytes, st));
   {
     RowGemmArgs g = gemm_args(m.X0, m.FC0, m.L0, false, R);
     g.bias = m.L0.b;
     g.out_f32 = m.Hf[0], g.ld_out = m.H, g.out_mode = m.fmode;
     if (!m.ln) g.out_op = m.A[0], g.FCo = m.FCH, g.act_out = m.act;
     if (m.relu_bits) g.mask_out = m.MH[0], g.mask_words = m.H / 32;
+    if (m.ln) g.stat_out = m.sf1[0];
     URUN(launch_row_gemm(g, sm, st));
-    if (m.ln) URUN(launch_ln_fwd(m.Hf[0], m.H, R, m.H, m.blk[0].g1, m.blk[0].be1, eps, m.act, m.st1[0], m.A[0], m.FCH, st));
+    if (m.ln) URUN(launch_ln_fwd_tiled(m.Hf[0], m.sf1[0], R, m.H, m.blk[0].g1, m.blk[0].be1, eps, m.act, m.st1[0], m.A[0], m.FCH, st));
   }
   for (int b = 0; b < m.nb; ++b) {
     const BlockW& B = m.blk[b];
@@ -387,8 +401,9 @@ static int resmlp_forward(const dppo_update* u, ResMlp& m, int R, float* out_ove
       if (m.relu_bits) g.mask_out = m.MY[b], g.mask_words = m.H / 32;
       else g.out_f32 = m.Yf[b], g.ld_out = m.H, g.out_mode = m.fmode;
       if (!m.ln) g.out_op = m.A1[b], g.FCo = m.FCH, g.act_out = m.act;
+      if (m.ln) g.stat_out = m.sf2[b];
       URUN(launch_row_gemm(g, sm, st));
-      if (m.ln) URUN(launch_ln_fwd(m.Yf[b], m.H, R, m.H, B.g2, B.be2, eps, m.act, m.st2[b], m.A1[b], m.FCH, st));
+      if (m.ln) URUN(launch_ln_fwd_tiled(m.Yf[b], m.sf2[b], R, m.H, B.g2, B.be2, eps, m.act, m.st2[b], m.A1[b], m.FCH, st));
     }
     {
       const bool last = b + 1 == m.nb;
@@ -401,10 +416,11 @@ static int resmlp_forward(const dppo_update* u, ResMlp& m, int R, float* out_ove
         g.out_f32 = m.Hf[b + 1], g.ld_out = m.H, g.out_mode = m.fmode;
         if (!m.ln) g.out_op = m.A[b + 1], g.FCo = m.FCH, g.act_out = m.act;
         if (m.relu_bits) g.mask_out = m.MH[b + 1], g.mask_words = m.H / 32;
+        if (m.ln) g.stat_out = m.sf1[b + 1];
       }
       URUN(launch_row_gemm(g, sm, st));
       if (!last && m.ln)
-        URUN(launch_ln_fwd(m.Hf[b + 1], m.H, R, m.H, m.blk[b + 1].g1, m.blk[b + 1].be1, eps, m.act, m.st1[b + 1], m.A[b + 1], m.FCH, st));
+        URUN(launch_ln_fwd_tiled(m.Hf[b + 1], m.sf1[b + 1], R, m.H, m.blk[b + 1].g1, m.blk[b + 1].be1, eps, m.act, m.st1[b + 1], m.A[b + 1], m.FCH, st));
     }
   }
   {
@@ -436,13 +452,13 @@ static int resmlp_backward(const dppo_update* u, ResMlp& m, int R, bool need_dh0
       else g.pre = m.Yf[b], g.ld_pre = m.H, g.pre_mode = m.fmode, g.act_grad = m.act;
       if (m.ln) {
         g.ln_stats = m.st2[b], g.ln_g = B.g2, g.ln_b = B.be2;
-        g.out_f32 = m.DZf, g.ld_out = m.H, g.out_mode = m.fmode;
+        g.out_f32 = m.DZf, g.ld_out = m.H, g.out_mode = m.fmode, g.stat_out = m.sb2[b];
       } else {
         g.out_op = m.G1op, g.FCo = m.FCH, g.act_out = kUActNone;
       }
       URUN(launch_row_gemm(g, sm, st));
       if (m.ln)
-        URUN(launch_ln_bwd(m.DZf, m.H, m.Yf[b], m.H, m.st2[b], B.g2, R, m.H, nullptr, 0, nullptr, 0, m.G1op, m.FCH, B.dg2, B.dbe2, sm, st));
+        URUN(launch_ln_bwd_tiled(m.DZf, m.sb2[b], m.Yf[b], m.st2[b], B.g2, R, m.H, nullptr, nullptr, m.G1op, m.FCH, B.dg2, B.dbe2, st));
     }
     URUN(launch_wgrad(wgrad_args(m.G1op, m.FCH, m.A[b], m.FCH, B.l1, R), sm, st));
     {
@@ -451,7 +467,7 @@ static int resmlp_backward(const dppo_update* u, ResMlp& m, int R, bool need_dh0
       else g.pre = m.Hf[b], g.ld_pre = m.H, g.pre_mode = m.fmode, g.act_grad = m.act;
       if (m.ln) {
         g.ln_stats = m.st1[b], g.ln_g = B.g1, g.ln_b = B.be1;
-        g.out_f32 = m.DZf, g.ld_out = m.H, g.out_mode = m.fmode;
+        g.out_f32 = m.DZf, g.ld_out = m.H, g.out_mode = m.fmode, g.stat_out = m.sb1[b];
       } else {
         g.res = m.DHf, g.ld_res = m.H, g.res_mode = m.fmode;
         g.out_f32 = m.DHf, g.ld_out = m.H, g.out_mode = m.fmode;
@@ -459,7 +475,7 @@ static int resmlp_backward(const dppo_update* u, ResMlp& m, int R, bool need_dh0
       }
       URUN(launch_row_gemm(g, sm, st));
       if (m.ln)
-        URUN(launch_ln_bwd(m.DZf, m.H, m.Hf[b], m.H, m.st1[b], B.g1, R, m.H, m.DHf, m.H, m.DHf, m.H, m.DHop, m.FCH, B.dg1, B.dbe1, sm, st));
+        URUN(launch_ln_bwd_tiled(m.DZf, m.sb1[b], m.Hf[b], m.st1[b], B.g1, R, m.H, m.DHf, m.DHf, m.DHop, m.FCH, B.dg1, B.dbe1, st));
     }
   }
   URUN(launch_wgrad(wgrad_args(m.DHop, m.FCH, m.X0, m.FC0, m.L0, R), sm, st));
@@ -483,15 +499,15 @@ extern "C" int dppo_update_create(dppo_update** out, dppo_ctx* ctx, const dppo_r
   if (ctx->kind != 0) return set_error("dppo_update_create: the tensor-core update path covers DiffusionMLP actors"), DPPO_ERR_UNSUPPORTED;
   if (max_rows < 1) return set_error("dppo_update_create: max_rows=%d", max_rows), DPPO_ERR_INVALID;
   const MlpGeom& g = ctx->g;
-  if (g.ln && (g.H % 256 || g.H > 1024)) return set_error("dppo_update_create: LayerNorm width %d unsupported", g.H), DPPO_ERR_UNSUPPORTED;
-  if (critic->use_layernorm && (critic->hidden_dim % 256 || critic->hidden_dim > 1024))
-    return set_error("dppo_update_create: critic LayerNorm width %d unsupported", critic->hidden_dim), DPPO_ERR_UNSUPPORTED;
+
   if (critic->hidden_dim % 8 || critic->hidden_dim < 16 || critic->n_blocks < 1 || critic->out_dim < 1 || critic->in_dim < 1 ||
       critic->in_dim != g.Dc_in)
     return set_error("dppo_update_create: critic geometry (%d -> %d x %d -> %d) unsupported", critic->in_dim, critic->hidden_dim,
                      critic->n_blocks, critic->out_dim), DPPO_ERR_UNSUPPORTED;
   if (g.CH && (g.CO % 64 || g.CH % 64))
     return set_error("dppo_update_create: cond_mlp widths (%d, %d) must be multiples of 64", g.CH, g.CO), DPPO_ERR_UNSUPPORTED;
+  if ((g.ln && g.act != DPPO_ACT_MISH) || (critic->use_layernorm && critic->activation != DPPO_ACT_MISH))
+    return set_error("dppo_update_create: LayerNorm nets are built for the Mish activation"), DPPO_ERR_UNSUPPORTED;
   if (g.H % 64 || critic->hidden_dim % 64)
     return set_error("dppo_update_create: hidden widths (%d, %d) must be multiples of 64", g.H, critic->hidden_dim), DPPO_ERR_UNSUPPORTED;
   if (ctx->ft < 1 || ctx->ft > 128) return set_error("dppo_update_create: ft_denoising_steps %d", ctx->ft), DPPO_ERR_UNSUPPORTED;
