@@ -807,6 +807,13 @@ extern "C" int dppo_update_minibatch(dppo_update* u, const dppo_update_batch* bt
   return dppo_update_backward(u, u->geps, u->gv, nullptr, nullptr, vf_coef, with_actor, 1, stream);
 }
 
+// stream-ordered zero fill (the flat gradient buffer before a minibatch) without a framework elementwise kernel
+extern "C" int dppo_memset_zero(void* ptr, size_t bytes, void* stream) {
+  if (!ptr && bytes) return set_error("dppo_memset_zero: null pointer"), DPPO_ERR_INVALID;
+  if (bytes) DPPO_CUDA(cudaMemsetAsync(ptr, 0, bytes, static_cast<cudaStream_t>(stream)));
+  return DPPO_OK;
+}
+
 extern "C" int dppo_update_buffers(dppo_update* u, float** eps, float** vpred, float** grad_eps, float** grad_vpred) {
   if (!u) return set_error("dppo_update_buffers: null argument"), DPPO_ERR_INVALID;
   if (eps) *eps = u->actor.OUT;

@@ -101,7 +101,12 @@ class FlatGradBuffer:
         return self.flat[self.n_grad:]
 
     def zero(self):
-        self.flat.zero_()
+        if self.flat.is_cuda:  # stream-ordered cudaMemsetAsync through the library: no framework fill kernel in the minibatch
+            from dppo_b200 import _lib
+
+            _lib.check(_lib.load().dppo_memset_zero(self.flat.data_ptr(), self.flat.numel() * 4, _lib.stream_ptr()), "dppo_memset_zero")
+        else:
+            self.flat.zero_()
 
     def allreduce(self):
         _, W = world()

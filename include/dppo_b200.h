@@ -259,6 +259,9 @@ int dppo_update_backward(dppo_update* up, const float* grad_eps, const float* gr
  * scalars[8] as in dppo_ppo_loss_fwd_bwd; workspace >= 128 bytes.                                                 */
 int dppo_update_minibatch(dppo_update* up, const dppo_update_batch* batch, const dppo_loss_hp* hp, float vf_coef,
                           int with_actor, float* scalars, void* workspace, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: zeroes the flat gradient buffer before a minibatch (what
+ * optimizer.zero_grad() does at train_ppo_diffusion_agent.py:336-338) without a framework fill kernel.            */
+int dppo_memset_zero(void* ptr, size_t bytes, void* stream);
 /* the library-owned buffers of the last forward: eps, vpred, and the gradient buffers dppo_update_minibatch fills   */
 int dppo_update_buffers(dppo_update* up, float** eps, float** vpred, float** grad_eps, float** grad_vpred);
 

@@ -419,9 +419,12 @@ def get_logprobs_subsample(p, nc, dc, state, chains_prev, chains_next, denoising
 def ppo_loss(
     p: Params, nc: NetCfg, dc: DiffCfg, state, chains_prev, chains_next, denoising_inds, returns, oldvalues,
     advantages, oldlogprobs, reward_horizon: int = 4, faithful_cost=True, python_discount_loop=True,
+    use_bc_loss=False, bc_noise=None,
 ):
     """
-    PPODiffusion.loss (use_bc_loss=False), reference dppo/model/diffusion/diffusion_ppo.py:57-199.
+    PPODiffusion.loss, reference dppo/model/diffusion/diffusion_ppo.py:57-199.  `use_bc_loss` (:105-126) samples a chain
+    from the BASE policy for every row (injected draws `bc_noise` (S+1, B, Ta, Da) stand in for torch.randn) and scores it
+    under the fine-tuned policy.
     Returns (pg_loss, entropy_loss, v_loss, clipfrac, approx_kl, ratio_mean, bc_loss, eta_mean); the first three are
     graph tensors when `p` holds leaf tensors with requires_grad.
     `python_discount_loop=True` builds the denoising discount with the reference's per-row Python loop (:138-143) so
@@ -433,6 +436,11 @@ def ppo_loss(
     newlp = newlp.clamp(min=-5, max=2)[:, :reward_horizon, :].mean(dim=(-1, -2)).view(-1)
     oldlp = oldlogprobs.clamp(min=-5, max=2)[:, :reward_horizon, :].mean(dim=(-1, -2)).view(-1)
     bc_loss = 0
+    if use_bc_loss:  # diffusion_ppo.py:105-126
+        with torch.no_grad():
+            _, bc_chains = sample_chain(p, nc, dc, state, bc_noise, deterministic=False, use_base_policy=True, faithful_cost=faithful_cost)
+        bc_lp = get_logprobs(p, nc, dc, state, bc_chains, use_base_policy=False, faithful_cost=faithful_cost)
+        bc_loss = -bc_lp.clamp(min=-5, max=2).mean(dim=(-1, -2)).view(-1).mean()
     adv = advantages
     if dc.norm_adv:
         adv = (adv - adv.mean()) / (adv.std() + 1e-8)

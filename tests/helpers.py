@@ -154,6 +154,8 @@ def oracle_cfgs(w):
         min_logprob_denoising_std=p.get("min_logprob_denoising_std", 0.1), gamma_denoising=p["gamma_denoising"],
         clip_ploss_coef=p["clip_ploss_coef"], clip_ploss_coef_base=p["clip_ploss_coef_base"],
         clip_ploss_coef_rate=p["clip_ploss_coef_rate"],
+        **{k: p[k] for k in ("clip_vloss_coef", "clip_advantage_lower_quantile", "clip_advantage_upper_quantile", "eps_clip_value",
+                             "final_action_clip_value", "denoised_clip_value", "norm_adv") if k in p},
     )
     return nc, dc
 

@@ -289,3 +289,105 @@ def test_empty_and_multi_wave_batches():
         with torch.no_grad():  # same chains on both sides (log-probs amplify chain differences by 1 / sigma^2)
             got = model.get_logprobs({"state": inp["state"][rows].cuda()}, chains_o.cuda())
         assert_close(got.cpu().numpy(), lp_o.numpy(), 1e-3, f"log-probs rows {rows}")
+
+
+# ------------------------------------------------------------------------------------------------ bench shapes
+@pytest.mark.parametrize("workload,n_envs,tile_envs,cluster", [
+    ("walker2d", 4096, 64, 2), ("furniture", 1000, 32, 4), ("transport", 50, 16, 8), ("square_unet", 1024, 16, 0),
+    ("hopper", 40, 0, -1),
+])
+def test_bench_shapes_match_oracle_on_row_slices(workload, n_envs, tile_envs, cluster):
+    """The launch shapes bench.py times (SURVEY.md §8d sizes), checked against the CPU oracle on the first / a middle / the
+    last tile of rows: chains, trajectories and teacher-forced chain log-probs."""
+    from oracle import dppo_oracle as O
+
+    w = get_workload(workload)
+    model = build_model(w, "cuda:0", our_classes())
+    eng = model.engine()
+    eng.set_launch_shape(tile_envs, cluster)
+    inp = make_inputs(w, n_envs, 8, seed=17)
+    out = model(cond={"state": inp["state"].cuda()}, noise=inp["noise"].cuda())
+    with torch.no_grad():
+        lp = model.get_logprobs({"state": inp["state"].cuda()}, out.chains)
+    torch.cuda.synchronize()
+    ft = w["ft_denoising_steps"]
+    lp = lp.view(n_envs, ft, w["horizon_steps"], w["action_dim"])
+    nc, dc = oracle_cfgs(w)
+    p = oracle_params(model)
+    torch.set_num_threads(8)
+    n = min(24, n_envs)
+    mid = (n_envs // 2 // 8) * 8
+    for rows in {slice(0, n), slice(mid, min(n_envs, mid + n)), slice(n_envs - n, n_envs)}:
+        traj_o, chains_o = O.sample_chain(p, nc, dc, inp["state"][rows], inp["noise"][:, rows], faithful_cost=False)
+        assert_close(out.chains[rows].cpu().numpy(), chains_o.numpy(), 1e-3, f"{workload} chains rows {rows}")
+        assert_close(out.trajectories[rows].cpu().numpy(), traj_o.numpy(), 1e-3, f"{workload} trajectories rows {rows}")
+        with torch.no_grad():  # same chains on both sides (log-probs amplify chain differences by 1 / sigma^2)
+            got = model.get_logprobs({"state": inp["state"][rows].cuda()}, chains_o.cuda())
+        lp_o = O.get_logprobs(p, nc, dc, inp["state"][rows], chains_o, faithful_cost=False)
+        assert_close(got.cpu().numpy(), lp_o.numpy(), 1e-3, f"{workload} log-probs rows {rows}")
+        # and the log-probs of the kernel's own chains, evaluated in the full-size launch, are finite and consistent
+        assert torch.isfinite(lp[rows]).all()
+
+
+# ------------------------------------------------------------------------------------------------ optional branches
+def _variant_setup(name):
+    from tests.helpers import GOLDEN_DIR, VARIANTS, perturb_again, variant_workload
+
+    spec = VARIANTS[name]
+    w = variant_workload(name)
+    model = build_model(w, "cuda:0", our_classes())
+    gold = dict(np.load(f"{GOLDEN_DIR}/variant_{name}.npz", allow_pickle=False))
+    inp = make_inputs(w, spec["n_envs"], spec["mb_rows"], seed=spec.get("seed", 0))
+    if spec.get("anneal"):
+        model.step()  # ft 10 -> 7, actor <- actor_ft (repacked), fresh actor_ft; the kernel context is rebuilt
+        perturb_again(model)
+        inp = make_inputs(w, spec["n_envs"], spec["mb_rows"], seed=spec.get("seed", 0), ft=model.ft_denoising_steps)
+    return spec, w, model, gold, inp
+
+
+@pytest.mark.parametrize("name", ["bc", "vclip_quant", "epsclip", "finalclip", "anneal"])
+def test_variant_chain_and_logprobs_match_reference(name):
+    """eps_clip_value (diffusion_vpg.py:194-195), final_action_clip_value (:300-303), annealed ft window + repack (:102-127)."""
+    spec, w, model, gold, inp = _variant_setup(name)
+    out = model(cond={"state": inp["state"].cuda()}, noise=inp["noise"].cuda())
+    assert out.chains.shape == gold["chains"].shape
+    assert_close(out.chains.cpu().numpy(), gold["chains"], 1e-3, f"{name} chains")
+    assert_close(out.trajectories.cpu().numpy(), gold["traj"], 1e-3, f"{name} trajectories")
+    with torch.no_grad():
+        lp = model.get_logprobs({"state": inp["state"].cuda()}, torch.from_numpy(gold["chains"]).cuda())
+    assert_close(lp.cpu().numpy(), gold["logprobs"], 1e-3, f"{name} log-probs")
+    if name == "finalclip":
+        assert float(out.trajectories.abs().max()) <= 0.5 + 1e-6 and float((out.trajectories.abs() >= 0.5 - 1e-6).float().mean()) > 0.01
+
+
+@pytest.mark.parametrize("name", ["bc", "vclip_quant", "epsclip"])
+def test_variant_loss_and_gradients_match_reference(name):
+    """use_bc_loss (diffusion_ppo.py:105-126), clip_vloss_coef (:178-187) + advantage quantiles (:133-135), eps_clip_value."""
+    spec, w, model, gold, inp = _variant_setup(name)
+    E, ft = spec["n_envs"], w["ft_denoising_steps"]
+    dev = "cuda:0"
+    chains = torch.from_numpy(gold["chains"]).to(dev)
+    lp_k = torch.from_numpy(gold["logprobs"]).to(dev).reshape(E, ft, w["horizon_steps"], w["action_dim"])
+    b, d = inp["mb_b"].to(dev), inp["mb_d"].to(dev)
+    state = inp["state"].to(dev)
+    if spec.get("use_bc_loss"):
+        S = chain_evals(w)
+        model.bc_noise = torch.randn((S + 1, spec["mb_rows"], w["horizon_steps"], w["action_dim"]),
+                                     generator=torch.Generator().manual_seed(int(gold["bc_noise_seed"]))).to(dev)
+    res = model.loss({"state": state[b]}, chains[b, d], chains[b, d + 1], d, inp["returns"].to(dev)[b],
+                     inp["oldvalues"].to(dev)[b], inp["advantages"].to(dev)[b], lp_k[b, d] + inp["lp_shift"].to(dev),
+                     use_bc_loss=bool(spec.get("use_bc_loss")), reward_horizon=w["act_steps"])
+    (res[0] + 0.5 * res[2] + spec.get("bc_coeff", 0.0) * res[6]).backward()
+    got = np.array([float(res[0]), float(res[1]), float(res[2]), res[3], res[4], res[5], float(res[6]), res[7]])
+    np.testing.assert_allclose(got[[0, 1, 2, 4, 5, 6, 7]], gold["loss_scalars"][[0, 1, 2, 4, 5, 6, 7]], rtol=2e-3, atol=1e-5)
+    assert abs(got[3] - gold["loss_scalars"][3]) <= 0.03
+    params = dict(model.actor_ft.named_parameters())
+    crit = {"critic." + n: p for n, p in model.critic.named_parameters()}
+    g_last = params[str(gold["grad_last_name"])].grad.cpu().numpy()
+    scale = np.abs(gold["grad_last"]).max()
+    assert np.abs(g_last - gold["grad_last"]).max() <= 2e-3 * scale
+    for gname, (norm, _) in zip(gold["grad_names"], gold["grad_stats"]):
+        gname = str(gname)
+        p = crit[gname] if gname.startswith("critic.") else params[gname]
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert abs(float(g.double().norm()) - norm) <= 5e-3 * max(norm, 1e-10), gname
