@@ -64,6 +64,11 @@ def workload_name(w, E):
             f"Tp=Ta={w['horizon_steps']}, {kind}, ft={w['ft_denoising_steps']}")
 
 
+def bench_config(w, E):
+    """The `config` object of BOTH arms (identical dicts): the workload the metric is quoted on."""
+    return {"workload": workload_name(w, E)}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
@@ -99,12 +104,51 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_classes():
+    """The UNMODIFIED reference classes from baseline/_ref/dppo (a git-ignored copy of /root/reference/dppo that travels
+    with the working tree), or None when it is absent / not importable."""
+    if not os.path.isdir(os.path.join(REF_DIR, "dppo")):
+        return None
+    try:
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        from dppo.model.common.critic import CriticObs
+        from dppo.model.diffusion.diffusion_ppo import PPODiffusion
+        from dppo.model.diffusion.eta import EtaFixed
+        from dppo.model.diffusion.mlp_diffusion import DiffusionMLP
+        from dppo.model.diffusion.unet import Unet1D
+
+        return dict(ppo=PPODiffusion, mlp=DiffusionMLP, unet=Unet1D, critic=CriticObs, eta=EtaFixed)
+    except Exception as ex:  # noqa: BLE001 - any import problem means "use the port"
+        print(f"[bench] reference classes not importable ({type(ex).__name__}: {ex}); timing the oracle port", file=sys.stderr)
+        return None
+
+
 def cpu_chain_seconds(w, E, reps, warmup, threads):
-    """Oracle port of VPGDiffusion.forward on the host cores (both networks on fine-tuned steps, like the reference)."""
-    from oracle import dppo_oracle as O
+    """(times, kind): the reference's own VPGDiffusion.forward (model(cond, deterministic=False, return_chain=True), CPU
+    fp32, all host threads) when baseline/_ref is present -> kind "reference"; else the oracle port of the same path (both
+    networks on fine-tuned steps, like the reference) -> kind "port"."""
     from tests.helpers import build_model, make_inputs, oracle_cfgs, oracle_params, our_classes
 
     torch.set_num_threads(threads)
+    ref = reference_classes()
+    if ref is not None:
+        model = build_model(w, "cpu", ref)
+        model.train()
+        state = make_inputs(w, E, 8)["state"]
+        times = []
+        with torch.no_grad():
+            for i in range(warmup + reps):
+                t0 = time.perf_counter()
+                model(cond={"state": state}, deterministic=False, return_chain=True)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+        return times, "reference"
+    from oracle import dppo_oracle as O
+
     model = build_model(w, "cpu", our_classes())
     nc, dc = oracle_cfgs(w)
     p = oracle_params(model)
@@ -115,22 +159,27 @@ def cpu_chain_seconds(w, E, reps, warmup, threads):
         O.sample_chain(p, nc, dc, inp["state"], inp["noise"], faithful_cost=True)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times
+    return times, "port"
+
+
+def cpu_kind_text(kind):
+    return ("the reference's own PPODiffusion.forward (baseline/_ref/dppo, unmodified)" if kind == "reference"
+            else "oracle port of the reference path (baseline/_ref absent)")
 
 
 def run_reference(args, w, E, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    times = cpu_chain_seconds(w, E, args.steps, args.warmup, cores)
+    times, kind = cpu_chain_seconds(w, E, args.steps, args.warmup, cores)
     t = sum(times) / len(times)
     value = E * w["act_steps"] / t
-    sample = f"{args.steps} full chains over all {E} envs (oracle port of the reference path, torch CPU fp32, {cores} threads)"
+    sample = f"{args.steps} full chains over all {E} envs ({cpu_kind_text(kind)}, torch CPU fp32, {cores} threads)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(w, E)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": bench_config(w, E),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -250,6 +299,13 @@ def run_b200(args, w, E, rank, world, local_rank):
 
     # ---- update (secondary): one PPO minibatch = fused loss kernel + autograd backward + both optimiser steps
     upd = bench_update(args, w, model, dev, E, rank, world) if args.update else None
+    # ---- strong scaling of north_star's sharded config (Furniture one_leg_low: 1000 envs and 17 600-row minibatches split
+    # over the ranks, gradients all-reduced): the path that HAS a collective
+    strong = None
+    if args.strong and args.workload != "furniture":
+        del model, eng
+        torch.cuda.empty_cache()
+        strong = bench_strong(args, dev, rank, world)
 
     t = torch.tensor([total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -278,9 +334,12 @@ def run_b200(args, w, E, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3" if args.precision == "split3" else "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(w, E), "envs_per_gpu": E, "precision": args.precision,
-                       "l2": "flushed between timed steps (512 MiB memset outside the event pairs)",
-                       "weights": "random init seed 42, actor_ft perturbed 1e-2", "noise": "in-kernel Philox4x32-10"},
+            "config": bench_config(w, E),
+            "setup": {"envs_per_gpu": E, "precision": args.precision,
+                      "l2": "flushed between timed steps (512 MiB memset outside the event pairs)",
+                      "weights": "random init seed 42, actor_ft perturbed 1e-2", "noise": "in-kernel Philox4x32-10",
+                      "scaling": "weak: every rank runs the workload's envs, no data-path collective in the rollout metric; "
+                                 "the collective path is measured in `strong_scaling`"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
                     "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_s / args.steps},
             "e2e_zero_copy": {
@@ -303,16 +362,177 @@ def run_b200(args, w, E, rank, world, local_rank):
             "wall_s_timed_region": wall,
             "update": upd,
         }
+        line["strong_scaling"] = strong
         if args.cpu_baseline:
             cores = os.cpu_count() or 1
             reps = max(3, min(10, int(15.0 / max(0.05, 0.16e-3 * E))))
-            times = cpu_chain_seconds(w, E, reps, 1, cores)
+            times, kind = cpu_chain_seconds(w, E, reps, 1, cores)
             tc = sum(times) / len(times)
-            line["cpu_baseline"] = {"value": E * act / tc, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{reps} full chains over {E} envs, oracle port, torch CPU fp32, {cores} threads"}
+            line["cpu_baseline"] = {"value": E * act / tc, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{reps} full chains over {E} envs, {cpu_kind_text(kind)}, torch CPU fp32, {cores} threads"}
+            if args.workload != "hopper":
+                line["hopper_50x_target"] = hopper_ratio(args, dev, cores)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hopper_ratio(args, dev, cores):
+    """north_star's explicit target: >= 50x the reference host-CPU env-steps/s for the 20-step DDPM Hopper chain (40 envs)
+    on one B200, measured in this run on both sides (end to end: pinned host obs in, host actions + chains out)."""
+    from tests.helpers import build_model, our_classes
+
+    w = get_workload("hopper")
+    E = w["n_envs"]
+    model = build_model(w, str(dev), our_classes())
+    model.engine_precision = args.precision
+    ft = w["ft_denoising_steps"]
+    rng = np.random.default_rng(5)
+    host_obs = [torch.from_numpy(rng.uniform(-1, 1, (E, w["cond_steps"], w["obs_dim"])).astype(np.float32)).pin_memory() for _ in range(4)]
+    host_traj = torch.empty((E, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
+    host_chain = torch.empty((E, ft + 1, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
+
+    def step(i):
+        obs = host_obs[i % 4].to(dev, non_blocking=True)
+        out = model(cond={"state": obs}, deterministic=False, return_chain=True)
+        host_traj.copy_(out.trajectories, non_blocking=True)
+        host_chain.copy_(out.chains, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def step_zero_copy(i):
+        model(cond={"state": host_obs[i % 4]}, deterministic=False, return_chain=True, out_trajectories=host_traj, out_chains=host_chain)
+        torch.cuda.current_stream().synchronize()
+
+    res = {}
+    for name, fn in (("e2e", step), ("e2e_zero_copy", step_zero_copy)):
+        for i in range(20):
+            fn(i)
+        t0 = time.perf_counter()
+        n = 200
+        for i in range(n):
+            fn(i)
+        res[name] = E * w["act_steps"] * n / (time.perf_counter() - t0)
+    times, kind = cpu_chain_seconds(w, E, 20, 3, cores)
+    cpu = E * w["act_steps"] / (sum(times) / len(times))
+    return {"workload": workload_name(w, E), "e2e_env_steps_s": res["e2e"], "e2e_zero_copy_env_steps_s": res["e2e_zero_copy"],
+            "cpu_env_steps_s": cpu, "cpu_kind": kind, "cores": cores, "ratio_e2e": res["e2e"] / cpu,
+            "ratio_e2e_zero_copy": res["e2e_zero_copy"] / cpu, "target": 50.0}
+
+
+def bench_strong(args, dev, rank, world):
+    """Furniture one_leg_low (reference cfg/furniture/finetune/one_leg_low/ft_ppo_diffusion_mlp.yaml:18-26,48,71): 1000
+    envs and 17 600-row minibatches, SHARDED over the ranks (strong scaling), gradients of actor_ft + critic all-reduced
+    every minibatch.  Reports rollout env-steps/s, update samples/s and the all-reduce alone."""
+    import torch.distributed as dist
+
+    from dppo_b200 import distributed as D
+    from dppo_b200.optim import FlatAdamW
+    from tests.helpers import build_model, our_classes
+
+    w = get_workload("furniture")
+    E_glob, bs_glob = w["n_envs"], w["train"]["batch_size"]
+    e0, e1 = D.env_shard(E_glob, rank, world)
+    E = e1 - e0
+    model = build_model(w, str(dev), our_classes())
+    model.engine_precision = args.precision
+    eng = model.engine()
+    ft, Ta, Da = w["ft_denoising_steps"], w["horizon_steps"], w["action_dim"]
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    state = torch.rand((E, w["cond_steps"], w["obs_dim"]), device=dev, generator=g) * 2 - 1
+    min_std = float(model.get_min_sampling_denoising_std())
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_ms(fn, reps):
+        for _ in range(3):
+            fn()
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        sync_all()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    chain_ms = timed_ms(lambda: eng.sample(state, seed=1, offset=1, env_offset=e0, min_sampling_std=min_std), 20)
+    # rollout buffers of this rank's envs, gathered into the global (step, env) order like the agent does
+    n_steps = 24
+    obs_l = torch.rand((n_steps, E, w["cond_steps"], w["obs_dim"]), device=dev, generator=g) * 2 - 1
+    with torch.no_grad():
+        chains_l = torch.stack([model(cond={"state": obs_l[s]}, env_offset=e0).chains for s in range(n_steps)])
+        lp_l = model.get_logprobs({"state": obs_l.flatten(0, 1)}, chains_l.flatten(0, 1)).view(n_steps, E, ft, Ta, Da)
+        val_l = model.critic({"state": obs_l.flatten(0, 1)}).view(n_steps, E)
+    adv_l = torch.randn((n_steps, E), device=dev, generator=g)
+    N = n_steps * E_glob
+    obs_k = D.gather_env_dim(obs_l, E_glob).view(N, w["cond_steps"], w["obs_dim"]).contiguous()
+    chains_k = D.gather_env_dim(chains_l, E_glob).view(N, ft + 1, Ta, Da).contiguous()
+    lp_k = D.gather_env_dim(lp_l, E_glob).view(N, ft, Ta, Da).contiguous()
+    val_k = D.gather_env_dim(val_l, E_glob).reshape(-1).contiguous()
+    adv_k = D.gather_env_dim(adv_l, E_glob).reshape(-1).contiguous()
+    ret_k = (adv_k + val_k).contiguous()
+    opt_a = FlatAdamW(model.actor_ft.parameters(), lr=w["train"]["actor_lr"], weight_decay=0)
+    opt_c = FlatAdamW(model.critic.parameters(), lr=w["train"]["critic_lr"], weight_decay=0)
+    grads = D.FlatGradBuffer([list(model.actor_ft.parameters()), list(model.critic.parameters())])
+    bs = min(bs_glob, N * ft)
+    lo, hi = D.minibatch_slice(bs, rank, world)
+    fused = model.fused_update_reason() is None
+
+    def fwd_bwd(inds):
+        grads.zero()
+        if fused:
+            model.update_minibatch(obs_k, chains_k, lp_k, ret_k, val_k, adv_k, inds, row_begin=lo, row_count=hi - lo,
+                                   reward_horizon=w["act_steps"], vf_coef=w["train"]["vf_coef"], scalars_out=grads.scalars)
+        else:
+            res = model.loss_gathered(obs_k, chains_k, lp_k, ret_k, val_k, adv_k, inds, row_begin=lo, row_count=hi - lo,
+                                      reward_horizon=w["act_steps"], scalars_out=grads.scalars)
+            (res[0] + w["train"]["vf_coef"] * res[2]).backward()
+        grads.allreduce()
+
+    step_fn = fwd_bwd
+    if args.graph_update:
+        from dppo_b200.agent.finetune.graphed import GraphedMinibatch
+
+        try:
+            step_fn = GraphedMinibatch(fwd_bwd, bs, dev)
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] strong block: graph capture failed ({type(ex).__name__}); eager", file=sys.stderr, flush=True)
+            torch.cuda.synchronize(dev)
+    perm = D.broadcast_permutation(N * ft, dev)
+    per_epoch = max(1, (N * ft) // bs)
+    k = [0]
+
+    def minibatch():
+        j = k[0] % per_epoch
+        k[0] += 1
+        step_fn(perm[j * bs:(j + 1) * bs])
+        grads.scalars.tolist()  # the KL early-stop read of the agent (train_ppo_diffusion_agent.py:379)
+        opt_a.step()
+        opt_c.step()
+
+    upd_ms = timed_ms(minibatch, 10)
+    ar_ms = timed_ms(grads.allreduce, 20) if world > 1 else 0.0
+    nbytes = grads.flat.numel() * 4
+    out = {
+        "workload": workload_name(w, E_glob), "scaling": "strong", "n_gpus": world, "envs_per_gpu": E,
+        "minibatch_rows_per_gpu": hi - lo, "minibatch_rows": bs,
+        "rollout_env_steps_s": E_glob * w["act_steps"] / (chain_ms * 1e-3), "rollout_ms_per_decision": chain_ms,
+        "update_samples_s": bs / (upd_ms * 1e-3), "update_ms_per_minibatch": upd_ms,
+        "allreduce_bytes": nbytes, "allreduce_us": 1e3 * ar_ms,
+        "allreduce_bus_GBps": (2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9) if world > 1 else None,
+        "update_path": "dppo_update_minibatch (tcgen05 GEMM kernels)" if fused else "torch autograd",
+        "note": "max over ranks of CUDA-event time; update = gather -> forward -> loss -> backward -> NCCL all-reduce of the flat "
+                "gradient buffer -> KL read -> both AdamW steps",
+    }
+    del model, eng, obs_k, chains_k, lp_k
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_update(args, w, model, dev, E, rank, world):
@@ -456,6 +676,8 @@ def main():
     ap.add_argument("--precision", default="split3", choices=["split3", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-update", dest="update", action="store_false", help="skip the secondary PPO-update measurement")
+    ap.add_argument("--no-strong", dest="strong", action="store_false",
+                    help="skip the Furniture strong-scaling block (sharded envs + minibatches, gradient all-reduce)")
     ap.add_argument("--no-graph-update", dest="graph_update", action="store_false",
                     help="run the PPO minibatch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -340,6 +340,8 @@ struct AdamArgs {
   long long n;
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm;
   const double* sqnorm;  // nullptr: no clipping
+  const int* stop;       // optional device flag: a set flag turns the launch into a no-op (KL early stop, see kl_check_kernel)
+  const float* coefs;    // optional device (bc1, bc2_sqrt) written by adam_tick_kernel (step count kept on the device)
 };
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamArgs& a, float coef) {
@@ -351,7 +353,32 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
   p -= (a.lr / a.bc1) * (m / denom);
 }
 
-__global__ void adamw_kernel(const AdamArgs a) {
+// device-resident step count: ++step, bias corrections of that step (skipped once the stop flag is set)
+__global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ coefs, const int* __restrict__ stop, float beta1,
+                                 float beta2) {
+  if (stop && *stop) return;
+  const int s = ++*step;
+  coefs[0] = float(1.0 - pow(double(beta1), s));
+  coefs[1] = float(sqrt(1.0 - pow(double(beta2), s)));
+}
+
+// after the gradient all-reduce of minibatch k (k = a device counter): keep the diagnostics, raise the stop flag when
+// approx_kl exceeds target_kl (reference train_ppo_diffusion_agent.py:376-382: the minibatch that trips the test has
+// already been applied; everything after it must not be)
+__global__ void kl_check_kernel(const float* __restrict__ scalars, float target_kl, int use_target, int* __restrict__ state,
+                                float* __restrict__ history, int max_history) {
+  const int k = state[2];
+  if (threadIdx.x < 8 && k < max_history) history[k * 8 + threadIdx.x] = scalars[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (!state[0] && use_target && scalars[2] > target_kl) state[0] = 1, state[1] = k;
+    state[2] = k + 1;
+  }
+}
+
+__global__ void adamw_kernel(AdamArgs a) {
+  if (a.stop && *a.stop) return;
+  if (a.coefs) a.bc1 = a.coefs[0], a.bc2_sqrt = a.coefs[1];
   float coef = 1.f;
   if (a.sqnorm) {  // clip_grad_norm_: coef = min(1, max_norm / (||g|| + 1e-6))
     const float total = float(sqrt(*a.sqnorm));
@@ -480,6 +507,19 @@ __global__ void split3_pack_kernel(const float* __restrict__ x, long long M, int
 
 using namespace dppo;
 
+// SM count of the current device (grid caps of the grid-stride kernels)
+static int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+
 extern "C" int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t ldx, int extra_mode, const float* extra,
                                 void* out, int pattern, void* stream) {
   if (!x || !out) return set_error("dppo_split3_pack: null argument"), DPPO_ERR_INVALID;
@@ -493,7 +533,7 @@ extern "C" int dppo_split3_pack(const float* x, int64_t rows, int cols, int64_t 
   const int Kp = (cols + (extra_mode ? 1 : 0) + 7) & ~7;
   const long long total = rows * (Kp / 4);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
   split3_pack_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, rows, cols, ldx, Kp, pattern, extra_mode, extra, static_cast<__nv_bfloat16*>(out));
   cudaError_t e = cudaGetLastError();
@@ -510,7 +550,7 @@ extern "C" int dppo_reward_scale_f64(const double* reward, const double* first, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = (long long)n_steps * n_envs;
   int blocks = int((n + 255) / 256);
-  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  blocks = blocks > device_sm_count() * 8 ? device_sm_count() * 8 : blocks;
   if (phase == 0) {
     DPPO_CUDA(cudaMemsetAsync(ws, 0, 8 * sizeof(double), st));
     reward_scan_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(reward, first, n_steps, n_envs, gamma, ret_state, rets_scratch, ws);
@@ -543,7 +583,7 @@ extern "C" int dppo_adamw_flat(float* params, const float* grads, float* exp_avg
   a.bc2_sqrt = float(sqrt(1.0 - pow(double(beta2), step)));
   a.max_norm = max_grad_norm;
   int blocks = int((n / 4 + 255) / 256);
-  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  blocks = blocks < 1 ? 1 : (blocks > device_sm_count() * 8 ? device_sm_count() * 8 : blocks);
   if (max_grad_norm >= 0.f) {
     if (!workspace) return set_error("dppo_adamw_flat: clipping needs a workspace"), DPPO_ERR_INVALID;
     double* ws = static_cast<double*>(workspace);
@@ -554,6 +594,43 @@ extern "C" int dppo_adamw_flat(float* params, const float* grads, float* exp_avg
   adamw_kernel<<<blocks, 256, 0, st>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "adamw_kernel launch");
+}
+
+extern "C" int dppo_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, int* step_state,
+                                   const int* stop_flag, float max_grad_norm, void* workspace, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !step_state) return set_error("dppo_adamw_flat_dev: null argument"), DPPO_ERR_INVALID;
+  if (n < 0) return set_error("dppo_adamw_flat_dev: n=%lld", (long long)n), DPPO_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return set_error("dppo_adamw_flat_dev: buffers must be 16-byte aligned"), DPPO_ERR_INVALID;
+  if (n == 0) return DPPO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AdamArgs a{};
+  a.p = params, a.g = grads, a.m = exp_avg, a.v = exp_avg_sq, a.n = n;
+  a.lr = lr, a.beta1 = beta1, a.beta2 = beta2, a.eps = eps, a.weight_decay = weight_decay;
+  a.max_norm = max_grad_norm, a.stop = stop_flag, a.coefs = reinterpret_cast<const float*>(step_state + 2);
+  adam_tick_kernel<<<1, 1, 0, st>>>(step_state, reinterpret_cast<float*>(step_state + 2), stop_flag, beta1, beta2);
+  int blocks = int((n / 4 + 255) / 256);
+  blocks = blocks < 1 ? 1 : (blocks > device_sm_count() * 8 ? device_sm_count() * 8 : blocks);
+  if (max_grad_norm >= 0.f) {
+    if (!workspace) return set_error("dppo_adamw_flat_dev: clipping needs a workspace"), DPPO_ERR_INVALID;
+    double* ws = static_cast<double*>(workspace);
+    DPPO_CUDA(cudaMemsetAsync(ws, 0, sizeof(double), st));
+    grad_sqnorm_kernel<<<blocks, 256, 0, st>>>(grads, n, ws);
+    a.sqnorm = ws;
+  }
+  adamw_kernel<<<blocks, 256, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "adamw_kernel launch");
+}
+
+extern "C" int dppo_kl_check(const float* scalars, float target_kl, int use_target, int* state, float* history, int max_history,
+                             void* stream) {
+  if (!scalars || !state || !history || max_history < 1) return set_error("dppo_kl_check: bad argument"), DPPO_ERR_INVALID;
+  kl_check_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(scalars, target_kl, use_target, state, history, max_history);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "kl_check_kernel launch");
 }
 
 extern "C" int dppo_gae_f64(const double* reward, const double* terminated, const double* values,

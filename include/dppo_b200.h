@@ -309,6 +309,22 @@ int dppo_adamw_flat(float* params, const float* grads, float* exp_avg, float* ex
                     float beta1, float beta2, float eps, float weight_decay, int step, float max_grad_norm,
                     void* workspace, void* stream);
 
+/* The same update with the STEP COUNT on the device (CUDA-graph friendly: a replayed launch advances its own bias
+ * correction) and an optional stop flag.  step_state: 4 ints on the device, [0] = step count (the call increments it),
+ * [2..3] = scratch for the bias corrections of the step; zero it once.  stop_flag (device int or NULL): once set, the call
+ * is a no-op and does not advance the step count.                                                                   */
+int dppo_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int* step_state, const int* stop_flag,
+                        float max_grad_norm, void* workspace, void* stream);
+
+/* KL early stop on the device (train_ppo_diffusion_agent.py:376-382).  Called after the gradient all-reduce and the
+ * optimiser steps of every minibatch: appends scalars[8] (dppo_ppo_loss_fwd_bwd layout) to history[k] with k = state[2]
+ * (a device-side minibatch counter, incremented here) and, when use_target and scalars[2] (approx_kl) > target_kl, sets
+ * state[0] = 1 and state[1] = k.  Later optimiser launches that were handed &state[0] as stop_flag do nothing, so the
+ * host may poll the flag lazily instead of synchronising on every minibatch.  state: 4 device ints, zeroed per update. */
+int dppo_kl_check(const float* scalars, float target_kl, int use_target, int* state, float* history, int max_history,
+                  void* stream);
+
 /* ---- bring-up ------------------------------------------------------------------------------------------------- */
 /* Single-CTA tcgen05 GEMM that validates the shared-memory / instruction descriptor encodings on hardware:
  * c[128,N] = a[128,K] * b[N,K]^T in bf16 with fp32 accumulation.  scratch >= K/64 * 16 KiB.                      */

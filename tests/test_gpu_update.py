@@ -165,7 +165,7 @@ def test_update_minibatch_equals_loss_and_shards_sum(case):
                                                            reward_horizon=w["act_steps"], vf_coef=0.5).tolist())
     np.testing.assert_allclose(s_all[:5], s_ref, rtol=1e-5, atol=1e-8)
     for a, r_ in zip(g_all, g_ref):
-        assert _relerr(a, r_) < 2e-5
+        assert _relerr(a, r_) < 1e-4
 
     def halves():
         model.update_minibatch(obs_k, chains_k, lp_k, ret_k, val_k, adv_k, inds, row_begin=0, row_count=200,
@@ -175,14 +175,14 @@ def test_update_minibatch_equals_loss_and_shards_sum(case):
 
     _, g_half = grads_of(halves)
     for a, r_ in zip(g_half, g_all):
-        assert _relerr(a, r_) < 2e-5
+        assert _relerr(a, r_) < 1e-4
     # critic warm-up: with_actor = 0 leaves the actor gradients untouched
     n_actor = len(list(model.actor_ft.parameters()))
     _, g_c = grads_of(lambda: model.update_minibatch(obs_k, chains_k, lp_k, ret_k, val_k, adv_k, inds, reward_horizon=w["act_steps"],
                                                      vf_coef=0.5, with_actor=False))
     assert all(float(x.abs().max()) == 0.0 for x in g_c[:n_actor])
     for a, r_ in zip(g_c[n_actor:], g_all[n_actor:]):
-        assert _relerr(a, r_) < 2e-5
+        assert _relerr(a, r_) < 1e-4
 
 
 def test_ratio_is_one_before_any_optimiser_step():
