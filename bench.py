@@ -495,15 +495,10 @@ def bench_strong(args, dev, rank, world):
             (res[0] + w["train"]["vf_coef"] * res[2]).backward()
         grads.allreduce()
 
-    step_fn = fwd_bwd
-    if args.graph_update:
-        from dppo_b200.agent.finetune.graphed import GraphedMinibatch
+    from dppo_b200.agent.finetune.graphed import MinibatchStep
 
-        try:
-            step_fn = GraphedMinibatch(fwd_bwd, bs, dev)
-        except Exception as ex:  # noqa: BLE001
-            print(f"[bench] strong block: graph capture failed ({type(ex).__name__}); eager", file=sys.stderr, flush=True)
-            torch.cuda.synchronize(dev)
+    step_fn = MinibatchStep(fwd_bwd, grads, opt_a, opt_c, True, None, w["train"]["target_kl"], 256, bs, dev,
+                            use_graph=args.graph_update, world=world)
     perm = D.broadcast_permutation(N * ft, dev)
     per_epoch = max(1, (N * ft) // bs)
     k = [0]
@@ -512,9 +507,6 @@ def bench_strong(args, dev, rank, world):
         j = k[0] % per_epoch
         k[0] += 1
         step_fn(perm[j * bs:(j + 1) * bs])
-        grads.scalars.tolist()  # the KL early-stop read of the agent (train_ppo_diffusion_agent.py:379)
-        opt_a.step()
-        opt_c.step()
 
     upd_ms = timed_ms(minibatch, 10)
     ar_ms = timed_ms(grads.allreduce, 20) if world > 1 else 0.0
@@ -527,8 +519,9 @@ def bench_strong(args, dev, rank, world):
         "allreduce_bytes": nbytes, "allreduce_us": 1e3 * ar_ms,
         "allreduce_bus_GBps": (2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9) if world > 1 else None,
         "update_path": "dppo_update_minibatch (tcgen05 GEMM kernels)" if fused else "torch autograd",
+        "gradient_buffer": grads.allocation, "cuda_graph": step_fn.graphed is not None,
         "note": "max over ranks of CUDA-event time; update = gather -> forward -> loss -> backward -> NCCL all-reduce of the flat "
-                "gradient buffer -> KL read -> both AdamW steps",
+                "gradient buffer -> both AdamW steps -> device-side KL check",
     }
     del model, eng, obs_k, chains_k, lp_k
     torch.cuda.empty_cache()
@@ -613,17 +606,14 @@ def bench_update(args, w, model, dev, E, rank, world):
             (res[0] + w["train"]["vf_coef"] * res[2]).backward()
         grads.allreduce()  # gradients of both networks + loss diagnostics: one NCCL all-reduce
 
-    graphed = None
-    if args.graph_update:
-        from dppo_b200.agent.finetune.graphed import GraphedMinibatch
+    # the agent's minibatch unit: forward / backward / all-reduce + both AdamW steps + device-side KL check, one CUDA graph
+    from dppo_b200.agent.finetune.graphed import MinibatchStep
 
-        try:
-            graphed = GraphedMinibatch(fwd_bwd, bs, dev)
-        except Exception as ex:  # capture is an optimisation: report and run eagerly
-            print(f"[bench] CUDA-graph capture of the minibatch failed ({type(ex).__name__}: {str(ex)[:200]}); running eagerly",
-                  file=sys.stderr, flush=True)
-            torch.cuda.synchronize(dev)
-
+    step_fn = MinibatchStep(fwd_bwd, grads, opt_a, opt_c, True, None, w["train"]["target_kl"], 64, bs, dev,
+                            use_graph=args.graph_update, world=world)
+    graphed = step_fn.graphed
+    if args.graph_update and graphed is None:
+        print(f"[bench] CUDA-graph capture of the minibatch failed ({step_fn.graph_error}); running eagerly", file=sys.stderr, flush=True)
     perm = [None]
 
     def minibatch(k):
@@ -633,12 +623,7 @@ def bench_update(args, w, model, dev, E, rank, world):
         if perm[0] is None or k % per_epoch == 0:
             perm[0] = D.broadcast_permutation(N * ft, dev)
         j = k % per_epoch
-        inds = perm[0][j * bs:(j + 1) * bs]
-        (graphed or fwd_bwd)(inds)
-        kl = grads.scalars.tolist()[2]  # the agent's early-stop test: one device->host read per minibatch
-        opt_a.step()
-        opt_c.step()
-        return kl
+        step_fn(perm[0][j * bs:(j + 1) * bs])
 
     for k in range(3):
         minibatch(k)
@@ -648,10 +633,12 @@ def bench_update(args, w, model, dev, E, rank, world):
     t0 = time.perf_counter()
     for k in range(reps):
         minibatch(k)
+    stop_state = step_fn.kl_state.tolist()  # the early-stop flag + the diagnostics history reach the host once, at the end
     torch.cuda.synchronize(dev)
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    assert stop_state[0] == 0 and stop_state[2] == reps + 3, stop_state
     return {"metric": "PPO-update samples/sec", "value": per_rank * world * reps / float(dt), "unit": "samples/s",
             "minibatch_rows": per_rank * world, "buffer_rows": N * ft, "prologue_per_gpu": prologue,
             "path": ("fused gather+log-prob+loss fwd/bwd kernel; flat gradient buffer + one all-reduce; "
@@ -660,9 +647,10 @@ def bench_update(args, w, model, dev, E, rank, world):
                         if fused else
                         "Linear layers as 3-product bf16-split tensor-core GEMMs (dppo_split3_pack + cuBLASLt bf16, fp32 accumulate) under "
                         "torch autograd (" + str(model.fused_update_reason()) + "); ")
-                     + "fused flat AdamW kernel per network; "
-                     + ("forward + loss + backward + all-reduce replayed as ONE CUDA graph per minibatch" if graphed
-                        else "eager launches"))}
+                     + "fused flat AdamW kernel per network (step count on the device), KL early-stop test on the device; "
+                     + ("forward + loss + backward + all-reduce + optimiser steps + KL check replayed as ONE CUDA graph per minibatch"
+                        if graphed else "eager launches")),
+            "gradient_buffer": grads.allocation}
 
 
 def main():

@@ -33,7 +33,7 @@ import torch
 
 from dppo_b200 import distributed as D
 from dppo_b200 import engine as E_
-from dppo_b200.agent.finetune.graphed import GraphedMinibatch
+from dppo_b200.agent.finetune.graphed import MinibatchStep
 from dppo_b200.optim import FlatAdamW
 from dppo_b200.util.config import instantiate
 from dppo_b200.util.reward_scaling import RunningRewardScaler, RunningRewardScalerCUDA  # noqa: F401
@@ -125,6 +125,8 @@ class TrainPPODiffusionAgent:
 
         # gradients of both networks + 8 diagnostics in ONE flat buffer -> one all-reduce per minibatch
         self.grads = D.FlatGradBuffer([list(self.model.actor_ft.parameters()), list(self.model.critic.parameters())])
+        self._actor_ft_id = id(self.model.actor_ft)
+        self._actor_frozen = False
         self.timings = {}
 
     # ------------------------------------------------------------------ schedules
@@ -220,13 +222,12 @@ class TrainPPODiffusionAgent:
         ret_k = D.gather_env_dim(ret, Eg).reshape(-1)
         total_steps = n * Eg * ft
         num_batch = max(1, total_steps // self.batch_size)  # the tail rows of each permutation are skipped, as in the reference
-        clipfracs, stats, flag_break = [], None, False
         lo, hi = D.minibatch_slice(min(self.batch_size, total_steps), self.rank, self.world)
         eta_mean = self.model._eta_value()
         ent_const = -eta_mean  # the entropy term of a fixed-eta policy is a constant (diffusion_ppo.py:183-187)
 
         fused = not self.use_bc_loss and self.model.fused_update_reason() is None
-        with_actor = self.itr >= self.n_critic_warmup_itr
+        with_actor = self.itr >= self.n_critic_warmup_itr and not self._actor_frozen
 
         def fwd_bwd(inds_b):
             """zero grads -> actor_ft / critic forward -> fused loss kernel -> backward -> one all-reduce (no host sync)"""
@@ -248,38 +249,67 @@ class TrainPPODiffusionAgent:
             self.grads.allreduce()  # gradients + [pg, v, kl, clipfrac, ratio] partial means, one collective
             return bc_loss
 
-        # the minibatch is launch-bound: replay it as one CUDA graph when the iteration has enough minibatches to
-        # amortise the capture (the rollout buffers get new addresses every iteration, so the graph is per iteration)
-        step_fn = fwd_bwd
-        n_minibatches = self.update_epochs * num_batch
+        # KL early stop without a host round trip per minibatch (reference :376-382 reads approx_kl on the host after every
+        # minibatch): MinibatchStep chains forward / backward / all-reduce, both AdamW steps and dppo_kl_check on the stream;
+        # the kernel keeps the diagnostics of minibatch k in history[k] and raises a device flag once approx_kl > target_kl,
+        # after which the optimiser launches of LATER minibatches do nothing.  What is applied is exactly what the reference
+        # applies (the minibatch that trips the test included), while the host only polls.  The unit is replayed as one CUDA
+        # graph when the iteration has enough minibatches to amortise the capture (the rollout buffers get new addresses
+        # every iteration, so the graph is per iteration).
+        n_max = self.update_epochs * num_batch
+        use_target = self.target_kl is not None
         quantile_clip = self.model.clip_advantage_lower_quantile > 0 or self.model.clip_advantage_upper_quantile < 1
-        if (self.cuda_graph_update and not self.use_bc_loss and not quantile_clip and n_minibatches >= 16
-                and total_steps >= self.batch_size):
-            try:
-                step_fn = GraphedMinibatch(fwd_bwd, self.batch_size, self.device)
-            except Exception as ex:  # capture is an optimisation only
-                log.warning("CUDA-graph capture of the PPO minibatch failed (%s); running eagerly", ex)
-                torch.cuda.synchronize()
-                self.cuda_graph_update = False
+        use_graph = (self.cuda_graph_update and not self.use_bc_loss and not quantile_clip and n_max >= 16
+                     and total_steps >= self.batch_size)
+        step_fn = MinibatchStep(fwd_bwd, self.grads, self.actor_optimizer, self.critic_optimizer, with_actor,
+                                self.max_grad_norm, self.target_kl, n_max, self.batch_size, self.device, use_graph=use_graph,
+                                world=self.world)
+        if use_graph and step_fn.graphed is None:
+            log.warning("CUDA-graph capture of the PPO minibatch failed (%s); running eagerly", step_fn.graph_error)
+            self.cuda_graph_update = False
+        kl_state, history = step_fn.kl_state, step_fn.history
+        bc_last, launched, stopped = 0.0, 0, False
+        # The host looks at the flag with a fixed lag of LAG minibatches (it waits for the copy issued LAG launches ago, never
+        # for the current one): the GPU always has work queued, and every rank takes the same decision at the same minibatch
+        # (the all-reduce inside a minibatch needs all ranks to launch the same number of them).
+        LAG = 2
+        ring = [(torch.zeros(4, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(LAG + 1)]
         for update_epoch in range(self.update_epochs):
             inds_k = D.broadcast_permutation(total_steps, self.device)
+            in_epoch = 0
             for batch in range(num_batch):
                 inds_b = inds_k[batch * self.batch_size:(batch + 1) * self.batch_size]
-                bc_loss = step_fn(inds_b)
-                bc_loss = 0.0 if bc_loss is None else float(bc_loss)
-                s = self.grads.scalars.tolist()  # the one device->host read of the minibatch
-                stats = dict(pg_loss=s[0], v_loss=s[1], approx_kl=s[2], clipfrac=s[3], ratio=s[4], bc_loss=bc_loss,
-                             eta=eta_mean, loss=s[0] + ent_const * self.ent_coef + s[1] * self.vf_coef
-                             + bc_loss * self.bc_loss_coeff)
-                clipfracs.append(s[3])
-                if self.itr >= self.n_critic_warmup_itr:
-                    self.actor_optimizer.step(max_grad_norm=self.max_grad_norm)  # clip_grad_norm_ folded into the kernel
-                self.critic_optimizer.step()
-                if self.target_kl is not None and s[2] > self.target_kl:
-                    flag_break = True
-                    break
-            if flag_break:
+                bc = step_fn(inds_b)
+                bc_last = 0.0 if bc is None else float(bc)
+                launched += 1
+                in_epoch += 1
+                if use_target:
+                    buf, ev = ring[launched % (LAG + 1)]
+                    buf.copy_(kl_state, non_blocking=True)
+                    ev.record()
+                    if in_epoch > LAG:
+                        old_buf, old_ev = ring[(launched - LAG) % (LAG + 1)]
+                        old_ev.synchronize()
+                        if int(old_buf[0]):
+                            stopped = True
+                            break
+            if stopped:
                 break
+            if use_target:  # epoch boundary: exact test, the next permutation is drawn only if the reference would draw it
+                if int(kl_state[0].item()):
+                    stopped = True
+                    break
+        torch.cuda.current_stream().synchronize()
+        st = kl_state.tolist()
+        applied = st[1] + 1 if st[0] else launched  # minibatches whose optimiser steps took effect
+        flag_break = bool(st[0])
+        hist = history[:applied].cpu().numpy()
+        s = hist[-1]
+        stats = dict(pg_loss=float(s[0]), v_loss=float(s[1]), approx_kl=float(s[2]), clipfrac=float(s[3]), ratio=float(s[4]),
+                     bc_loss=bc_last, eta=eta_mean,
+                     loss=float(s[0]) + ent_const * self.ent_coef + float(s[1]) * self.vf_coef + bc_last * self.bc_loss_coeff)
+        clipfracs = [float(v) for v in hist[:, 3]]
+        step_fn.finish()  # version counters: the chain kernels repack actor_ft at the next rollout
         y_pred, y_true = values_k.cpu().numpy(), ret_k.cpu().numpy()
         var_y = np.var(y_true)
         stats["explained_var"] = np.nan if var_y == 0 else 1 - np.var(y_true - y_pred) / var_y
@@ -341,6 +371,15 @@ class TrainPPODiffusionAgent:
             self._sched["critic"] += 1
             self._apply_lr()
             self.model.step()
+            if id(self.model.actor_ft) != self._actor_ft_id:
+                # ft_denoising_steps was annealed (reference diffusion_vpg.py:102-127): actor_ft is a fresh copy the
+                # reference's optimiser never learns about - its parameter list still holds the old tensors, now the frozen
+                # base policy, whose gradients stay None, so actor training silently stops.  Same here: no further actor
+                # steps (and no weight decay / momentum on the base policy); the gradient buffer follows the new tensors.
+                log.warning("ft_denoising_steps annealed to %d: like the reference, the actor optimiser is not rebuilt - "
+                            "actor_ft is no longer updated", self.model.ft_denoising_steps)
+                self._actor_ft_id, self._actor_frozen = id(self.model.actor_ft), True
+                self.grads = D.FlatGradBuffer([list(self.model.actor_ft.parameters()), list(self.model.critic.parameters())])
             if self.itr % self.save_model_freq == 0 or self.itr == self.n_train_itr - 1:
                 self.save_model()
             rec = {"itr": self.itr, "step": cnt_train_step, "time": time.perf_counter() - t_start,

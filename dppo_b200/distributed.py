@@ -14,10 +14,14 @@ built so that W ranks reproduce the single-process arithmetic:
             reference minibatch bit-exactly; a remainder goes to the last rank.
 """
 
+import logging
+import os
 from typing import List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+log = logging.getLogger(__name__)
 
 
 def world() -> Tuple[int, int]:
@@ -64,13 +68,44 @@ def gather_env_dim(local: torch.Tensor, n_envs: int, env_dim: int = 1) -> torch.
 def broadcast_permutation(n: int, device, generator=None) -> torch.Tensor:
     """torch.randperm(n) drawn on rank 0 (the reference's call, train_ppo_diffusion_agent.py:311) and broadcast."""
     rank, W = world()
+    if W == 1:
+        return torch.randperm(n, device=device, generator=generator)
+    # the int64 permutation is drawn once (rank 0, the reference's generator stream); indices < 2^31 travel as int32
+    wire_dtype = torch.int32 if n < 2 ** 31 else torch.int64
     if rank == 0:
         perm = torch.randperm(n, device=device, generator=generator)
+        wire = perm.to(wire_dtype)
     else:
-        perm = torch.empty(n, dtype=torch.int64, device=device)
-    if W > 1:
-        dist.broadcast(perm, 0)
-    return perm
+        perm = None
+        wire = torch.empty(n, dtype=wire_dtype, device=device)
+    dist.broadcast(wire, 0)
+    return perm if rank == 0 else wire.to(torch.int64)
+
+
+def alloc_collective_buffer(n: int, device) -> Tuple[torch.Tensor, str]:
+    """Zeroed fp32 buffer of n elements for the per-minibatch gradient all-reduce.  Under NCCL it is allocated with
+    ncclMemAlloc and registered with the communicator (ProcessGroupNCCL.allocate_tensor, or a torch MemPool on the
+    backend's allocator + register_mem_pool), which makes it eligible for the zero-copy / NVLS (in-switch reduction) paths;
+    anything else - gloo in the CPU tests, a single process, an older torch - gets a plain allocation.  Returns
+    (tensor, how it was allocated).  DPPO_B200_NCCL_REGISTER=0 forces the plain path."""
+    dev = torch.device(device)
+    if (dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+            and os.environ.get("DPPO_B200_NCCL_REGISTER", "1") == "1"):
+        try:
+            backend = dist.group.WORLD._get_backend(dev)
+            if hasattr(backend, "supports_tensor_alloc") and backend.supports_tensor_alloc(dev):
+                t = backend.allocate_tensor(n, dtype=torch.float32, device=dev)
+                t.zero_()
+                return t, "ncclMemAlloc + registered (ProcessGroupNCCL.allocate_tensor)"
+            pool = torch.cuda.MemPool(backend.mem_allocator)
+            with torch.cuda.use_mem_pool(pool):
+                t = torch.zeros(n, dtype=torch.float32, device=dev)
+            backend.register_mem_pool(pool)
+            t._dppo_pool = pool  # keep the pool alive with the tensor
+            return t, "ncclMemAlloc + ncclCommRegister (torch MemPool on the NCCL allocator)"
+        except Exception as ex:  # noqa: BLE001 - registration is an optimisation
+            log.warning("NCCL buffer registration unavailable (%s: %s); plain allocation", type(ex).__name__, ex)
+    return torch.zeros(n, dtype=torch.float32, device=dev), "plain allocation"
 
 
 class FlatGradBuffer:
@@ -88,8 +123,9 @@ class FlatGradBuffer:
         self.params = [p for g in groups for p in g]
         n = sum((p.numel() + 3) // 4 * 4 for p in self.params)  # every tensor padded to 16 bytes (same layout as FlatAdamW)
         dev = self.params[0].device
-        self.flat = torch.zeros(n + n_scalars, dtype=torch.float32, device=dev)
+        self.flat, self.allocation = alloc_collective_buffer(n + n_scalars, dev)
         self.n_grad, self.n_scalars = n, n_scalars
+        self.group_sizes = [sum((p.numel() + 3) // 4 * 4 for p in g) for g in groups]
         o = 0
         for g in groups:
             for p in g:
@@ -112,3 +148,8 @@ class FlatGradBuffer:
         _, W = world()
         if W > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+    def segment(self, group: int) -> torch.Tensor:
+        """The contiguous gradient segment of parameter group `group` (e.g. 0 = actor_ft, 1 = critic)."""
+        o = sum(self.group_sizes[:group])
+        return self.flat[o:o + self.group_sizes[group]]

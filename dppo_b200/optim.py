@@ -45,8 +45,18 @@ class FlatAdamW:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self._ws = torch.zeros(2, dtype=torch.float64, device=dev)
         self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]
-        self.step_count = 0
+        # the step count lives on the device ([0] = count, [2..3] = bias corrections of the current step) so that a step
+        # captured in a CUDA graph advances its own bias correction on every replay (dppo_adamw_flat_dev)
+        self._state = torch.zeros(4, dtype=torch.int32, device=dev)
         self._grad_flat = None
+
+    @property
+    def step_count(self):
+        return int(self._state[0].item())
+
+    @step_count.setter
+    def step_count(self, v):
+        self._state[0] = int(v)
 
     def _grads(self):
         """The contiguous gradient segment (views handed out by FlatGradBuffer); verified once."""
@@ -67,20 +77,28 @@ class FlatAdamW:
         return self._grad_flat
 
     @torch.no_grad()
-    def step(self, max_grad_norm=None):
+    def step(self, max_grad_norm=None, stop_flag=None, bump=True):
+        """One AdamW step (stream-ordered, no host synchronisation, CUDA-graph capturable).  `stop_flag`: optional device
+        int32 tensor; once it is non-zero the launch is a no-op and the step count does not advance (KL early stop).
+        `bump=False` leaves the parameters' version counters alone (the caller bumps them after a graph replay)."""
         g = self._grads()
         if g.data_ptr() % 16:
             raise RuntimeError("FlatAdamW: gradient segment must be 16-byte aligned")
         hp = self.param_groups[0]
-        self.step_count += 1
         _lib.check(
-            self.lib.dppo_adamw_flat(_lib.ptr(self.flat), C.c_void_p(g.data_ptr()), _lib.ptr(self.exp_avg),
-                                     _lib.ptr(self.exp_avg_sq), self.n, float(hp["lr"]), float(hp["betas"][0]),
-                                     float(hp["betas"][1]), float(hp["eps"]), float(hp["weight_decay"]), self.step_count,
-                                     -1.0 if max_grad_norm is None else float(max_grad_norm), _lib.ptr(self._ws),
-                                     _lib.stream_ptr()),
-            "dppo_adamw_flat")
-        for p in self.params:  # the packed weight caches key on Tensor._version
+            self.lib.dppo_adamw_flat_dev(_lib.ptr(self.flat), C.c_void_p(g.data_ptr()), _lib.ptr(self.exp_avg),
+                                         _lib.ptr(self.exp_avg_sq), self.n, float(hp["lr"]), float(hp["betas"][0]),
+                                         float(hp["betas"][1]), float(hp["eps"]), float(hp["weight_decay"]),
+                                         _lib.ptr(self._state), _lib.ptr(stop_flag),
+                                         -1.0 if max_grad_norm is None else float(max_grad_norm), _lib.ptr(self._ws),
+                                         _lib.stream_ptr()),
+            "dppo_adamw_flat_dev")
+        if bump:
+            self.bump_versions()
+
+    def bump_versions(self):
+        """The packed weight caches (chain kernels) key on Tensor._version: mark the parameters as changed."""
+        for p in self.params:
             torch.autograd.graph.increment_version(p)
 
     def zero_grad(self, set_to_none=False):

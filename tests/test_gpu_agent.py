@@ -319,3 +319,63 @@ def test_graft_entry_smoke_runs():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_device_side_kl_early_stop_equals_host_loop(tmp_path, graph):
+    """The device stop flag (dppo_kl_check + no-op AdamW launches, polled with a lag) applies exactly the minibatches the
+    reference's host-side loop applies (train_ppo_diffusion_agent.py:313-382: step, then test approx_kl, then break)."""
+    from dppo_b200 import distributed as D
+
+    w, ag = _agent(tmp_path, n_envs=16, n_steps=8, batch_size=64, update_epochs=3)
+    ag.cuda_graph_update = graph
+    ag.cfg.train.actor_lr = 3e-3
+    for grp in ag.actor_optimizer.param_groups:
+        grp["lr"] = 3e-3  # large steps: approx_kl crosses the target after a few minibatches
+    ag.target_kl = 2e-4
+    firsts = np.zeros((ag.n_steps + 1, ag.n_envs))
+    obs_buf, chains_buf, rew, term, last_obs, _, _ = ag.rollout(ag.reset_env_all(), False, firsts)
+    values, logprobs, adv, ret = ag.prologue(obs_buf, chains_buf, rew, term, firsts, last_obs)
+    opts = (ag.actor_optimizer, ag.critic_optimizer)
+    snap = [(o.flat.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o._state.clone()) for o in opts]
+
+    def restore():
+        for o, (f, m, v, s) in zip(opts, snap):
+            o.flat.copy_(f), o.exp_avg.copy_(m), o.exp_avg_sq.copy_(v), o._state.copy_(s)
+            o.bump_versions()
+
+    torch.cuda.manual_seed(77)
+    stats = ag.update(obs_buf, chains_buf, logprobs, values, adv, ret)
+    got = [o.flat.clone() for o in opts]
+    steps_got = [o.step_count for o in opts]
+    n_total = 3 * (16 * 8 * w["ft_denoising_steps"] // 64)
+    assert 1 <= stats["minibatches"] < n_total, stats["minibatches"]  # the test tripped mid-way
+    assert stats["approx_kl"] > ag.target_kl
+
+    # the reference's loop on the host: same permutations, optimiser step, THEN the KL test
+    restore()
+    torch.cuda.manual_seed(77)
+    m, ft = ag.model, ag.model.ft_denoising_steps
+    N = ag.n_steps * ag.n_envs
+    obs_k, chains_k = obs_buf.view(N, 1, -1), chains_buf.view(N, ft + 1, *chains_buf.shape[3:])
+    lp_k = logprobs.view(N, ft, *logprobs.shape[3:])
+    done, stop = 0, False
+    for _ in range(ag.update_epochs):
+        perm = D.broadcast_permutation(N * ft, "cuda:0")
+        for b in range(N * ft // ag.batch_size):
+            ag.grads.zero()
+            m.update_minibatch(obs_k, chains_k, lp_k, ret.reshape(-1), values.reshape(-1), adv.reshape(-1),
+                               perm[b * ag.batch_size:(b + 1) * ag.batch_size], reward_horizon=ag.reward_horizon, vf_coef=ag.vf_coef,
+                               scalars_out=ag.grads.scalars)
+            ag.actor_optimizer.step()
+            ag.critic_optimizer.step()
+            done += 1
+            if float(ag.grads.scalars[2]) > ag.target_kl:
+                stop = True
+                break
+        if stop:
+            break
+    assert stop and done == stats["minibatches"]
+    assert [o.step_count for o in opts] == steps_got == [snap[0][3][0].item() + done, snap[1][3][0].item() + done]
+    for a, o in zip(got, opts):
+        assert float((a - o.flat).abs().max()) <= 2e-6 * max(1.0, float(o.flat.abs().max()))
