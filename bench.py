@@ -374,7 +374,9 @@ def run_b200(args, w, E, rank, world, local_rank):
                 line["hopper_50x_target"] = hopper_ratio(args, dev, cores)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        from dppo_b200 import distributed as D
+
+        D.shutdown()  # registered gradient buffers first, then the process group
 
 
 def hopper_ratio(args, dev, cores):

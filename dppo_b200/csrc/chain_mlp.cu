@@ -809,17 +809,17 @@ static LaunchShape pick_shape(const dppo_ctx* ctx, int E) {
     env_c = e ? atoi(e) : 0;
   }
   const int forced_ne = ctx->force_ne ? ctx->force_ne : env_ne, forced_c = ctx->force_c > 0 ? ctx->force_c : env_c;
-  const int max_clusters[4] = {ctx->sm_count, ctx->sm_count / 2, (ctx->sm_count - 16) / 4, 16};  // C = 1, 2, 4, 8
   LaunchShape best{cap, 1};
   double best_t = 1e30;
   for (int ci = 0; ci < 4; ++ci) {
     const int C = 1 << ci;
     if (g.MT % C) continue;
     if (forced_c > 0 && C != forced_c) continue;
-    for (int NE = 16; NE <= cap; NE *= 2) {
+    for (int NE = 16, ni = 0; NE <= cap; NE *= 2, ++ni) {
       if (forced_ne > 0 && NE != forced_ne) continue;
       const int tiles = (E + NE - 1) / NE;
-      const int waves = (tiles + max_clusters[ci] - 1) / max_clusters[ci];
+      const int max_clusters = ctx->chain_clusters[ni][ci] > 0 ? ctx->chain_clusters[ni][ci] : 1;  // co-resident clusters (occupancy query)
+      const int waves = (tiles + max_clusters - 1) / max_clusters;
       const double pairs = double(g.MT / C) * (g.KC0 + 2.0 * g.nb * g.KCH) + g.KCH;  // (hi, lo) tile pairs per step
       const double ingest = pairs * g.nsplit * 16384.0 / 34.7;
       const double per_mma = NE / 2.0 > 32.0 + NE / 4.0 ? NE / 2.0 : 32.0 + NE / 4.0;
@@ -853,6 +853,51 @@ static int launch(const ChainArgs& a, size_t smem_bytes, cudaStream_t st) {
   cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, a);
   if (e != cudaSuccess) return cuda_fail(e, "chain_mlp_kernel launch");
   return DPPO_OK;
+}
+
+// co-resident clusters of C CTAs of the chain kernel on this device, from the occupancy calculator (the GPC layout strands
+// SMs for the larger cluster sizes, so sm_count / C overestimates)
+template <int NE, int ACT, bool LN>
+static int query_clusters_t(int C, size_t smem_bytes) {
+  auto kfn = chain_mlp_kernel<NE, ACT, LN>;
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(C) * 148), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(C), attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static void fill_chain_clusters(dppo_ctx* ctx) {
+  const MlpGeom& g = ctx->g;
+  const int fallback[4] = {ctx->sm_count, ctx->sm_count / 2, (ctx->sm_count - 16) / 4, 16};
+  for (int ni = 0; ni < 3; ++ni) {
+    const int NE = 16 << ni;
+    const size_t fixed = smem_fixed_bytes(g, NE);
+    for (int ci = 0; ci < 4; ++ci) {
+      const int C = 1 << ci;
+      int n = 0;
+      if (fixed + 2 * kTile <= 232448) {
+        size_t nst = (232448 - fixed) / kTile;
+        if (nst > size_t(kMaxStages)) nst = kMaxStages;
+        const size_t smem = fixed + nst * kTile;
+#define DPPO_Q(NE_, ACT_) (g.ln ? query_clusters_t<NE_, ACT_, true>(C, smem) : query_clusters_t<NE_, ACT_, false>(C, smem))
+#define DPPO_QA(NE_) (g.act == DPPO_ACT_RELU ? DPPO_Q(NE_, DPPO_ACT_RELU) : DPPO_Q(NE_, DPPO_ACT_MISH))
+        n = NE == 64 ? DPPO_QA(64) : (NE == 32 ? DPPO_QA(32) : DPPO_QA(16));
+#undef DPPO_QA
+#undef DPPO_Q
+      }
+      ctx->chain_clusters[ni][ci] = n > 0 ? n : fallback[ci];
+    }
+  }
+  ctx->chain_clusters_known = true;
 }
 
 int small_chain_capacity(const dppo_ctx* ctx);
@@ -900,6 +945,7 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
   a.prof = ctx->d_prof;
 
+  if (!ctx->chain_clusters_known) fill_chain_clusters(ctx);
   const LaunchShape shape = pick_shape(ctx, E);
   const int NE = shape.NE;
   a.C = shape.C;
@@ -928,3 +974,16 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
 }
 
 }  // namespace dppo
+
+// bring-up: the launch shape the cost model picks for E environments and the occupancy table it uses (12 ints)
+extern "C" int dppo_debug_get_shape(dppo_ctx* ctx, int E, int* tile_envs, int* cluster, int* table) {
+  using namespace dppo;
+  if (!ctx || ctx->kind != 0) return DPPO_ERR_INVALID;
+  if (!ctx->chain_clusters_known) fill_chain_clusters(ctx);
+  const LaunchShape s = pick_shape(ctx, E);
+  if (tile_envs) *tile_envs = s.NE;
+  if (cluster) *cluster = s.C;
+  if (table)
+    for (int i = 0; i < 12; ++i) table[i] = ctx->chain_clusters[i / 4][i % 4];
+  return DPPO_OK;
+}

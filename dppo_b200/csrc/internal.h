@@ -89,6 +89,8 @@ struct dppo_ctx {
   const float** d_unet_params[2] = {nullptr, nullptr};
   int sample_dim = 0;  // Ta * Da of either denoiser kind
   int small_clusters = 0;  // 16-CTA clusters of the weights-stationary small-batch kernel the device co-schedules
+  int chain_clusters[3][4] = {};  // co-resident clusters of the MLP chain kernel per (tile envs 16/32/64, cluster size 1/2/4/8)
+  bool chain_clusters_known = false;
   int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

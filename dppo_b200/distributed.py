@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 log = logging.getLogger(__name__)
+_LIVE_BUFFERS = []  # the FlatGradBuffers whose storage is registered with the NCCL communicator (until release())
 
 
 def world() -> Tuple[int, int]:
@@ -124,6 +125,8 @@ class FlatGradBuffer:
         n = sum((p.numel() + 3) // 4 * 4 for p in self.params)  # every tensor padded to 16 bytes (same layout as FlatAdamW)
         dev = self.params[0].device
         self.flat, self.allocation = alloc_collective_buffer(n + n_scalars, dev)
+        if self.allocation != "plain allocation":
+            _LIVE_BUFFERS.append(self)  # the .grad views keep the storage alive anyway; shutdown() must be able to find it
         self.n_grad, self.n_scalars = n, n_scalars
         self.group_sizes = [sum((p.numel() + 3) // 4 * 4 for p in g) for g in groups]
         o = 0
@@ -149,7 +152,31 @@ class FlatGradBuffer:
         if W > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
+    def release(self):
+        """Drop the buffer (the parameters' .grad views included).  A buffer registered with the NCCL communicator must be
+        gone before the process group is destroyed: destroy_process_group() with a live ncclMemAlloc'ed tensor hangs
+        (observed on 2 x B200, torch 2.11 / NCCL 2.28) - shutdown() below does both in the right order."""
+        for p in self.params:
+            p.grad = None
+        self.flat = None
+        if self in _LIVE_BUFFERS:
+            _LIVE_BUFFERS.remove(self)
+
     def segment(self, group: int) -> torch.Tensor:
         """The contiguous gradient segment of parameter group `group` (e.g. 0 = actor_ft, 1 = critic)."""
         o = sum(self.group_sizes[:group])
         return self.flat[o:o + self.group_sizes[group]]
+
+
+def shutdown():
+    """Release every NCCL-registered gradient buffer, then destroy the process group (no-op without one)."""
+    import gc
+
+    for buf in list(_LIVE_BUFFERS):
+        buf.release()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

@@ -59,21 +59,20 @@ class FlatAdamW:
         self._state[0] = int(v)
 
     def _grads(self):
-        """The contiguous gradient segment (views handed out by FlatGradBuffer); verified once."""
-        if self._grad_flat is not None and self._grad_flat.data_ptr() == self.params[0].grad.data_ptr():
-            return self._grad_flat
+        """Device address of the contiguous gradient segment (views handed out by FlatGradBuffer); the layout is verified
+        once per buffer.  Only the address is cached - no tensor that would keep a (possibly NCCL-registered) gradient
+        buffer alive behind FlatGradBuffer.release()."""
         first = self.params[0].grad
         if first is None:
             raise RuntimeError("FlatAdamW.step: parameters have no gradients")
+        if self._grad_flat == first.data_ptr():
+            return self._grad_flat
         ptr = first.data_ptr()
         for p in self.params:
             if p.grad is None or p.grad.data_ptr() != ptr or not p.grad.is_contiguous():
                 raise RuntimeError("FlatAdamW needs gradients laid out contiguously in parameter order (FlatGradBuffer)")
             ptr += (p.numel() + 3) // 4 * 16
-        base = first.untyped_storage()
-        off = (first.data_ptr() - base.data_ptr()) // 4
-        whole = torch.empty(0, dtype=torch.float32, device=first.device).set_(base)
-        self._grad_flat = whole[off:off + self.n]
+        self._grad_flat = first.data_ptr()
         return self._grad_flat
 
     @torch.no_grad()
@@ -82,11 +81,11 @@ class FlatAdamW:
         int32 tensor; once it is non-zero the launch is a no-op and the step count does not advance (KL early stop).
         `bump=False` leaves the parameters' version counters alone (the caller bumps them after a graph replay)."""
         g = self._grads()
-        if g.data_ptr() % 16:
+        if g % 16:
             raise RuntimeError("FlatAdamW: gradient segment must be 16-byte aligned")
         hp = self.param_groups[0]
         _lib.check(
-            self.lib.dppo_adamw_flat_dev(_lib.ptr(self.flat), C.c_void_p(g.data_ptr()), _lib.ptr(self.exp_avg),
+            self.lib.dppo_adamw_flat_dev(_lib.ptr(self.flat), C.c_void_p(g), _lib.ptr(self.exp_avg),
                                          _lib.ptr(self.exp_avg_sq), self.n, float(hp["lr"]), float(hp["betas"][0]),
                                          float(hp["betas"][1]), float(hp["eps"]), float(hp["weight_decay"]),
                                          _lib.ptr(self._state), _lib.ptr(stop_flag),

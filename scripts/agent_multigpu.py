@@ -33,4 +33,6 @@ if rank == 0:
     print(f"{name}: world {world}, envs/rank {ag.n_envs}, itrs {len(res)}, pg_loss {last['pg_loss']:.4e} v_loss {last['v_loss']:.4e} "
           f"kl {last['approx_kl']:.3e} minibatches {last['minibatches']}  params+stats identical on all ranks: {bool(ok.item())}")
     assert ok.item() == 1
-dist.destroy_process_group()
+from dppo_b200 import distributed as D
+
+D.shutdown()  # registered gradient buffers first, then the process group
