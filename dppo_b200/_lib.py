@@ -18,11 +18,10 @@ PRECISIONS = {"split3": PRECISION_SPLIT3, "bf16": PRECISION_BF16}
 # every symbol include/dppo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "dppo_last_error", "dppo_version", "dppo_ctx_create", "dppo_ctx_destroy", "dppo_pack_mlp", "dppo_ctx_create_unet",
-    "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain",
+    "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain", "dppo_sample_nonfinite",
     "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64", "dppo_split3_pack", "dppo_reward_scale_f64", "dppo_adamw_flat",
     "dppo_update_create", "dppo_update_destroy", "dppo_update_bind", "dppo_update_forward", "dppo_update_backward",
     "dppo_update_minibatch", "dppo_update_buffers", "dppo_memset_zero", "dppo_adamw_flat_dev", "dppo_kl_check",
-    "dppo_selftest_umma",
 ]
 
 
@@ -128,6 +127,7 @@ def load(build_if_missing=True):
                  "dppo_unet_plan_dense", "dppo_unet_plan_side"):
         getattr(lib, name).restype = i32
     lib.dppo_sample_chain.argtypes = [vp, vp, i32, vp, u64, u64, i64, i32, i32, f32, vp, vp, vp]
+    lib.dppo_sample_nonfinite.argtypes = [vp, C.POINTER(C.c_int), i32, vp]
     lib.dppo_chain_logprobs.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.dppo_logprob_rows.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.dppo_ppo_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, C.POINTER(LossHp), vp, vp,
@@ -137,7 +137,6 @@ def load(build_if_missing=True):
     lib.dppo_split3_pack.argtypes = [vp, i64, i32, i64, i32, vp, vp, i32, vp]
     lib.dppo_reward_scale_f64.argtypes = [vp, vp, i32, i32, C.c_longlong, f64, f64, f64, vp, vp, vp, vp, vp, i32, vp]
     lib.dppo_adamw_flat.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp]
-    lib.dppo_selftest_umma.argtypes = [vp, vp, vp, vp, i32, i32, u64, C.c_uint32, vp]
     lib.dppo_update_create.argtypes = [C.POINTER(vp), vp, C.POINTER(ResMlpDesc), i32]
     lib.dppo_update_destroy.argtypes = [vp]
     lib.dppo_update_bind.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp), i32]
@@ -159,6 +158,25 @@ def load(build_if_missing=True):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib
+
+
+_test_lib = None
+
+
+def load_test():
+    """The test-only library (tcgen05 descriptor self-test + micro-benchmarks, csrc/umma_selftest.cu, csrc/microbench.cu)."""
+    global _test_lib
+    if _test_lib is None:
+        load()
+        path = os.path.join(_HERE, "lib", "libdppo_b200_test.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built; run `python -m dppo_b200.build`")
+        lib = C.CDLL(path)
+        vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+        lib.dppo_selftest_umma.argtypes = [vp, vp, vp, vp, i32, i32, u64, C.c_uint32, vp]
+        lib.dppo_selftest_umma.restype = i32
+        _test_lib = lib
+    return _test_lib
 
 
 def check(rc, what):

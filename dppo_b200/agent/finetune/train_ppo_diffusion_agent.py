@@ -339,6 +339,8 @@ class TrainPPODiffusionAgent:
             obs_buf, chains_buf, reward_trajs, terminated_trajs, prev_obs_venv, done_venv, env_steps = self.rollout(
                 prev_obs_venv, eval_mode, firsts_trajs)
             torch.cuda.synchronize()
+            if self.model.engine(sync=False).nonfinite():  # the reference documents NaN observations from IsaacGym (README.md:184)
+                log.warning("itr %d: the sampler produced non-finite actions (NaN / Inf observations or diverged weights)", self.itr)
             t_roll = time.perf_counter() - t0
             cnt_train_step += env_steps * (self.n_envs_global // max(1, self.n_envs)) if self.world > 1 else env_steps
 

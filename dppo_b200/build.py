@@ -13,16 +13,19 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libdppo_b200.so")
-SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "update_gemm.cu", "update_plan.cu", "umma_selftest.cu", "microbench.cu"]
+SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "update_gemm.cu", "update_plan.cu"]
+# bring-up code (descriptor self-test, micro-benchmarks) lives in its own test-only library, not in the product .so
+TEST_LIB = os.path.join(PKG, "lib", "libdppo_b200_test.so")
+TEST_SOURCES = ["umma_selftest.cu", "microbench.cu"]
 HEADERS = ["common.cuh", "internal.h", "unet_plan.h", "update_gemm.h", os.path.join("..", "..", "include", "dppo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(TEST_LIB):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(TEST_LIB))
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + TEST_SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
@@ -45,12 +48,13 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
         return obj, res.stdout + res.stderr
 
-    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
-        results = list(pool.map(compile_one, SOURCES))
-    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [o for o, _ in results] + ["-o", LIB]
-    res = subprocess.run(link, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES) + len(TEST_SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES + TEST_SOURCES))
+    for objs, out in ((results[:len(SOURCES)], LIB), (results[len(SOURCES):], TEST_LIB)):
+        link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [o for o, _ in objs] + ["-o", out]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     if verbose:
         print("".join(out for _, out in results) + res.stdout + res.stderr)
     return LIB

@@ -173,6 +173,8 @@ static int ctx_create_common(dppo_ctx** out, const dppo_mlp_desc* mlp, const dpp
     if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && dev_sms > 0)
       c->sm_count = dev_sms;
     cudaError_t e = cudaMalloc(&c->d_rows, sizeof(StepRow) * c->S);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_nonfinite, 16);
+    if (e == cudaSuccess) e = cudaMemset(c->d_nonfinite, 0, 16);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_rows, c->rows.data(), sizeof(StepRow) * c->S, cudaMemcpyHostToDevice);
     const size_t blob = unet ? c->unet->n_tiles * 16384 : c->g.blob_bytes;
     const size_t n_side = unet ? c->unet->n_side : c->g.n_side;
@@ -225,6 +227,7 @@ extern "C" int dppo_unet_param_count(const dppo_unet_desc* actor) {
 extern "C" int dppo_ctx_destroy(dppo_ctx* c) {
   if (!c) return DPPO_OK;
   cudaFree(c->d_rows);
+  cudaFree(c->d_nonfinite);
   for (int w = 0; w < 2; ++w) {
     cudaFree(c->nets[w].tiles);
     cudaFree(c->nets[w].side);
@@ -279,6 +282,15 @@ extern "C" int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const floa
   return (ctx->kind == 1 ? sample_chain_unet_impl : sample_chain_impl)(
       ctx, state, n_rows, nullptr, 0, 0, 0, 0, use_base_policy, ctx->min_logprob_std, nullptr, nullptr, chains, logp,
       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dppo_sample_nonfinite(dppo_ctx* ctx, int* flag, int reset, void* stream) {
+  if (!ctx || !flag) return set_error("dppo_sample_nonfinite: null argument"), DPPO_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DPPO_CUDA(cudaMemcpyAsync(flag, ctx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DPPO_CUDA(cudaStreamSynchronize(st));
+  if (reset && *flag) DPPO_CUDA(cudaMemsetAsync(ctx->d_nonfinite, 0, sizeof(int), st));
+  return DPPO_OK;
 }
 
 // bring-up hook (not in the public header): the chain kernel writes 8 cycle counters per CTA into `buf`

@@ -67,6 +67,7 @@ struct ChainArgs {
   uint64_t seed, offset;
   int64_t env_offset;
   unsigned long long* prof;  // optional [grid][16] cycle counters (bring-up / profiling), nullptr in production
+  int* nonfinite;            // OR-ed with 1 when a final action element is NaN / Inf (NaN observations, diverged weights)
 };
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
@@ -757,7 +758,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
                 if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
                 if (rank == 0) {
                   if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
-                  if (last) a.traj[size_t(env) * a.D + f] = xn;
+                  if (last) {
+                    a.traj[size_t(env) * a.D + f] = xn;
+                    if (!(fabsf(xn) <= 3.0e38f)) atomicOr(a.nonfinite, 1);
+                  }
                 }
               }
             }
@@ -944,6 +948,7 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   a.state = state, a.E = E, a.noise = noise, a.traj = traj, a.chain = chain, a.chains_in = chains_in, a.logp = logp;
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
   a.prof = ctx->d_prof;
+  a.nonfinite = ctx->d_nonfinite;
 
   if (!ctx->chain_clusters_known) fill_chain_clusters(ctx);
   const LaunchShape shape = pick_shape(ctx, E);

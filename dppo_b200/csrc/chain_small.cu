@@ -46,6 +46,7 @@ struct SmallArgs {
   float* chain;
   uint64_t seed, offset;
   int64_t env_offset;
+  int* nonfinite;  // OR-ed with 1 when a final action element is NaN / Inf
 };
 
 __device__ __forceinline__ float philox_normal_s(uint64_t seed, uint64_t offset, uint64_t elem, uint32_t slot) {
@@ -263,7 +264,10 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
         if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
         if (lane == 0) {
           if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + j] = xn;
-          if (last) a.traj[size_t(env) * a.D + j] = xn;
+          if (last) {
+            a.traj[size_t(env) * a.D + j] = xn;
+            if (!(fabsf(xn) <= 3.0e38f)) atomicOr(a.nonfinite, 1);
+          }
         }
         if (lane < kCS) st_remote_f32(x0 + e * K0p + j, uint32_t(lane), xn);
       }
@@ -334,6 +338,7 @@ int sample_chain_small_impl(dppo_ctx* ctx, const float* state, int E, const floa
   a.eps_clip = ctx->eps_clip;
   a.state = state, a.noise = noise, a.traj = traj, a.chain = chain;
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
+  a.nonfinite = ctx->d_nonfinite;
   // spread the environments over as many clusters as the device co-schedules
   const int clusters = E < ctx->small_clusters ? E : ctx->small_clusters;
   const int epc = (E + clusters - 1) / clusters;

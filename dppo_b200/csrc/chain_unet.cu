@@ -59,6 +59,7 @@ struct UArgs {
   uint64_t seed, offset;
   int64_t env_offset;
   unsigned long long* prof;  // optional [grid][16] cycle counters (bring-up / profiling), nullptr in production
+  int* nonfinite;            // OR-ed with 1 when a final action element is NaN / Inf
 };
 
 // Philox4x32-10 keyed exactly like chain_mlp.cu (same draws for the same (seed, offset, element, slot))
@@ -595,7 +596,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
                 xn = mu + stdv * zreg[j];
                 if (last && a.final_clip >= 0.f) xn = fminf(fmaxf(xn, -a.final_clip), a.final_clip);
                 if (a.chain && row.slot >= 0) a.chain[(size_t(env) * (a.ft + 1) + row.slot) * a.D + f] = xn;
-                if (last) a.traj[size_t(env) * a.D + f] = xn;
+                if (last) {
+                  a.traj[size_t(env) * a.D + f] = xn;
+                  if (!(fabsf(xn) <= 3.0e38f)) atomicOr(a.nonfinite, 1);
+                }
               }
             }
             xreg[j] = xn;
@@ -707,6 +711,7 @@ int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float
   a.state = state, a.E = E, a.noise = noise, a.traj = traj, a.chain = chain, a.chains_in = chains_in, a.logp = logp;
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
   a.prof = ctx->d_prof;
+  a.nonfinite = ctx->d_nonfinite;
 
   const UShape shape = pick_unet_shape(ctx, E);
   const int NE = shape.NE;

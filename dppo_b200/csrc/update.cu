@@ -661,6 +661,8 @@ extern "C" int dppo_logprob_rows(dppo_ctx* ctx, const float* eps, const float* x
 static int loss_impl(dppo_ctx* ctx, LossArgs a, const int64_t* stat_inds, const dppo_loss_hp* hp, float* scalars,
                      void* workspace, void* stream, const char* who) {
   const int D = ctx->sample_dim;
+  // the row kernels hold one sample (Ta * Da elements) in one group of <= 32 lanes x 4 elements
+  if (D < 1 || D > 128) return set_error("%s: Ta * Da = %d outside [1, 128]", who, D), DPPO_ERR_UNSUPPORTED;
   if (a.n_rows < 0 || a.global_rows < 1 || a.n_rows > a.global_rows)
     return set_error("%s: bad row counts %d of %d", who, a.n_rows, a.global_rows), DPPO_ERR_INVALID;
   if (hp->ft_denoising_steps != ctx->ft || hp->horizon_steps * hp->action_dim != D)
@@ -676,7 +678,7 @@ static int loss_impl(dppo_ctx* ctx, LossArgs a, const int64_t* stat_inds, const 
   DPPO_CUDA(cudaMemsetAsync(reinterpret_cast<int*>(ws + 6) + 1, 0x80, sizeof(int), st));  // max key: below every float
   {
     int blocks = (a.global_rows + 255) / 256;
-    blocks = blocks > 296 ? 296 : blocks;
+    blocks = blocks > 2 * device_sm_count() ? 2 * device_sm_count() : blocks;
     adv_partial_kernel<<<blocks, 256, 0, st>>>(a.adv, stat_inds, a.global_rows, ctx->ft, ws);
     adv_finalize_kernel<<<1, 1, 0, st>>>(a.global_rows, ws);
   }

@@ -241,6 +241,12 @@ class ChainEngine:
             "dppo_sample_chain")
         return traj, chain
 
+    def nonfinite(self, reset=True):
+        """True when a sampling launch since the last reset produced a NaN / Inf action element (synchronises the stream)."""
+        flag = C.c_int(0)
+        _lib.check(self.lib.dppo_sample_nonfinite(self.ctx, C.byref(flag), int(reset), _lib.stream_ptr()), "dppo_sample_nonfinite")
+        return bool(flag.value)
+
     def chain_logprobs(self, state, chains, use_base_policy=False):
         B = chains.shape[0]
         state = state.reshape(B, -1).contiguous().float()

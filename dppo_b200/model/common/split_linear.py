@@ -10,7 +10,7 @@ The update path of DPPO (PPODiffusion.loss -> get_logprobs_subsample -> actor_ft
 over the 3K-long rows (a plain library GEMM: torch.mm(..., out_dtype=float32) -> cuBLASLt) is the whole product.
 forward: y = [x | 1] [W | b]^T (the bias rides along as one more K column);  backward: dx = dy W (same trick on dy and
 W^T), [dW | db] = dy^T [x | 1] (three small-output GEMMs on the hi / lo column blocks of the packed operands).  Parameters, names and state_dict are nn.Linear's.
-On CPU tensors (oracle / host-logic tests) the module is plain F.linear.
+CPU tensors are refused unless the host-logic tests switch CPU_TEST_HOOK on (then plain F.linear).
 """
 
 import ctypes as C
@@ -22,6 +22,14 @@ from torch import nn
 from dppo_b200 import _lib
 
 ENABLED = True  # module-level switch (tests compare both paths)
+# Test hook, OFF in production: evaluating these modules on CPU tensors (stock torch kernels) is something only the host
+# logic tests do (tests/conftest.py switches it on); a product run that ends up with CPU tensors here fails loudly.
+CPU_TEST_HOOK = False
+
+
+def require_cuda(x, who):
+    if not x.is_cuda and not CPU_TEST_HOOK:
+        raise RuntimeError(f"{who}: CPU tensors - dppo_b200 has no CPU path (tests enable split_linear.CPU_TEST_HOOK explicitly)")
 
 
 def _pack(x2d, pattern, ones=False, extra=None):
@@ -77,6 +85,7 @@ class SplitLinear(nn.Linear):
     """Drop-in nn.Linear (same parameters / state_dict); CUDA fp32 inputs take the split-3 tensor-core path."""
 
     def forward(self, x):
+        require_cuda(x, "SplitLinear")
         # (a 1-wide value head is a GEMV: not worth three operand passes, and an odd leading dimension suits no tensor-core tile)
         if ENABLED and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32 and self.out_features >= 8:
             return _Split3Linear.apply(x, self.weight, self.bias)

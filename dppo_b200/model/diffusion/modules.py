@@ -52,6 +52,9 @@ class FastGroupNorm(nn.GroupNorm):
     minibatch on (B, C, 1, 4) tensors - followed by the per-channel affine; numerically the same biased-variance formula."""
 
     def forward(self, x):
+        from dppo_b200.model.common.split_linear import require_cuda
+
+        require_cuda(x, "FastGroupNorm")  # CPU tensors only under the explicit test hook
         if not (x.is_cuda and x.is_contiguous() and x.dim() >= 3):
             return super().forward(x)
         return self.via_layer_norm(x)

@@ -160,6 +160,11 @@ int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, const float
                       uint64_t offset, int64_t env_offset, int deterministic, int use_base_policy,
                       float min_sampling_denoising_std, float* traj, float* chain, void* stream);
 
+/* NaN / Inf guard (the reference documents NaN observations from IsaacGym, README.md:184): every dppo_sample_chain
+ * launch ORs a device flag when an element of `traj` is not finite.  This call copies the flag to *flag (HOST int; it
+ * synchronises `stream`) and, with reset != 0, clears it.  The sampling calls themselves never synchronise.        */
+int dppo_sample_nonfinite(dppo_ctx* ctx, int* flag, int reset, void* stream);
+
 /* Replaces VPGDiffusion.get_logprobs (diffusion_vpg.py:319-396): log-density of every fine-tuned transition of
  * stored chains, network evaluation included.
  *   state [Bc, cond_dim], chains [Bc, ft+1, Ta*Da]  ->  logp [Bc*ft, Ta*Da]  (row = env-major, denoise-minor)   */
@@ -324,12 +329,6 @@ int dppo_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float
  * host may poll the flag lazily instead of synchronising on every minibatch.  state: 4 device ints, zeroed per update. */
 int dppo_kl_check(const float* scalars, float target_kl, int use_target, int* state, float* history, int max_history,
                   void* stream);
-
-/* ---- bring-up ------------------------------------------------------------------------------------------------- */
-/* Single-CTA tcgen05 GEMM that validates the shared-memory / instruction descriptor encodings on hardware:
- * c[128,N] = a[128,K] * b[N,K]^T in bf16 with fp32 accumulation.  scratch >= K/64 * 16 KiB.                      */
-int dppo_selftest_umma(const float* a, const float* b, float* c, void* scratch, int N, int K, uint64_t desc_hi,
-                       uint32_t idesc, void* stream);
 
 #ifdef __cplusplus
 }

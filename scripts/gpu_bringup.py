@@ -15,7 +15,7 @@ STAGES = {
     "selftest": """
 import torch
 from dppo_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_test()
 g = torch.Generator().manual_seed(0)
 for N, K in [(32, 64), (64, 64), (64, 128), (64, 256)]:
     a = torch.randn(128, K, generator=g).cuda(); b = torch.randn(N, K, generator=g).cuda()

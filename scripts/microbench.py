@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, ".")
 from dppo_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_test()
 lib.dppo_debug_mma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.dppo_debug_stream_rate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 out = torch.zeros(256, dtype=torch.int64, device="cuda")

@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, ".")
 from dppo_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_test()
 lib.dppo_debug_tmem_read_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 out = torch.zeros(16, dtype=torch.int64, device="cuda")
 names = {0: "x16 + wait each", 1: "x32 + wait each", 2: "2 x x32, one wait", 3: "4 x x32, one wait", 4: "4 x x16, one wait"}

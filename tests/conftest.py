@@ -8,6 +8,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# host-logic tests evaluate the parameter containers on CPU tensors: an explicit test hook, off in production
+from dppo_b200.model.common import split_linear as _sl  # noqa: E402
+
+_sl.CPU_TEST_HOOK = True
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -40,7 +40,7 @@ def _setup(case, precision="split3"):
 def test_umma_descriptor_selftest():
     from dppo_b200 import _lib
 
-    lib = _lib.load()
+    lib = _lib.load_test()  # bring-up code lives in the test-only library
     g = torch.Generator(device="cpu").manual_seed(0)
     for N, K in [(32, 64), (64, 128), (64, 256)]:
         a = torch.randn(128, K, generator=g).cuda()
