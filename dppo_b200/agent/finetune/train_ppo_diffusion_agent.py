@@ -125,6 +125,12 @@ class TrainPPODiffusionAgent:
 
         # gradients of both networks + 8 diagnostics in ONE flat buffer -> one all-reduce per minibatch
         self.grads = D.FlatGradBuffer([list(self.model.actor_ft.parameters()), list(self.model.critic.parameters())])
+        # parity-test hooks (tests/test_gpu_agent.py, agent-level golden): "noise" -> callable(E) returning the (S+1, E, Ta, Da)
+        # draws of one decision (instead of in-kernel Philox), "perm" -> callable(n) returning the minibatch permutation
+        # (instead of torch.randperm on the device: a recorded CPU permutation stream cannot be reproduced by the CUDA
+        # generator).  Empty in production.
+        self.test_hooks = {}
+        self.last_history = None  # per-minibatch diagnostics [pg, v, kl, clipfrac, ratio, ...] of the last update()
         self._actor_ft_id = id(self.model.actor_ft)
         self._actor_frozen = False
         self.timings = {}
@@ -173,8 +179,9 @@ class TrainPPODiffusionAgent:
             obs_buf[step].copy_(pinned_obs, non_blocking=True)
             # the kernel stores the chains straight into the device-resident rollout buffer and the action chunk straight
             # into pinned host memory: no copy launches after it
+            noise = self.test_hooks["noise"](E).to(dev) if "noise" in self.test_hooks else None
             self.model(cond={"state": obs_buf[step]}, deterministic=eval_mode, return_chain=True, env_offset=self.env_begin,
-                       out_trajectories=pinned_act, out_chains=chains_buf[step])
+                       out_trajectories=pinned_act, out_chains=chains_buf[step], noise=noise)
             torch.cuda.current_stream().synchronize()  # the simulator needs the action chunk on the host
             action_venv = pinned_act.numpy()[:, : self.act_steps]
             obs_venv, reward_venv, terminated_venv, truncated_venv, _ = self.venv.step(action_venv)
@@ -275,7 +282,10 @@ class TrainPPODiffusionAgent:
         LAG = 2
         ring = [(torch.zeros(4, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(LAG + 1)]
         for update_epoch in range(self.update_epochs):
-            inds_k = D.broadcast_permutation(total_steps, self.device)
+            if "perm" in self.test_hooks:
+                inds_k = self.test_hooks["perm"](total_steps).to(self.device)
+            else:
+                inds_k = D.broadcast_permutation(total_steps, self.device)
             in_epoch = 0
             for batch in range(num_batch):
                 inds_b = inds_k[batch * self.batch_size:(batch + 1) * self.batch_size]
@@ -304,6 +314,7 @@ class TrainPPODiffusionAgent:
         applied = st[1] + 1 if st[0] else launched  # minibatches whose optimiser steps took effect
         flag_break = bool(st[0])
         hist = history[:applied].cpu().numpy()
+        self.last_history = hist
         s = hist[-1]
         stats = dict(pg_loss=float(s[0]), v_loss=float(s[1]), approx_kl=float(s[2]), clipfrac=float(s[3]), ratio=float(s[4]),
                      bc_loss=bc_last, eta=eta_mean,

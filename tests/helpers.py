@@ -171,3 +171,39 @@ def oracle_params(model, requires_grad=False):
             t.requires_grad_(True)
         out[k] = t
     return out
+
+
+def agent_golden_cfg(device, logdir, reference=False, target_kl=None):
+    """Config of the agent-level golden run (tests/golden/make_golden_agent.py): Hopper-shaped, small networks, 3 iterations
+    with one critic warm-up iteration, LR warm-up, several minibatches per epoch.  `reference=True` points the `_target_`
+    nodes at the reference classes and adds the keys only the reference constructor reads."""
+    from dppo_b200.workloads import get_workload, make_agent_cfg
+
+    w = get_workload("hopper")
+    w["actor"] = dict(w["actor"], mlp_dims=[128, 128, 128])
+    w["critic"] = dict(w["critic"], mlp_dims=[128, 128, 128])
+    w["train"] = dict(w["train"], actor_lr=2e-3, critic_lr=1e-3, n_critic_warmup_itr=1)
+    cfg = make_agent_cfg(w, device, logdir, n_envs=8, n_steps=6, n_train_itr=3, batch_size=96, update_epochs=2)
+    cfg.env.reset_at_iteration = True
+    cfg.train.actor_lr_scheduler = type(cfg)(first_cycle_steps=10, warmup_steps=2, min_lr=2e-4)
+    cfg.train.critic_lr_scheduler = type(cfg)(first_cycle_steps=10, warmup_steps=2, min_lr=1e-4)
+    cfg.train.target_kl = AGENT_GOLDEN_TARGET_KL if target_kl is None else target_kl
+    cfg.train.logprob_batch_size = 16  # several chunks in the old-log-prob prologue (a multiple of n_envs, train_ppo_agent.py:24)
+    if reference:
+        def retarget(node):
+            for k, v in list(node.items()):
+                if isinstance(v, dict):
+                    retarget(v)
+                elif k == "_target_":
+                    node[k] = v.replace("dppo_b200.", "dppo.")
+        retarget(cfg.model)
+        cfg.model.pop("engine_precision", None)
+        cfg.wandb = None
+        cfg.train.render = type(cfg)(freq=10 ** 9, num=0)
+        cfg.train.save_trajs = False
+        cfg.env.save_video = False
+    return cfg
+
+
+# chosen between two well separated approx_kl values of the recorded reference run (printed by make_golden_agent.py)
+AGENT_GOLDEN_TARGET_KL = 7.5e-5

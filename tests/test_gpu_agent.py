@@ -379,3 +379,71 @@ def test_device_side_kl_early_stop_equals_host_loop(tmp_path, graph):
     assert [o.step_count for o in opts] == steps_got == [snap[0][3][0].item() + done, snap[1][3][0].item() + done]
     for a, o in zip(got, opts):
         assert float((a - o.flat).abs().max()) <= 2e-6 * max(1.0, float(o.flat.abs().max()))
+
+
+def test_agent_run_matches_reference_run_golden(tmp_path):
+    """Three iterations of TrainPPODiffusionAgent.run against the UNMODIFIED reference loop (tests/golden/agent_run.npz,
+    recorded by make_golden_agent.py under the SURVEY §8c shim): same synthetic env, same injected draws, same recorded
+    permutations.  Checks, per minibatch, the loss diagnostics and the sums of the loss inputs (reward scaling -> GAE with
+    the bootstrap on the post-rollout observation -> tail-row drop -> (b, d) indexing), per iteration the number of
+    minibatches (KL early stop in the last one) and the learning rates (critic warm-up, LR warm-up), and at the end the
+    parameters of actor_ft / critic."""
+    from dppo_b200.agent.finetune.train_ppo_diffusion_agent import TrainPPODiffusionAgent
+    from tests.helpers import GOLDEN_DIR, PERTURB_SCALE, PERTURB_SEED, agent_golden_cfg
+
+    gold = dict(np.load(f"{GOLDEN_DIR}/agent_run.npz", allow_pickle=False))
+    cfg = agent_golden_cfg("cuda:0", str(tmp_path))
+    ag = TrainPPODiffusionAgent(cfg)
+    g = torch.Generator().manual_seed(PERTURB_SEED)
+    with torch.no_grad():
+        for p in ag.model.actor_ft.parameters():
+            p.add_((PERTURB_SCALE * torch.randn(p.shape, generator=g)).to(p.device))
+    for o in (ag.actor_optimizer, ag.critic_optimizer):
+        o.bump_versions()
+    gen = torch.Generator().manual_seed(int(gold["noise_seed"]))
+    S = ag.model.denoising_steps
+    shape = (cfg.horizon_steps, cfg.action_dim)
+    perms = [torch.from_numpy(p.astype(np.int64)) for p in gold["perms"]]
+    ag.test_hooks["noise"] = lambda E: torch.stack([torch.randn((E,) + shape, generator=gen) for _ in range(S + 1)])
+    ag.test_hooks["perm"] = lambda n: perms.pop(0)
+    records, update0 = [], ag.update
+
+    def update(obs_buf, chains_buf, logprobs, values, adv, ret):
+        n_before = len(gold["perms"]) - len(perms)
+        lrs = (ag.actor_optimizer.param_groups[0]["lr"], ag.critic_optimizer.param_groups[0]["lr"])
+        stats = update0(obs_buf, chains_buf, logprobs, values, adv, ret)
+        used = [torch.from_numpy(p.astype(np.int64)) for p in gold["perms"][n_before:len(gold["perms"]) - len(perms)]]
+        ft, bs = ag.model.ft_denoising_steps, ag.batch_size
+        k = 0
+        for perm in used:
+            for b0 in range(0, (perm.numel() // bs) * bs, bs):
+                if k >= len(ag.last_history):
+                    break
+                idx = perm[b0:b0 + bs].cuda()
+                bb, dd = idx // ft, idx % ft
+                h = ag.last_history[k]
+                records.append([h[0], h[1], h[3], h[2], h[4], float(ret.reshape(-1)[bb].double().sum()),
+                                float(values.reshape(-1)[bb].double().sum()), float(adv.reshape(-1)[bb].double().sum()),
+                                float(logprobs.reshape(-1, ft, *logprobs.shape[3:])[bb, dd].double().sum()), float(dd.double().sum()),
+                                ag.itr, lrs[0], lrs[1]])
+                k += 1
+        return stats
+
+    ag.update = update
+    res = ag.run()
+    got, ref = np.array(records, dtype=np.float64), gold["minibatch"]
+    assert got.shape == ref.shape, (got.shape, ref.shape)  # same number of applied minibatches in every iteration
+    assert [r["minibatches"] for r in res] == [int((ref[:, 10] == i).sum()) for i in range(3)]
+    np.testing.assert_array_equal(got[:, 9:11], ref[:, 9:11])                         # (b, d) indexing and iteration
+    np.testing.assert_allclose(got[:, 11:13], ref[:, 11:13], rtol=1e-12)               # learning rates
+    np.testing.assert_allclose(got[:, 5:9], ref[:, 5:9], rtol=2e-3, atol=2e-3)         # returns / values / advantages / old log-probs
+    np.testing.assert_allclose(got[:, 0:2], ref[:, 0:2], rtol=5e-3, atol=2e-5)         # pg_loss, v_loss
+    np.testing.assert_allclose(got[:, 3], ref[:, 3], rtol=2e-2, atol=2e-7)             # approx_kl
+    np.testing.assert_allclose(got[:, 4], ref[:, 4], rtol=1e-4)                        # ratio
+    assert np.abs(got[:, 2] - ref[:, 2]).max() <= 0.05                                 # clipfrac (rows on the clip boundary may flip)
+    sd = ag.model.state_dict()
+    for name, (s1, s2) in zip(gold["param_names"], gold["param_sums"]):
+        v = sd[str(name)].double()
+        assert abs(float(v.pow(2).sum()) - s2) <= 2e-3 * max(s2, 1e-12), name
+    np.testing.assert_allclose(sd["critic.Q1.layers.2.bias"].cpu().numpy(), gold["critic_out_bias"], atol=5e-4)
+    np.testing.assert_allclose(sd["actor_ft.mlp_mean.layers.2.bias"].cpu().numpy(), gold["actor_out_bias"], atol=2e-3)
