@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--envs", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-actor", action="store_true")
+    ap.add_argument("--n-steps", type=int, default=None, help="rollout steps in the synthetic buffer (small for ncu runs)")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the eager timed loop (ncu --profile-from-start off)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     w = get_workload(args.workload)
@@ -33,7 +36,7 @@ def main():
     ft, Ta, Da = w["ft_denoising_steps"], w["horizon_steps"], w["action_dim"]
     E = args.envs or w["n_envs"]
     bs = args.rows or w["train"]["batch_size"]
-    n_steps = max(1, min(w["train"]["n_steps"], (1 << 21) // max(1, E * ft)))
+    n_steps = args.n_steps or max(1, min(w["train"]["n_steps"], (1 << 21) // max(1, E * ft)))
     N = n_steps * E
     g = torch.Generator(device=dev).manual_seed(7)
     obs_k = torch.rand((N, w["cond_steps"], w["obs_dim"]), device=dev, generator=g) * 2 - 1
@@ -69,12 +72,16 @@ def main():
         step(fwd_bwd, k)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStart()
     t0 = time.perf_counter()
     a.record()
     for k in range(args.reps):
         step(fwd_bwd, k)
     b.record()
     torch.cuda.synchronize()
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     wall = (time.perf_counter() - t0) / args.reps
     ms = a.elapsed_time(b) / args.reps
     print(f"eager : {ms:.3f} ms / minibatch (device), {wall * 1e3:.3f} ms wall -> {bs / (ms * 1e-3) / 1e6:.2f} M samples/s", flush=True)
