@@ -46,6 +46,7 @@ struct ChainArgs {
   // geometry
   int D, Dc_in, Dc, H, nb, act, ln, CH, CO, MT, KCH, KC0, KCc, MTc, nsplit, nstage;
   int C;  // CTAs per cluster (feature split), divides MT
+  int early;  // block layers run in the early-first-tile order (two M tiles per CTA, no LayerNorm): see run_layer
   uint32_t off_tb, off_blk, blk_stride, off_bout, off_bc0, off_bc1;
   const uint8_t* tiles[2];
   const float* side[2];
@@ -104,7 +105,7 @@ __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, int row,
 
 struct Smem {
   uint8_t *x_hi, *x_lo, *x0_hi, *x0_lo, *ring;
-  uint64_t *full, *empty, *layer_done, *x_full, *x0_full, *can_send, *ln_bar;
+  uint64_t *full, *empty, *layer_done, *x_full, *x0_full, *can_send, *ln_bar, *tile_done, *early_ok;
   uint32_t* tmem_slot;
   float* ln_part;  // [kEpiWarps][2][32] per-warp partial sums
   float* ln_x;     // [8 ranks][64 envs][2] per-CTA partial sums of a cluster (LayerNorm over features split across CTAs)
@@ -127,6 +128,8 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
   s.x0_full = reinterpret_cast<uint64_t*>(p), p += 8;   // layer-0 / cond_mlp operands (written as a whole)
   s.can_send = reinterpret_cast<uint64_t*>(p), p += 16;  // two barriers, used alternately (see wait_layer)
   s.ln_bar = reinterpret_cast<uint64_t*>(p), p += 8;
+  s.tile_done = reinterpret_cast<uint64_t*>(p), p += 8;  // early order: the first output tile of a block layer is complete
+  s.early_ok = reinterpret_cast<uint64_t*>(p), p += 8;   // early order: the peers hold the blocks this CTA pushed last
   s.tmem_slot = reinterpret_cast<uint32_t*>(p), p += 16;
   s.ln_part = reinterpret_cast<float*>(p), p += a.ln ? kEpiWarps * 2 * 32 * 4 : 0;  // LayerNorm scratch only when used:
   s.ln_x = reinterpret_cast<float*>(p);                                             // 6 KiB decide about a ring stage
@@ -136,7 +139,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, const ChainArgs& a) {
 static size_t smem_fixed_bytes(const MlpGeom& g, int NE) {
   const size_t xb = size_t(NE) * g.H * 2 * g.nsplit, x0b = size_t(g.KC0) * NE * 128 * g.nsplit;
   const size_t ln_bytes = g.ln ? kEpiWarps * 2 * 32 * 4 + 8 * 64 * 2 * 4 : 0;
-  return xb + x0b + 16 * kMaxStages + 176 + ln_bytes + 1024 /* alignment slack */;
+  return xb + x0b + 16 * kMaxStages + 192 + ln_bytes + 1024 /* alignment slack */;
 }
 
 // ============================================================================================== the kernel
@@ -165,6 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     mbar_init(&s.can_send[0], C > 1 ? C - 1 : 1);
     mbar_init(&s.can_send[1], C > 1 ? C - 1 : 1);
     mbar_init(s.ln_bar, C * NE);
+    mbar_init(s.tile_done, 1);
+    mbar_init(s.early_ok, C > 1 ? C - 1 : 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_slot, 512);
@@ -190,13 +195,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // rows are its first R * 128 bytes).  The output layer has only D <= 128 real rows; the rows behind them keep whatever
     // the ring slot held before (finite or not - they only reach accumulator lanes >= D, which nobody reads).
     const uint32_t p_leader = elect_one() ? 1u : 0u;  // same issue discipline as the MMA warp: no divergent region per tile
-    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot, uint32_t bytes) {
+    // `early`: the order of run_layer's early mode - phase 0 = the first two chunks for both output tiles, phase 1 / 2 =
+    // the remaining chunks for the first / second output tile
+    auto stream = [&](const uint8_t* base, int m_begin, int m_end, int KCl, int rot, uint32_t bytes, bool early) {
       // chunk-major: every output tile consumes K chunk kc before anybody touches the next chunk, so one arrived tile of
       // X feeds (m_end - m_begin) x 2 tile-MMAs before the next one is needed
-      for (int j = 0; j < KCl; ++j) {
+      for (int ph = 0; ph < (early ? 3 : 1); ++ph)
+      for (int j = (early && ph > 0) ? 2 : 0; j < ((early && ph == 0) ? 2 : KCl); ++j) {
         int kc = j + rot;
         if (kc >= KCl) kc -= KCl;
-        for (int mt = m_begin; mt < m_end; ++mt) {
+        for (int mt = (early && ph == 2) ? m_begin + 1 : m_begin; mt < ((early && ph == 1) ? m_begin + 1 : m_end); ++mt) {
           const uint8_t* src = base + size_t(mt) * KCl * a.nsplit * kTile;
           for (int h = 0; h < a.nsplit; ++h) {
 #ifdef DPPO_CHAIN_PROF
@@ -219,15 +227,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
       if (a.CH && net != cur_net) {
-        stream(a.tiles[net], 0, a.MTc, a.KCc, 0, kTile);
-        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64, 0, kTile);
+        stream(a.tiles[net], 0, a.MTc, a.KCc, 0, kTile, false);
+        stream(a.tiles[net] + size_t(a.MTc) * a.KCc * a.nsplit * kTile, 0, 1, a.CH / 64, 0, kTile, false);
       }
       cur_net = net;
       const uint8_t* base = a.tiles[net] + a.off_step_tiles;
-      stream(base, mt0, mt0 + MTo, a.KC0, 0, kTile);
+      stream(base, mt0, mt0 + MTo, a.KC0, 0, kTile, false);
       base += lin0;
-      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH, rot, kTile);
-      stream(base, 0, 1, a.KCH, rot, out_bytes);
+      for (int b = 0; b < 2 * a.nb; ++b, base += linh) stream(base, mt0, mt0 + MTo, a.KCH, rot, kTile, a.early != 0);
+      stream(base, 0, 1, a.KCH, rot, out_bytes, false);
     }
     if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 0] = p_wait, a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0;
   } else if (warp == 1) {
@@ -244,6 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     uint32_t stage = 0, phase = 0, x0_phase = 0, xf_phase = 0;
     const int rot = mt0 * 2;
     long long m_wait_x = 0, m_wait_full = 0;
+    [[maybe_unused]] long long m_wx[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // DPPO_CHAIN_PROF: x waits by (layer kind, tile class)
+    [[maybe_unused]] int kind = 0;                                                // 0 layer 0 / cond, 1 l1, 2 l2, 3 output layer
     const long long m_t0 = clock64();
     const uint32_t ring_lo = umma_desc_lo(smem_u32(s.ring));
     // The issue loop is ONE warp's dependent instruction stream on a scheduler it shares with two epilogue warps, and it
@@ -254,22 +264,31 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
 #ifdef DPPO_CHAIN_PROF
 #define DPPO_MMA_T0() tw = clock64()
 #define DPPO_MMA_T1(acc_) acc_ += clock64() - tw
+#define DPPO_MMA_TX(cls_) m_wx[kind * 3 + (cls_)] += clock64() - tw
 #else
+#define DPPO_MMA_TX(cls_)
 #define DPPO_MMA_T0()
 #define DPPO_MMA_T1(acc_)
 #endif
-    auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc, bool tiled) {
+    // `early` (block layers of a CTA that owns two M tiles): phase 0 issues the two K chunks of this CTA's own first tile
+    // of X for both output tiles, phase 1 the remaining chunks for output tile 0 (commit -> tile_done), phase 2 the
+    // remaining chunks for output tile 1 (commit -> layer_done).  After tile_done nobody in this CTA reads the first own
+    // tile of X any more, so the epilogue of output tile 0 (which overwrites exactly that tile) runs under phase 2.
+    auto run_layer = [&](const uint8_t* b_hi, const uint8_t* b_lo, int MTl, int KCl, uint32_t d_col, bool acc, bool tiled,
+                         bool early) {
       [[maybe_unused]] long long tw = 0;
       DPPO_MMA_T0();
       if (!tiled) {
         mbar_wait(s.x0_full, x0_phase);
         x0_phase ^= 1;
         tc_fence_after();
+        DPPO_MMA_TX(0);
       }
       DPPO_MMA_T1(m_wait_x);
       uint32_t waited = 0;
       const uint32_t bh = umma_desc_lo(smem_u32(b_hi)), bl = umma_desc_lo(smem_u32(b_lo));
-      for (int j = 0; j < KCl; ++j) {
+      for (int ph = 0; ph < (early ? 3 : 1); ++ph) {
+      for (int j = (early && ph > 0) ? 2 : 0; j < ((early && ph == 0) ? 2 : KCl); ++j) {
         int kc = j;
         if (tiled) {
           kc = j + rot;
@@ -280,13 +299,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
             DPPO_MMA_T0();
             mbar_wait(&s.x_full[t], (xf_phase >> t) & 1u);
             DPPO_MMA_T1(m_wait_x);
+            DPPO_MMA_TX(int(t) == mt0 ? 0 : ((int(t) > mt0 && int(t) < mt0 + MTo) ? 1 : 2));
             tc_fence_after();
             waited |= 1u << t;
           }
         }
         const uint32_t boff = uint32_t(kc) * (NE * 128 / 16);
         const uint32_t first_acc = (acc || j > 0) ? 1u : 0u;
-        for (int mt = 0; mt < MTl; ++mt) {
+        for (int mt = (early && ph == 2) ? 1 : 0; mt < ((early && ph == 1) ? 1 : MTl); ++mt) {
           const uint32_t d = tmem + d_col + uint32_t(mt) * NE;
           DPPO_MMA_T0();
           mbar_wait(&s.full[stage], phase);
@@ -309,6 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         }
       }
+      if (early && ph == 1) umma_commit_p(s.tile_done, leader);
+      }
       xf_phase ^= waited;
       umma_commit_p(s.layer_done, leader);
     };
@@ -316,20 +338,27 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     for (int step = a.first_step; step < a.S; ++step) {
       const int net = (a.rows[step].ft && !a.use_base) ? 1 : 0;
       if (a.CH && net != cur_net) {
-        run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false, false);
-        run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false, false);
+        run_layer(s.x_hi, s.x_lo, a.MTc, a.KCc, col_y, false, false, false);
+        run_layer(s.x_hi, s.x_lo, 1, a.CH / 64, col_y, false, false, false);
       }
       cur_net = net;
-      run_layer(s.x0_hi, s.x0_lo, MTo, a.KC0, col_h, false, false);
+      kind = 0;
+      run_layer(s.x0_hi, s.x0_lo, MTo, a.KC0, col_h, false, false, false);
       for (int b = 0; b < a.nb; ++b) {
-        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_y, false, true);
-        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_h, true, true);
+        kind = 1;
+        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_y, false, true, a.early != 0);
+        kind = 2;
+        run_layer(s.x_hi, s.x_lo, MTo, a.KCH, col_h, true, true, a.early != 0);
       }
-      run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false, true);
+      kind = 3;
+      run_layer(s.x_hi, s.x_lo, 1, a.KCH, col_y, false, true, false);
     }
     if (a.prof && lane == 0) {
       a.prof[blockIdx.x * 16 + 2] = m_wait_x, a.prof[blockIdx.x * 16 + 3] = m_wait_full;
       a.prof[blockIdx.x * 16 + 4] = clock64() - m_t0;
+#ifdef DPPO_CHAIN_PROF
+      for (int i = 0; i < 12; ++i) a.prof[(4096 + blockIdx.x) * 16 + i] = m_wx[i];
+#endif
     }
   } else {
     // ======================================================================================= epilogue warps
@@ -344,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     float zreg[CPT];  // the step's injected noise, drawn while the output-layer MMAs run (see the step loop)
     const int nxe = NE * a.D;  // sample elements of this tile (<= 256 * CPT because D <= 128)
 
-    long long e_wait = 0, e_hand = 0;
+    long long e_wait = 0, e_hand = 0, e_early = 0, e_ack = 0;
     const long long e_t0 = clock64();
     // Handshakes alternate between TWO barriers.  Consecutive handshakes are not always separated by an all-to-all data
     // dependency: the output layer ends with a handshake but no push, and layer 0 of the next step runs on the local x0
@@ -395,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     const uint32_t tile_bytes = 2u * NE * 128u;  // one M tile = two 64-feature chunks of X
     // tile `mt` of this CTA's block is complete in shared memory: copy it into the peers (completing on THEIR barrier of
     // that tile) and release it to this CTA's MMA warp
-    auto publish_tile = [&](int mt) {
+    auto push_tile = [&](int mt) {
       const uint32_t off = blk_off + uint32_t(mt) * tile_bytes;
       uint64_t* bar = &s.x_full[mt0 + mt];
       uint64_t* peer_bar = MTo == 1 ? &s.x_full[kPeerBar] : bar;  // where this tile is accounted at the receivers
@@ -404,7 +433,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         bulk_s2peer(s.x_hi + off, s.x_hi + off, tile_bytes, peer_bar, p);
         if (split) bulk_s2peer(s.x_lo + off, s.x_lo + off, tile_bytes, peer_bar, p);
       }
-      mbar_arrive(bar);
+    };
+    auto publish_tile = [&](int mt) {
+      push_tile(mt);
+      mbar_arrive(&s.x_full[mt0 + mt]);
     };
     // `exchange`: the epilogue wrote (the last tile of) this CTA's block of X; otherwise a whole-operand hand-off
     auto signal_x = [&](bool exchange) {
@@ -436,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     // lanes swap one value per column pair (even lane keeps column c, odd lane column c + 1), so that every thread owns
     // TWO consecutive features of one env row: one packed bf16x2 convert and one 4-byte store per operand half.
     const uint32_t odd = lane & 1;
-    uint32_t ln_phase = 0;
+    uint32_t ln_phase = 0, td_phase = 0, eo_phase = 0;
     // Per-feature constants (bias, LayerNorm gain / shift) of the first four M tiles are fetched BEFORE the wait for the
     // layer's MMAs: they come from the L2-resident side table (the L1 is a few KB next to 220 KB of shared memory), and
     // a load issued after tcgen05.ld would put ~700 cycles of L2 latency on the critical path of every M tile.
@@ -452,8 +484,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       }
     };
     // `whole_row`: this CTA holds every feature of the layer (cond_mlp), otherwise they are split over the cluster
+    // [mt_lo, mt_hi): the M tiles of the layer handled by this call (the early order handles them in two calls)
     auto epi_hidden = [&](uint32_t region, int mt_first, int MTl, const float* bias_a, const float* bias_b, bool identity,
-                          const float* ln_g, const float* ln_b, bool whole_row, bool push) {
+                          const float* ln_g, const float* ln_b, bool whole_row, bool push, int mt_lo, int mt_hi) {
       float mean[LN ? CPT : 1], rstd[LN ? CPT : 1];
       if (LN && ln_g != nullptr) {
         float s1[CPT], s2[CPT];
@@ -532,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         }
       }
-      for (int mt = 0; mt < MTl; ++mt) {
+      for (int mt = mt_lo; mt < mt_hi; ++mt) {
         float v[CPT];
         tmem_ld(tmem + lane_addr + region + uint32_t(mt) * NE + col0, v);
         const int f = (mt_first + mt) * 128 + fl;
@@ -665,9 +698,40 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         }
         prefetch_side(mt_first, MTl, ba, bb, lg, lb);
+        if (!LN && a.early && L >= 1) {
+          // early order (see run_layer): output tile 0 is complete while the MMAs of output tile 1 still run.  Its
+          // epilogue overwrites this CTA's first own tile of X, which (a) the local MMAs no longer read (tile_done) and
+          // (b) was the source of the push after the previous layer: every peer acknowledges, at ITS tile_done, that the
+          // blocks pushed to it have landed (its phase 1 has consumed them).
+          const long long te0 = clock64();
+          mbar_wait(s.tile_done, td_phase);
+          e_early += clock64() - te0;
+          td_phase ^= 1;
+          tc_fence_after();
+          if (C > 1) {
+            if (et == 0)
+              for (uint32_t p = 0; p < uint32_t(C); ++p)
+                if (p != rank) mbar_arrive_remote(s.early_ok, p);
+            const long long te1 = clock64();
+            mbar_wait_cluster(s.early_ok, eo_phase);
+            e_ack += clock64() - te1;
+            eo_phase ^= 1;
+          }
+          epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, false, false, 0, 1);
+          tc_fence_before();
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) mbar_arrive(&s.x_full[mt0]);  // the next layer's first chunks may be issued right behind this layer
+          wait_layer(true);
+          expect_peer_tiles();
+          if (et == 0) push_tile(0);  // the peers are done reading their copies: now the block may land in them
+          epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, false, false, 1, 2);
+          signal_x(true);
+          continue;
+        }
         wait_layer(L >= 0);
         if (L >= 0) expect_peer_tiles();
-        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0, L >= 0);
+        epi_hidden(region, mt_first, MTl, ba, bb, identity, lg, lb, L < 0, L >= 0, 0, MTl);
         signal_x(L >= 0);
       }
       cur_net = net;
@@ -781,7 +845,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
       signal_x(false);
     }
     if (a.prof && et == 0) a.prof[blockIdx.x * 16 + 5] = e_wait, a.prof[blockIdx.x * 16 + 6] = clock64() - e_t0, a.prof[blockIdx.x * 16 + 7] = e_hand;
-    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 8 + (warp - 2)] = (clock64() - e_t0) - e_wait - e_hand;
+    if (a.prof && lane == 0) a.prof[blockIdx.x * 16 + 8 + (warp - 2)] = (clock64() - e_t0) - e_wait - e_hand - e_early - e_ack;
+#ifdef DPPO_CHAIN_PROF
+    if (a.prof && et == 0) a.prof[(4096 + blockIdx.x) * 16 + 12] = e_early, a.prof[(4096 + blockIdx.x) * 16 + 13] = e_ack;
+#endif
   }
 
   tc_fence_before();
@@ -954,6 +1021,14 @@ int sample_chain_impl(dppo_ctx* ctx, const float* state, int E, const float* noi
   const LaunchShape shape = pick_shape(ctx, E);
   const int NE = shape.NE;
   a.C = shape.C;
+  {
+    static int env_early = -1;  // DPPO_B200_EARLY=0: block layers in the plain chunk-major order (A/B measurements)
+    if (env_early < 0) {
+      const char* e = getenv("DPPO_B200_EARLY");
+      env_early = e ? atoi(e) : 1;
+    }
+    a.early = (env_early && !g.ln && g.MT / a.C == 2 && g.KCH >= 4) ? 1 : 0;
+  }
   const size_t fixed = smem_fixed_bytes(g, NE);
   const size_t budget = 232448;
   if (fixed + 2 * kTile > budget) return set_error("chain kernel: geometry needs %zu B of shared memory", fixed), DPPO_ERR_INVALID;

@@ -24,7 +24,7 @@ model.engine_precision = prec
 eng = model.engine()
 eng.set_launch_shape(ne, cl)
 grid = ((E + 15) // 16) * 8
-prof = torch.zeros(grid * 16, dtype=torch.int64, device="cuda")
+prof = torch.zeros((4096 + grid) * 16, dtype=torch.int64, device="cuda")  # detail rows of a PROF build start at row 4096
 lib = _lib.load()
 lib.dppo_debug_set_prof.argtypes = [C.c_void_p, C.c_void_p]
 lib.dppo_debug_set_prof(eng.ctx, C.c_void_p(prof.data_ptr()))
@@ -37,8 +37,8 @@ a.record()
 eng.sample(state)
 b.record()
 torch.cuda.synchronize()
-p = prof.view(grid, 16).cpu()
-used = p[p[:, 4] > 0]
+p = prof.view(4096 + grid, 16).cpu()
+used = p[:grid][p[:grid][:, 4] > 0]
 if "unet" in name and cl == 2:  # track-split pair: even CTAs = main path, odd CTAs = FiLM encoders
     for r, lab in ((0, "main"), (1, "encoders")):
         sub = p[r::2][p[r::2][:, 4] > 0]
@@ -51,3 +51,12 @@ print(f"{name} E={E} {prec} NE={ne} C={cl}: kernel {a.elapsed_time(b):.3f} ms, {
 for i, n in enumerate(names):
     col = used[:, i].double()
     print(f"  {n:16s} mean {col.mean() / 1e3:10.1f} kcyc   max {col.max() / 1e3:10.1f} kcyc")
+
+# detail rows of a DPPO_B200_CHAIN_PROF=1 build: the MMA warp's operand waits by (layer kind, tile class), early-order waits
+n = len(used)
+det = p[4096:4096 + n].double()
+if det.abs().sum() > 0:
+    kinds, cls = ["layer0", "l1", "l2", "out"], ["own tile 0 / x0", "own tile 1", "peer tiles"]
+    for k in range(4):
+        print("  mma_wait_x %-7s" % kinds[k] + "  ".join(f"{cls[c]} {det[:, k * 3 + c].mean() / 1e3:8.1f}k" for c in range(3)))
+    print(f"  epi wait tile_done {det[:, 12].mean() / 1e3:8.1f}k   wait early_ok {det[:, 13].mean() / 1e3:8.1f}k")
