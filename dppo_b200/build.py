@@ -13,11 +13,11 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libdppo_b200.so")
-SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "update_gemm.cu", "update_plan.cu"]
+SOURCES = ["api.cu", "pack.cu", "chain_mlp.cu", "chain_pair.cu", "chain_small.cu", "unet_plan.cu", "chain_unet.cu", "update.cu", "update_gemm.cu", "update_plan.cu"]
 # bring-up code (descriptor self-test, micro-benchmarks) lives in its own test-only library, not in the product .so
 TEST_LIB = os.path.join(PKG, "lib", "libdppo_b200_test.so")
 TEST_SOURCES = ["umma_selftest.cu", "microbench.cu"]
-HEADERS = ["common.cuh", "internal.h", "unet_plan.h", "update_gemm.h", os.path.join("..", "..", "include", "dppo_b200.h")]
+HEADERS = ["common.cuh", "internal.h", "chain_mlp.cuh", "unet_plan.h", "update_gemm.h", os.path.join("..", "..", "include", "dppo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -42,6 +42,7 @@ def build(force=False, verbose=False):
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         prof = ["-DDPPO_CHAIN_PROF"] if os.environ.get("DPPO_B200_CHAIN_PROF") == "1" else []  # MMA-warp wait counters
+        prof += os.environ.get("DPPO_B200_NVCC_DEFS", "").split()  # bring-up: extra -D switches for A/B variants
         cmd = [nvcc] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

@@ -55,7 +55,14 @@ for i, n in enumerate(names):
 # detail rows of a DPPO_B200_CHAIN_PROF=1 build: the MMA warp's operand waits by (layer kind, tile class), early-order waits
 n = len(used)
 det = p[4096:4096 + n].double()
-if det.abs().sum() > 0:
+if det.abs().sum() > 0 and det[:, 4:].abs().sum() == 0:  # pair kernel (leader CTAs): own ring, follower ring, own X, follower X
+    lead = det[det[:, 0] + det[:, 1] > 0]
+    fol = used[1::2].double()
+    print("  follower CTAs: producer wait-empty %.1fk of %.1fk; relay wait-full %.1fk of %.1fk" % (fol[:, 0].mean() / 1e3, fol[:, 1].mean() / 1e3, fol[:, 3].mean() / 1e3, fol[:, 4].mean() / 1e3))
+    led = used[0::2].double()
+    print("  leader CTAs  : producer wait-empty %.1fk of %.1fk" % (led[:, 0].mean() / 1e3, led[:, 1].mean() / 1e3))
+    print("  pair leader waits: own ring %.1fk  follower ring (relay) %.1fk  own X/x0 %.1fk  follower X/x0 %.1fk" % tuple(lead[:, i].mean() / 1e3 for i in range(4)))
+elif det.abs().sum() > 0:
     kinds, cls = ["layer0", "l1", "l2", "out"], ["own tile 0 / x0", "own tile 1", "peer tiles"]
     for k in range(4):
         print("  mma_wait_x %-7s" % kinds[k] + "  ".join(f"{cls[c]} {det[:, k * 3 + c].mean() / 1e3:8.1f}k" for c in range(3)))

@@ -179,6 +179,7 @@ def test_bf16_fast_mode_within_its_tolerance_report():
     ("transport_k20", 32, 2), ("transport_k20", 16, 8), ("transport", 32, 4),
     ("furniture", 16, 8), ("furniture", 32, 2), ("furniture_ddpm100", 16, 4),
     ("square_unet", 16, 0), ("square_unet", 32, 0),
+    ("hopper", 0, -2), ("walker2d", 0, -2),  # cluster = -2: the cta_group::2 CTA-pair kernel (chain_pair.cu)
 ])
 def test_chain_and_logprobs_every_launch_shape(case, tile_envs, cluster):
     """Feature-split clusters (C CTAs share one env tile) and every tile size give the same chains / log-probs."""
@@ -246,6 +247,7 @@ def test_zero_copy_pinned_io_matches_device_io(case):
 @pytest.mark.parametrize("workload,n_envs,tile_envs,cluster,launches", [
     ("walker2d", 4096, 64, 2, 3000), ("walker2d", 2048, 32, 4, 3000), ("furniture", 500, 32, 4, 2000),
     ("transport_k20", 50, 16, 8, 2000), ("square_unet", 512, 16, 2, 1500), ("hopper", 40, 0, -1, 5000),
+    ("walker2d", 4096, 0, -2, 3000), ("walker2d", 301, 0, -2, 2000),
 ])
 def test_back_to_back_launch_stress(workload, n_envs, tile_envs, cluster, launches):
     """Protocol stress: thousands of back-to-back launches of every cluster protocol (a handshake race once hung one launch
@@ -294,7 +296,7 @@ def test_empty_and_multi_wave_batches():
 # ------------------------------------------------------------------------------------------------ bench shapes
 @pytest.mark.parametrize("workload,n_envs,tile_envs,cluster", [
     ("walker2d", 4096, 64, 2), ("furniture", 1000, 32, 4), ("transport", 50, 16, 8), ("square_unet", 1024, 16, 0),
-    ("hopper", 40, 0, -1),
+    ("hopper", 40, 0, -1), ("walker2d", 4096, 0, -2),
 ])
 def test_bench_shapes_match_oracle_on_row_slices(workload, n_envs, tile_envs, cluster):
     """The launch shapes bench.py times (SURVEY.md §8d sizes), checked against the CPU oracle on the first / a middle / the
