@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
         uint64_t* bar = &s.can_send[hs & 1u];
         if (et == 0)
           for (uint32_t p = 0; p < uint32_t(C); ++p)
-            if (p != rank) mbar_arrive_remote(bar, p);
+            if (p != rank) mbar_arrive_remote_nodata(bar, p);
         // ... and once every peer says the same, (a) the block this CTA pushed after the previous layer has been
         // consumed, so its source may be overwritten, and (b) the new block may be pushed into the peers' copies
         const long long th = clock64();
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           if (C > 1) {
             if (et == 0)
               for (uint32_t p = 0; p < uint32_t(C); ++p)
-                if (p != rank) mbar_arrive_remote(s.early_ok, p);
+                if (p != rank) mbar_arrive_remote_nodata(s.early_ok, p);
             const long long te1 = clock64();
             mbar_wait_cluster(s.early_ok, eo_phase);
             e_ack += clock64() - te1;

@@ -89,14 +89,6 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols)
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// Arrive on the barrier at the same CTA-relative address in CTA `rank`.  Default semantics (release at CTA scope): one
-// SYNCS.ARRIVE.  The .release.cluster form costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of it - measured ~1000 cycles
-// per arrive in the relay warp, which made the first version of this kernel 1.75x SLOWER than the cta_group::1 kernel.
-// What the arrive announces is shared-memory data for the ASYNC proxy (tensor-core operand reads), made visible by the
-// bulk copy's own completion or by fence.proxy.async + the CTA barrier in front of the arrive, not by this instruction.
-__device__ __forceinline__ void arrive_peer(uint64_t* bar, uint32_t rank) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), rank)) : "memory");
-}
 // completion of every MMA issued so far -> the barrier at this CTA-relative address in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit2_p(uint64_t* bar, uint32_t leader) {
   asm volatile(
@@ -314,7 +306,7 @@ __global__ void __launch_bounds__(kPThreads, 1) chain_pair_kernel(const ChainArg
           const uint32_t t = uint32_t(pair_chunk(i, MTo)) >> 1;
           if (int(t) < MTo && !((waited >> t) & 1u)) {  // the leader's tiles; this CTA's own are announced by its epilogue
             mbar_wait(&s.x_full[t], (xf_phase >> t) & 1u);
-            if (lane == 0) arrive_peer(&s.px_full[t], 0);
+            if (lane == 0) mbar_arrive_remote_nodata(&s.px_full[t], 0);
             waited |= 1u << t;
           }
         }
@@ -326,7 +318,7 @@ __global__ void __launch_bounds__(kPThreads, 1) chain_pair_kernel(const ChainArg
 #ifdef DPPO_CHAIN_PROF
           r_wait += clock64() - tw;
 #endif
-          if (lane == 0) arrive_peer(&s.pfull[stage], 0);
+          if (lane == 0) mbar_arrive_remote_nodata(&s.pfull[stage], 0);
           if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
         }
       }
@@ -379,7 +371,7 @@ __global__ void __launch_bounds__(kPThreads, 1) chain_pair_kernel(const ChainArg
         bulk_s2peer(s.x_hi + xo, s.stg_hi + so, tile_bytes, &s.x_full[mt0 + mt], peer);
         if (split) bulk_s2peer(s.x_lo + xo, s.stg_lo + so, tile_bytes, &s.x_full[mt0 + mt], peer);
         mbar_arrive(&s.x_full[mt0 + mt]);
-        if (rank != 0) arrive_peer(&s.px_full[mt0 + mt], 0);
+        if (rank != 0) mbar_arrive_remote_nodata(&s.px_full[mt0 + mt], 0);
       }
     };
     auto signal_x0 = [&]() {
@@ -388,7 +380,7 @@ __global__ void __launch_bounds__(kPThreads, 1) chain_pair_kernel(const ChainArg
       named_bar_sync(1, kPEpiThreads);
       if (et == 0) {
         mbar_arrive(s.x0_full);
-        if (rank != 0) arrive_peer(s.px0_full, 0);
+        if (rank != 0) mbar_arrive_remote_nodata(s.px0_full, 0);
       }
     };
     float pre_b[4];

@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
           if (film && C > 1) {
             // every epilogue thread is done reading the buffer: hand it back to the encoder CTA
             named_bar_sync(1, kEpiThreads);
-            if (et == 0) mbar_arrive_remote(&s.film_free[film_n & 1], 1);
+            if (et == 0) mbar_arrive_remote_nodata(&s.film_free[film_n & 1], 1);
             ++film_n;
           }
         } else if (kind == U_EPI_FILM) {

@@ -116,9 +116,26 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), rank)) : "memory");
 }
+// The same arrive without the cluster-scope release: ONE instruction (SYNCS.ARRIVE), where the form above is
+// MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR + SYNCS.ARRIVE (~1000 cycles when bulk copies are in flight,
+// profiles/r2/r2i_chain_pair_kernel_and_early_order.txt).  For arrivals that publish no data written by this thread
+// ("I am done reading", "your block has landed"); anything that follows remote st.shared::cluster stores needs the
+// release form.
+__device__ __forceinline__ void mbar_arrive_remote_nodata(uint64_t* bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), rank)) : "memory");
+}
 // store one float into CTA `rank`'s shared memory at the CTA-relative address of `local`
 __device__ __forceinline__ void st_remote_f32(float* local, uint32_t rank, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_u32(smem_u32(local), rank)), "f"(v) : "memory");
+}
+// The same store as an ASYNC store that completes 4 bytes on the mbarrier `bar` of the destination CTA: the receiver
+// waits for the expected byte count on its own barrier, no cluster-scope release fence on the sending side
+// (barrier.cluster.arrive.release / mbarrier.arrive.release.cluster are MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in SASS).
+__device__ __forceinline__ void st_async_f32(float* local, uint32_t rank, float v, uint64_t* bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(
+                   mapa_u32(smem_u32(local), rank)),
+               "f"(v), "r"(mapa_u32(smem_u32(bar), rank))
+               : "memory");
 }
 // 16-byte variant (the address must be 16-byte aligned)
 __device__ __forceinline__ void st_remote_v4(float* local, uint32_t rank, float4 v) {
