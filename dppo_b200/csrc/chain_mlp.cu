@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
     mbar_init(s.x0_full, 1);
     mbar_init(&s.can_send[0], C > 1 ? C - 1 : 1);
     mbar_init(&s.can_send[1], C > 1 ? C - 1 : 1);
-    mbar_init(s.ln_bar, C * NE);
+    mbar_init(s.ln_bar, 1);  // one expect-tx arrival per use; the partial sums arrive as async stores (8 bytes each)
     mbar_init(s.tile_done, 1);
     mbar_init(s.early_ok, C > 1 ? C - 1 : 1);
     fence_mbar_init();
@@ -471,7 +471,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
           }
         } else {
           // the row's features are split over the C CTAs of the cluster: thread e < NE publishes this CTA's partial sums of
-          // env e to every CTA (remote stores, then a releasing arrive on that CTA's ln_bar); everybody then adds C partials
+          // env e to every CTA as ONE async 8-byte store that completes on that CTA's ln_bar (no release fence: the first
+          // version paid MEMBAR.ALL.GPU per arrive); everybody then adds C partials
+          if (et == 0) mbar_arrive_expect_tx(s.ln_bar, uint32_t(C) * NE * 8u);
           if (et < NE) {
             const int h_ = et / CPT, c_ = et % CPT;
             float t1 = 0.f, t2 = 0.f;
@@ -481,13 +483,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
               t1 += part[c_], t2 += part[32 + c_];
             }
             float* slot = s.ln_x + (rank * 64 + et) * 2;
-            for (uint32_t p = 0; p < uint32_t(C); ++p) {
-              st_remote_f32(slot, p, t1);
-              st_remote_f32(slot + 1, p, t2);
-              mbar_arrive_remote(s.ln_bar, p);
-            }
+            for (uint32_t p = 0; p < uint32_t(C); ++p) st_async_v2(slot, p, t1, t2, s.ln_bar);
           }
-          mbar_wait_cluster(s.ln_bar, ln_phase);
+          mbar_wait(s.ln_bar, ln_phase);
           ln_phase ^= 1;
           const float inv_n = 1.f / float(MTl * 128 * C);
 #pragma unroll

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
     mbar_init(s.x_full, 1);
     for (int i = 0; i < 8; ++i) mbar_init(&s.xt_full[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.film_full[i], kEpiThreads);  // every epilogue thread of the encoder CTA arrives after its own stores
+      mbar_init(&s.film_full[i], 1);  // the encoder CTA announces the byte count; its values arrive as async stores
       mbar_init(&s.film_free[i], 1);
     }
     fence_mbar_init();
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
           if (film && C > 1) {
             // this block's (scale, bias) vectors arrive from the encoder CTA
             const long long tw = clock64();
-            mbar_wait_cluster(&s.film_full[film_n & 1], (film_n >> 1) & 1);
+            mbar_wait(&s.film_full[film_n & 1], (film_n >> 1) & 1);
             e_film += clock64() - tw;
             film_buf = s.film + (film_n & 1) * s.film_stride;
           }
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
           if (C > 1) {
             // double-buffered in the MAIN CTA's shared memory; block n may be written once block n - 2 was consumed
             const long long tw = clock64();
-            if (film_n >= 2) mbar_wait_cluster(&s.film_free[film_n & 1], ((film_n >> 1) - 1) & 1);
+            if (film_n >= 2) mbar_wait(&s.film_free[film_n & 1], ((film_n >> 1) - 1) & 1);
             e_film += clock64() - tw;
             film_buf = s.film + (film_n & 1) * s.film_stride;
           }
@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
               const float b = mt < 2 ? pb[mt & 1] : bias[f];
               if (C > 1) {
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) st_remote_f32(film_buf + size_t(col0 + c) * a.film_dim + f, 0, v[c] + b);
+                for (int c = 0; c < CPT; ++c)
+                  st_async_f32(film_buf + size_t(col0 + c) * a.film_dim + f, 0, v[c] + b, &s.film_full[film_n & 1]);
               } else {
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) film_buf[size_t(col0 + c) * a.film_dim + f] = v[c] + b;
@@ -536,7 +537,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             }
           }
           if (C > 1) {
-            mbar_arrive_remote(&s.film_full[film_n & 1], 0);  // release.cluster: orders this thread's remote stores
+            // nf features x NE environments, 4 bytes each, complete on the main CTA's barrier (async stores: no release
+            // fence per thread, which was MEMBAR.ALL.GPU x 256 threads per block)
+            if (et == 0) mbar_arrive_expect_tx_remote(&s.film_full[film_n & 1], 0, uint32_t(nf) * NE * 4u);
             ++film_n;
           }
         } else {

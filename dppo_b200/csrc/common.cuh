@@ -137,6 +137,18 @@ __device__ __forceinline__ void st_async_f32(float* local, uint32_t rank, float 
                "f"(v), "r"(mapa_u32(smem_u32(bar), rank))
                : "memory");
 }
+// two floats (8-byte aligned), 8 bytes completed on the destination CTA's barrier
+__device__ __forceinline__ void st_async_v2(float* local, uint32_t rank, float x, float y, uint64_t* bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                   mapa_u32(smem_u32(local), rank)),
+               "f"(x), "f"(y), "r"(mapa_u32(smem_u32(bar), rank))
+               : "memory");
+}
+// one arrival + `bytes` expected transaction bytes on the barrier of CTA `rank` (the sender announces how much it sends)
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint64_t* bar, uint32_t rank, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(mapa_u32(smem_u32(bar), rank)), "r"(bytes)
+               : "memory");
+}
 // 16-byte variant (the address must be 16-byte aligned)
 __device__ __forceinline__ void st_remote_v4(float* local, uint32_t rank, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mapa_u32(smem_u32(local), rank)), "f"(v.x),
