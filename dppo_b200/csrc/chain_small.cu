@@ -69,10 +69,11 @@ __device__ __forceinline__ float act_s(int act, float x) { return act == DPPO_AC
 
 // floats of shared memory
 __host__ __device__ inline size_t small_smem_floats(int FS, int K0p, int H, int nb, int OR, int EPC, int S) {
+  const int KS = kThreadsS / (FS / 2);  // k-slices of a hidden layer (two features per thread)
   return size_t(FS) * K0p + size_t(2 * nb) * FS * (H + 4) + size_t(OR) * (H + 4)  // resident weight slices
-         + size_t(2) * EPC * H                                                    // double-buffered layer input
+         + size_t(2) * EPC * (H + 4 * KS)                                         // double-buffered layer input (padded slices)
          + size_t(EPC) * K0p                                                      // layer-0 input [x | obs]
-         + size_t(kThreadsS) * EPC                                                // k-slice partial sums
+         + size_t(KS) * EPC * FS                                                  // k-slice partial sums
          + size_t(2 * nb) * FS + size_t(OR)                                       // bias slices (b1 / b2 per block, output)
          + size_t(S) * (sizeof(StepRow) / 4) + 4                                  // the schedule rows
          + 8;                                                                     // three mbarriers (8-byte aligned)
@@ -95,16 +96,23 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
   float* w0 = sm;                                        // [FS][K0p]
   float* wh = w0 + size_t(FS) * K0p;                     // [2 nb][FS][HS]
   float* wos = wh + size_t(2 * a.nb) * FS * HS;          // [OR][HS]
-  float* xb = wos + size_t(a.OR) * HS;                   // [2][EPC][H]
-  float* x0 = xb + size_t(2) * EPC * H;                  // [EPC][K0p]
-  float* red = x0 + size_t(EPC) * K0p;                   // [256 / FS][EPC][FS]
-  float* bh = red + size_t(kThreadsS) * EPC;             // [2 nb][FS] hidden biases of the owned features
+  float* xb = wos + size_t(a.OR) * HS;                   // [2][EPC][HP], column c at c + 4 (c / KQ)
+  // Hidden layers: a thread owns TWO features (fa, fa + FS/2) x one k-slice, so every activation it loads feeds two
+  // FMAs: the dot products are bound by shared-memory wavefronts (a broadcast read of x delivers 16 bytes per wavefront),
+  // and with one feature per thread 96 of the 160 wavefronts per warp were those reads.  A warp then spans two or more
+  // k-slices; 4 floats of padding per slice put their broadcast addresses into different banks.
+  const int FP = FS / 2;                                 // feature pairs
+  const int KS = kThreadsS / FP;                         // k-slices of a hidden layer
+  const int KQ = H / KS;                                 // columns per slice (multiple of 4)
+  const int HP = H + 4 * KS;                             // padded length of one environment's activation row
+  float* x0 = xb + size_t(2) * EPC * HP;                 // [EPC][K0p]
+  float* red = x0 + size_t(EPC) * K0p;                   // [KS][EPC][FS]
+  float* bh = red + size_t(KS) * EPC * FS;               // [2 nb][FS] hidden biases of the owned features
   float* bos = bh + size_t(2 * a.nb) * FS;               // [OR] output biases of the owned rows
   // the whole schedule lives in shared memory: no global load at a step start
   StepRow* s_rows = reinterpret_cast<StepRow*>(bos + ((a.OR + 3) & ~3));
-  const int KS = kThreadsS / FS;                         // k-slices of a hidden layer
-  const int KQ = H / KS;                                 // columns per slice (multiple of 4)
-  const int f = t % FS, kq = t / FS;                     // compute role: (owned feature, k-slice)
+  const int fa = t % FP, kq = t / FP;                    // compute role: (feature pair fa / fa + FP, k-slice)
+  const int f = t % FS;                                  // reduce role: owned feature
   const int F = int(rank) * FS + f;                      // global feature index
   const bool owner = t < FS * EPC;                       // reduce role: thread (f, e = t / FS) owns one output
   const int oe = t / FS;
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
     // every fourth CTA - a quarter of the transaction updates - is slower, 0.1606 vs 0.1544 ms.)
     auto publish = [&](float v) {
       if (!owner) return;
-      float* dstp = xb + size_t(buf) * EPC * H + oe * H + F;
+      float* dstp = xb + size_t(buf) * EPC * HP + oe * HP + F + 4 * (F / KQ);
 #pragma unroll
       for (uint32_t p = 0; p < uint32_t(kCS); ++p) st_async_f32(dstp, p, v, &sbar[buf]);
     };
@@ -210,31 +218,39 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
 
     // ---- residual blocks: y = W1 act(h) + b1 ; h += W2 act(y) + b2
     for (int l = 0; l < 2 * a.nb; ++l) {
-      const float* xin = xb + size_t(buf) * EPC * H + kq * KQ;
-      const float* wr = wh + size_t(l) * FS * HS + f * HS + kq * KQ;
-      float acc[EPC];
+      const float* xin = xb + size_t(buf) * EPC * HP + kq * (KQ + 4);
+      const float* wra = wh + size_t(l) * FS * HS + fa * HS + kq * KQ;
+      const float* wrb = wra + size_t(FP) * HS;
+      float acca[EPC], accb[EPC];
 #pragma unroll
-      for (int e = 0; e < EPC; ++e) acc[e] = 0.f;
+      for (int e = 0; e < EPC; ++e) acca[e] = 0.f, accb[e] = 0.f;
+#pragma unroll 8
       for (int i = 0; i < KQ; i += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(wr + i);
+        const float4 wa = *reinterpret_cast<const float4*>(wra + i);
+        const float4 wb = *reinterpret_cast<const float4*>(wrb + i);
 #pragma unroll
         for (int e = 0; e < EPC; ++e) {
-          const float4 xv = *reinterpret_cast<const float4*>(xin + e * H + i);
-          acc[e] = fmaf(wv.x, xv.x, acc[e]);
-          acc[e] = fmaf(wv.y, xv.y, acc[e]);
-          acc[e] = fmaf(wv.z, xv.z, acc[e]);
-          acc[e] = fmaf(wv.w, xv.w, acc[e]);
+          const float4 xv = *reinterpret_cast<const float4*>(xin + e * HP + i);
+          acca[e] = fmaf(wa.x, xv.x, acca[e]), accb[e] = fmaf(wb.x, xv.x, accb[e]);
+          acca[e] = fmaf(wa.y, xv.y, acca[e]), accb[e] = fmaf(wb.y, xv.y, accb[e]);
+          acca[e] = fmaf(wa.z, xv.z, acca[e]), accb[e] = fmaf(wb.z, xv.z, accb[e]);
+          acca[e] = fmaf(wa.w, xv.w, acca[e]), accb[e] = fmaf(wb.w, xv.w, accb[e]);
         }
       }
 #pragma unroll
-      for (int e = 0; e < EPC; ++e) red[(kq * EPC + e) * FS + f] = acc[e];
+      for (int e = 0; e < EPC; ++e) red[(kq * EPC + e) * FS + fa] = acca[e], red[(kq * EPC + e) * FS + fa + FP] = accb[e];
       __syncthreads();
       buf ^= 1;
       {
         float pv = 0.f;
         if (owner) {
-          float v = 0.f;
-          for (int s = 0; s < KS; ++s) v += red[(s * EPC + oe) * FS + f];
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;  // KS is a multiple of 4; four chains instead of one of KS dependent adds
+#pragma unroll 2
+          for (int s = 0; s < KS; s += 4) {
+            v0 += red[(s * EPC + oe) * FS + f], v1 += red[((s + 1) * EPC + oe) * FS + f];
+            v2 += red[((s + 2) * EPC + oe) * FS + f], v3 += red[((s + 3) * EPC + oe) * FS + f];
+          }
+          float v = (v0 + v1) + (v2 + v3);
           const int b = l >> 1;
           v += bh[l * FS + f];
           if (!(l & 1)) {
@@ -260,20 +276,21 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
       } else {
         stdv = fmaxf(row.std_train, a.min_std);
       }
-      const float* xin = xb + size_t(buf) * EPC * H;
+      const float* xin = xb + size_t(buf) * EPC * HP;
       for (int pq = warp; pq < a.OR * ne; pq += kThreadsS / 32) {
         const int r = pq / ne, e = pq % ne, j = int(rank) + kCS * r;
         if (j >= a.D) continue;
         const float* wr = wos + r * HS;
-        const float* xr = xin + e * H;
+        const float* xr = xin + e * HP;
         const int env = env0 + e;
         // the draw does not depend on the network output: issue it (global load or Philox) ahead of the dot product
         float z = a.noise ? a.noise[(size_t(step + 1) * a.E + env) * a.D + j]
                           : philox_normal_s(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + j, uint32_t(step + 1));
         float acc = 0.f;
+#pragma unroll 4
         for (int k = lane * 4; k < H; k += 128) {
           const float4 wv = *reinterpret_cast<const float4*>(wr + k);
-          const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+          const float4 xv = *reinterpret_cast<const float4*>(xr + k + 4 * (k / KQ));
           acc = fmaf(wv.x, xv.x, acc), acc = fmaf(wv.y, xv.y, acc), acc = fmaf(wv.z, xv.z, acc), acc = fmaf(wv.w, xv.w, acc);
         }
 #pragma unroll
@@ -340,7 +357,10 @@ int launch_small(const SmallArgs& a, int clusters, cudaStream_t st) {
 int small_chain_capacity(const dppo_ctx* ctx) {
   const MlpGeom& g = ctx->g;
   if (ctx->kind != 0 || g.CH || g.ln || g.nb > kMaxBlocks || g.H % (kCS * 4) || kThreadsS % (g.H / kCS)) return 0;
-  if ((g.H / (kThreadsS / (g.H / kCS))) % 4) return 0;
+  {
+    const int FP = g.H / kCS / 2;  // feature pairs per CTA: a thread owns a pair x one k-slice
+    if (FP <= 0 || kThreadsS % FP || (g.H / (kThreadsS / FP)) % 4) return 0;
+  }
   if (ctx->small_clusters <= 0) return 0;
   const int FS = g.H / kCS, K0p = ((g.D + g.Dc + 3) & ~3) + 1, OR = (g.D + kCS - 1) / kCS;
   int epc = kThreadsS / FS < 8 ? kThreadsS / FS : 8;
