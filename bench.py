@@ -470,7 +470,7 @@ def bench_strong(args, dev, rank, world):
     with torch.no_grad():
         chains_l = torch.stack([model(cond={"state": obs_l[s]}, env_offset=e0).chains for s in range(n_steps)])
         lp_l = model.get_logprobs({"state": obs_l.flatten(0, 1)}, chains_l.flatten(0, 1)).view(n_steps, E, ft, Ta, Da)
-        val_l = model.critic({"state": obs_l.flatten(0, 1)}).view(n_steps, E)
+        val_l = model.values({"state": obs_l.flatten(0, 1)}).view(n_steps, E)
     adv_l = torch.randn((n_steps, E), device=dev, generator=g)
     N = n_steps * E_glob
     obs_k = D.gather_env_dim(obs_l, E_glob).view(N, w["cond_steps"], w["obs_dim"]).contiguous()
@@ -547,7 +547,7 @@ def bench_update(args, w, model, dev, E, rank, world):
         chunk = 32768
         for s in range(0, N, chunk):
             logprobs_k[s:s + chunk] = model.get_logprobs({"state": obs_k[s:s + chunk]}, chains_k[s:s + chunk]).view(-1, ft, Ta, Da)
-        values_k = model.critic({"state": obs_k}).view(-1)
+        values_k = model.values({"state": obs_k})
     # ---- once-per-iteration prologue (reference train_ppo_diffusion_agent.py:197-279): old log-probs of every stored
     # chain (dppo_chain_logprobs, teacher-forced chain kernel), running reward scaling + GAE (float64 scan kernels)
     from dppo_b200 import engine as E_

@@ -203,15 +203,15 @@ class TrainPPODiffusionAgent:
         logprobs = torch.empty((n * E, ft, self.horizon_steps, self.action_dim), dtype=torch.float32, device=self.device)
         for s in range(0, n * E, self.logprob_batch_size):
             e = min(n * E, s + self.logprob_batch_size)
-            values[s:e] = self.model.critic({"state": obs_k[s:e]}).view(-1)
+            values[s:e] = self.model.values({"state": obs_k[s:e]})
             logprobs[s:e] = self.model.get_logprobs({"state": obs_k[s:e]}, chains_k[s:e]).view(e - s, ft, self.horizon_steps,
                                                                                              self.action_dim)
         f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)  # noqa: E731
         reward_dev = f64(reward_trajs)
         if self.reward_scale_running:
             reward_dev = self.running_reward_scaler(reward=reward_dev, first=f64(firsts_trajs[:-1]))
-        next_value = self.model.critic({"state": torch.from_numpy(np.ascontiguousarray(last_obs["state"], dtype=np.float32))
-                                        .to(self.device)}).view(-1)
+        next_value = self.model.values({"state": torch.from_numpy(np.ascontiguousarray(last_obs["state"], dtype=np.float32))
+                                        .to(self.device)})
         adv, ret = E_.gae(reward_dev, f64(terminated_trajs), values.view(n, E).double(), next_value.double(),
                           self.gamma, self.gae_lambda, self.reward_scale_const)
         return values.view(n, E), logprobs.view(n, E, ft, self.horizon_steps, self.action_dim), adv.float(), ret.float()

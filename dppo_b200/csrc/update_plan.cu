@@ -769,6 +769,29 @@ extern "C" int dppo_update_forward(dppo_update* u, const dppo_update_batch* bt, 
   return DPPO_OK;
 }
 
+// critic(obs) for n_rows observation rows [n_rows, cond_dim] (no gather): the value pass of the rollout buffer
+// (train_ppo_diffusion_agent.py:197-206, 259-263) through the same row-GEMM kernels as the minibatch forward
+extern "C" int dppo_update_values(dppo_update* u, const float* obs, int n_rows, float* vpred_out, void* stream) {
+  if (!u || !obs || !vpred_out) return set_error("dppo_update_values: null argument"), DPPO_ERR_INVALID;
+  if (!u->bound) return set_error("dppo_update_values: parameters not bound (dppo_update_bind)"), DPPO_ERR_STATE;
+  if (n_rows < 0 || n_rows > u->max_rows)
+    return set_error("dppo_update_values: %d rows outside [0, %d]", n_rows, u->max_rows), DPPO_ERR_INVALID;
+  if (n_rows == 0) return DPPO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const MlpGeom& g = u->ctx->g;
+  u->n_rows = 0;  // the saved activations no longer belong to a minibatch: a backward call needs a new forward
+  PackArgs p{};
+  p.ft = u->ctx->ft, p.chain_stride = int64_t(u->ctx->ft + 1) * g.D, p.chain_d = g.D;
+  p.R = n_rows;
+  p.n_seg = 1;
+  p.seg[0] = PackSeg{obs, g.Dc_in, 0, g.Dc_in, 0};
+  p.FCp = u->FCobs, p.out = u->OBS;
+  URUN(launch_pack_rows(p, st));
+  URUN(launch_pack_weights(u->d_jobs + u->n_jobs_actor, u->n_jobs - u->n_jobs_actor, u->max_job, st));
+  URUN(resmlp_forward(u, u->critic, n_rows, vpred_out, st));
+  return DPPO_OK;
+}
+
 extern "C" int dppo_update_backward(dppo_update* u, const float* grad_eps, const float* grad_vpred, const float* scale_pg,
                                     const float* scale_v, float vf_coef, int with_actor, int with_critic, void* stream) {
   if (!u) return set_error("dppo_update_backward: null argument"), DPPO_ERR_INVALID;

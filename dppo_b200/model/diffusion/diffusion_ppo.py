@@ -116,6 +116,29 @@ class PPODiffusion(VPGDiffusion):
             self._update_plan = plan = UpdatePlan(self, rows)
         return plan
 
+    @torch.no_grad()
+    def values(self, cond):
+        """critic(cond) -> (rows,) for the value pass over the rollout buffer and the bootstrap value (reference
+        train_ppo_diffusion_agent.py:197-206, 259-263).  On the tensor-core update path this runs the critic through the
+        same hand-written row GEMMs as the minibatch forward (dppo_update_values), in chunks of the plan's workspace;
+        otherwise it is the critic module's own forward."""
+        state = cond["state"]
+        rows = state.shape[0]
+        if rows == 0 or not state.is_cuda or self.fused_update_reason() is not None:
+            return self.critic(cond).view(-1)
+        from dppo_b200.update_engine import _c32
+
+        flat = _c32(state, (rows, -1))
+        plan = getattr(self, "_update_plan", None)
+        if plan is None or plan.engine is not self.engine(sync=False):
+            plan = self.update_plan(min(rows, 16384))
+        plan.bind_model(self)
+        out = torch.empty(rows, dtype=torch.float32, device=flat.device)
+        for s in range(0, rows, plan.max_rows):
+            e = min(rows, s + plan.max_rows)
+            plan.values(flat[s:e], out[s:e])
+        return out
+
     def _loss_fused(self, obs, chains_prev, chains_next, denoising_inds, returns, oldvalues, advantages, oldlogprobs,
                     reward_horizon):
         from dppo_b200.engine import _mlp_param_list

@@ -115,6 +115,14 @@ class UpdatePlan:
         _lib.check(self.lib.dppo_update_forward(self.handle, C.byref(batch), _lib.ptr(eps_out), _lib.ptr(vpred_out),
                                                 _lib.stream_ptr()), "dppo_update_forward")
 
+    def values(self, obs, out=None):
+        """critic(obs) for (rows, cond_dim) observation rows, rows <= max_rows (bind_model first)."""
+        rows = obs.shape[0]
+        out = torch.empty(rows, dtype=torch.float32, device=obs.device) if out is None else out
+        _lib.check(self.lib.dppo_update_values(self.handle, _lib.ptr(obs), rows, _lib.ptr(out), _lib.stream_ptr()),
+                   "dppo_update_values")
+        return out
+
     def backward(self, grad_eps, grad_v, scale_pg=None, scale_v=None, vf_coef=1.0, with_actor=True, with_critic=True):
         _lib.check(self.lib.dppo_update_backward(self.handle, _lib.ptr(grad_eps), _lib.ptr(grad_v), _lib.ptr(scale_pg),
                                                  _lib.ptr(scale_v), float(vf_coef), int(with_actor), int(with_critic),

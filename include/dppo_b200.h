@@ -255,6 +255,11 @@ int dppo_update_bind(dppo_update* up, const float* const* actor_params, float* c
  * buffers (dppo_update_buffers).                                                                                   */
 int dppo_update_forward(dppo_update* up, const dppo_update_batch* batch, float* eps_out, float* vpred_out,
                         void* stream);
+/* critic(obs) -> vpred_out [n_rows] for plain observation rows obs [n_rows, cond_dim] (n_rows <= max_rows): the value
+ * pass over the rollout buffer and the bootstrap value (train_ppo_diffusion_agent.py:197-206, 259-263;
+ * common/critic.py:40-54) on the same kernels as the minibatch forward.  Invalidates the activations a later
+ * dppo_update_backward would need (call dppo_update_forward again first).                                          */
+int dppo_update_values(dppo_update* up, const float* obs, int n_rows, float* vpred_out, void* stream);
 /* Back-propagate grad_eps [n_rows, D] / grad_vpred [n_rows] of the last forward into the bound gradient tensors.
  * scale_pg / scale_v: optional DEVICE scalars multiplied into the two gradients (autograd's incoming factors),
  * vf_coef an immediate factor on grad_vpred.  with_actor = 0 skips actor_ft (critic warm-up iterations).          */

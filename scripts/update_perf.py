@@ -47,7 +47,7 @@ def main():
         logprobs_k = torch.empty((N, ft, Ta, Da), device=dev)
         for s in range(0, N, 32768):
             logprobs_k[s:s + 32768] = model.get_logprobs({"state": obs_k[s:s + 32768]}, chains_k[s:s + 32768]).view(-1, ft, Ta, Da)
-        values_k = model.critic({"state": obs_k}).view(-1)
+        values_k = model.values({"state": obs_k})
     adv_k = torch.randn(N, device=dev, generator=g)
     ret_k = adv_k + values_k
     opt_a = FlatAdamW(model.actor_ft.parameters(), lr=w["train"]["actor_lr"], weight_decay=0)

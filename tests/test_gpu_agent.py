@@ -31,14 +31,16 @@ def test_prologue_matches_oracle_gae_and_model_calls(tmp_path):
     # values / log-probs are the model's own calls on the flattened (step, env) rows
     obs_k = obs_buf.view(-1, 1, w["obs_dim"])
     with torch.no_grad():
-        v_ref = ag.model.critic({"state": obs_k}).view(ag.n_steps, ag.n_envs)
+        v_ref = ag.model.values({"state": obs_k}).view(ag.n_steps, ag.n_envs)
+        v_mod = ag.model.critic({"state": obs_k}).view(ag.n_steps, ag.n_envs)  # the torch module (library GEMM route)
         lp_ref = ag.model.get_logprobs({"state": obs_k}, chains_buf.view(-1, *chains_buf.shape[2:]))
     assert torch.equal(values, v_ref) and torch.equal(logprobs.view_as(lp_ref), lp_ref)
+    np.testing.assert_allclose(values.cpu().numpy(), v_mod.cpu().numpy(), rtol=1e-4, atol=1e-5)
     # GAE (float64 kernel) against the oracle's restatement of the reference's numpy loop, with the same scaled rewards
     scaler = O.RunningRewardScaler(ag.n_envs)
     rew_s = scaler(rew0.T, firsts[:-1].T).T
     with torch.no_grad():
-        nxt = ag.model.critic({"state": torch.from_numpy(last_obs["state"]).cuda()}).view(-1).double().cpu().numpy()
+        nxt = ag.model.values({"state": torch.from_numpy(last_obs["state"]).cuda()}).double().cpu().numpy()
     adv_o, ret_o = O.gae(rew_s, term, values.double().cpu().numpy(), nxt, ag.gamma, ag.gae_lambda, 1.0)
     np.testing.assert_allclose(adv.cpu().numpy(), adv_o, rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(ret.cpu().numpy(), ret_o, rtol=1e-6, atol=1e-6)

@@ -210,3 +210,24 @@ def test_ratio_is_one_before_any_optimiser_step():
     ratio = torch.exp(new - old)
     assert float((ratio - 1).abs().max()) < 1e-4, float((ratio - 1).abs().max())
     assert float((vpred - val_k[b]).abs().max()) < 1e-4 * max(1.0, float(val_k.abs().max()))
+
+
+@pytest.mark.parametrize("case,rows", [("hopper", 1), ("hopper", 1000), ("walker2d", 40000), ("furniture", 777), ("transport", 130)])
+def test_values_match_the_critic_module_in_float64(case, rows):
+    """PPODiffusion.values (dppo_update_values: the critic through the tcgen05 row GEMMs, chunked over the plan's
+    workspace) against the critic module evaluated in float64 - the value pass of train_ppo_diffusion_agent.py:197-206."""
+    import copy
+
+    w = get_workload(GOLDEN_CASES[case]["workload"])
+    model = build_model(w, DEV, our_classes())
+    assert model.fused_update_reason() is None
+    g = torch.Generator().manual_seed(11)
+    obs = (torch.rand(rows, w["cond_steps"], w["obs_dim"], generator=g) * 2 - 1).to(DEV)
+    got = model.values({"state": obs})
+    ref = copy.deepcopy(model.critic).double()
+    with torch.no_grad():
+        want = ref({"state": obs.double()}).view(-1)
+    assert got.shape == (rows,)
+    assert _relerr(got, want) < 1e-4, _relerr(got, want)
+    again = model.values({"state": obs[: min(rows, 7)]})  # a second, shorter call reuses the bound plan
+    assert _relerr(again, want[: min(rows, 7)]) < 1e-4
