@@ -355,15 +355,16 @@ def run_b200(args, w, E, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "chain_unet_kernel" if w["actor"]["kind"] == "unet" else "chain_mlp_kernel",
                          "note": ("algorithmic FLOPs S*F_net*E (1x); split3 issues 3 bf16 MMAs per logical MMA so frac <= 1/3; "
-                                  "the kernel is bound by the per-SM L2->shared weight ingest (34.7 B/cycle/SM measured), "
-                                  "see DESIGN.md section 3; traffic = ncu dram bytes per launch (bytes); "
+                                  "inside a layer the kernel runs at the per-SM L2->shared weight ingest (34.7 B/cycle/SM "
+                                  "measured), between the 80 dependent layers of a launch at hand-off latency, see DESIGN.md "
+                                  "sections 3 and 6b; traffic = ncu dram bytes per launch (bytes); "
                                   + ("peak = MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone), of measured"
                                      if peaks else "peak = fallback 1.59 PF, of fallback"))},
             "wall_s_timed_region": wall,
             "update": upd,
         }
         line["strong_scaling"] = strong
-        if args.cpu_baseline:
+        if args.cpu_baseline and world == 1:  # rank 0 at N = 1 only: under torchrun the other ranks' host threads compete for the cores
             cores = os.cpu_count() or 1
             reps = max(3, min(10, int(15.0 / max(0.05, 0.16e-3 * E))))
             times, kind = cpu_chain_seconds(w, E, reps, 1, cores)
