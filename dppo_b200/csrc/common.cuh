@@ -60,6 +60,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polling wait (mbarrier.test_wait, no suspend): for waits where the whole CTA has nothing else to issue and the wake-up
+// latency of the suspending try_wait (NANOSLEEP.SYNCS) is on the critical path.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xFFFF) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        printf("dppo_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
 // one lane of the (converged) warp gets true; keeps surrounding address arithmetic in the uniform datapath
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
