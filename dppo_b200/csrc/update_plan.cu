@@ -201,7 +201,8 @@ __device__ __forceinline__ float mish_grad_exact_u(float x) {
   return th + x * sg * (1.f - th * th);
 }
 
-// grid = ft blocks of 128 threads: SinusoidalPosEmb -> Linear -> Mish -> Linear (reference modules.py:14-27,
+// grid = (ft, ceil(H / 128)) blocks of 128 threads (every block recomputes the tiny MLP of its denoising index and owns
+// 128 features of TB; blockIdx.y == 0 also stores the intermediates): SinusoidalPosEmb -> Linear -> Mish -> Linear (reference modules.py:14-27,
 // mlp_diffusion.py:191-196) for the timestep of denoising index d, then TB[d][f] = b0[f] + W0[f, D:D+td] . temb
 // (same arithmetic as time_bias_table_kernel in pack.cu; the intermediates are kept for the backward kernel)
 __global__ void time_table_fwd_kernel(const float* __restrict__ tw1, const float* __restrict__ tb1,
@@ -220,12 +221,13 @@ __global__ void time_table_fwd_kernel(const float* __restrict__ tw1, const float
     s_emb[threadIdx.x + half] = cosf(ph);
   }
   __syncthreads();
-  if (threadIdx.x < td) emb[d * td + threadIdx.x] = s_emb[threadIdx.x];
+  const bool keep = blockIdx.y == 0;
+  if (keep && threadIdx.x < td) emb[d * td + threadIdx.x] = s_emb[threadIdx.x];
   if (threadIdx.x < 2 * td) {
     float acc = 0.f;
     for (int j = 0; j < td; ++j) acc += s_emb[j] * tw1[threadIdx.x * td + j];
     acc += tb1[threadIdx.x];
-    hpre[d * 2 * td + threadIdx.x] = acc;
+    if (keep) hpre[d * 2 * td + threadIdx.x] = acc;
     s_hid[threadIdx.x] = mish_exact_u(acc);
   }
   __syncthreads();
@@ -234,10 +236,11 @@ __global__ void time_table_fwd_kernel(const float* __restrict__ tw1, const float
     for (int j = 0; j < 2 * td; ++j) acc += s_hid[j] * tw2[threadIdx.x * 2 * td + j];
     acc += tb2[threadIdx.x];
     s_out[threadIdx.x] = acc;
-    temb[d * td + threadIdx.x] = acc;
+    if (keep) temb[d * td + threadIdx.x] = acc;
   }
   __syncthreads();
-  for (int f = threadIdx.x; f < H; f += blockDim.x) {
+  const int f = blockIdx.y * blockDim.x + threadIdx.x;
+  if (f < H) {
     float acc = 0.f;
     const float* w = W0 + size_t(f) * in0 + D;
     for (int j = 0; j < td; ++j) acc += w[j] * s_out[j];
@@ -271,8 +274,8 @@ __global__ void scatter_dw0_kernel(const float* __restrict__ dW0p, int H, int in
 
 // G[d][f] = dW0p[f][Dc + D + d] is the gradient w.r.t. TB[d][f] = b0[f] + W0[f, D:D+td] . temb[d]; three small kernels
 // carry it back through the time MLP.  All outputs are accumulated (+=) into the parameter gradients.
-// (a) grid = ft blocks: dtemb[d][j] = sum_f G[d][f] W0[f][D + j] (one warp per j, lanes over f); G is also copied to a
-//     contiguous [ft][H] scratch for (c)
+// (a) grid = (ft, ceil(td / 8)) blocks of 8 warps: dtemb[d][j] = sum_f G[d][f] W0[f][D + j] (one warp per j, lanes over f);
+//     G is also copied to a contiguous [ft][H] scratch for (c) by the blocks with blockIdx.y == 0
 __global__ void __launch_bounds__(256) time_bwd_a_kernel(const float* __restrict__ dW0p, int K0p, int gcol, int H, int td, int D,
                                                          int in0, const float* __restrict__ W0, float* __restrict__ Gs,
                                                          float* __restrict__ dtemb) {
@@ -281,12 +284,13 @@ __global__ void __launch_bounds__(256) time_bwd_a_kernel(const float* __restrict
   for (int f = threadIdx.x; f < H; f += blockDim.x) {
     const float v = dW0p[size_t(f) * K0p + gcol + d];
     s_g[f] = v;
-    Gs[size_t(d) * H + f] = v;
+    if (blockIdx.y == 0) Gs[size_t(d) * H + f] = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < td; j += nw) {
+  for (int j = blockIdx.y * nw + warp; j < td; j += nw * gridDim.y) {
     float s = 0.f;
+#pragma unroll 8
     for (int f = lane; f < H; f += 32) s += s_g[f] * W0[size_t(f) * in0 + D + j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -337,16 +341,17 @@ __global__ void __launch_bounds__(256) time_bwd_b_kernel(int ft, int td, const f
   }
 }
 
-// (c) one thread per feature: db0[f] += sum_d G[d][f], dW0[f][D + j] += sum_d G[d][f] temb[d][j]
+// (c) one thread per (feature, column j <= td): dW0[f][D + j] += sum_d G[d][f] temb[d][j]; j == td: db0[f] += sum_d G[d][f]
 __global__ void time_bwd_c_kernel(const float* __restrict__ Gs, int ft, int H, int td, int D, int in0,
                                   const float* __restrict__ temb, float* __restrict__ dW0, float* __restrict__ db0) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = i / (td + 1), j = i - f * (td + 1);
   if (f >= H) return;
-  float sb = 0.f;
-  for (int d = 0; d < ft; ++d) sb += Gs[size_t(d) * H + f];
-  db0[f] += sb;
-  for (int j = 0; j < td; ++j) {
-    float s = 0.f;
+  float s = 0.f;
+  if (j == td) {
+    for (int d = 0; d < ft; ++d) s += Gs[size_t(d) * H + f];
+    db0[f] += s;
+  } else {
     for (int d = 0; d < ft; ++d) s += Gs[size_t(d) * H + f] * temb[d * td + j];
     dW0[size_t(f) * in0 + D + j] += s;
   }
@@ -685,7 +690,7 @@ static int actor_forward(dppo_update* u, int R, float* eps_out, cudaStream_t st)
   const dppo_ctx* ctx = u->ctx;
   const MlpGeom& g = ctx->g;
   const int in0 = g.D + g.td + g.Dc;
-  time_table_fwd_kernel<<<ctx->ft, 128, 0, st>>>(u->tw1, u->tb1, u->tw2, u->tb2, u->W0, u->b0, g.td, g.D, in0, g.H, u->d_ts,
+  time_table_fwd_kernel<<<dim3(ctx->ft, (g.H + 127) / 128), 128, 0, st>>>(u->tw1, u->tb1, u->tw2, u->tb2, u->W0, u->b0, g.td, g.D, in0, g.H, u->d_ts,
                                                  u->t_emb, u->t_hpre, u->t_temb, u->TB);
   assemble_w0_kernel<<<(g.H * u->K0p + 255) / 256, 256, 0, st>>>(u->W0, u->TB, g.H, in0, g.D, g.td, g.Dc, ctx->ft, u->K0p, u->W0p);
   URUN(launch_pack_weights(u->d_jobs, u->n_jobs_actor, u->max_job, st));
@@ -731,11 +736,11 @@ static int actor_backward(dppo_update* u, int R, cudaStream_t st) {
     URUN(launch_wgrad(wgrad_args(u->GC0, opmat_chunks(g.CH), u->OBS, u->FCobs, u->c0, R), u->sm_count, st));
   }
   scatter_dw0_kernel<<<(g.H * (g.Dc + g.D) + 255) / 256, 256, 0, st>>>(u->dW0p, g.H, in0, g.D, g.td, g.Dc, u->K0p, u->dW0);
-  time_bwd_a_kernel<<<ctx->ft, 256, size_t(g.H) * 4, st>>>(u->dW0p, u->K0p, g.Dc + g.D, g.H, g.td, g.D, in0, u->W0, u->t_G,
+  time_bwd_a_kernel<<<dim3(ctx->ft, (g.td + 7) / 8), 256, size_t(g.H) * 4, st>>>(u->dW0p, u->K0p, g.Dc + g.D, g.H, g.td, g.D, in0, u->W0, u->t_G,
                                                            u->t_dtemb);
   time_bwd_b_kernel<<<1, 256, 0, st>>>(ctx->ft, g.td, u->tw2, u->t_emb, u->t_hpre, u->t_dtemb, u->t_hid, u->t_dpre, u->dtw1,
                                        u->dtb1, u->dtw2, u->dtb2);
-  time_bwd_c_kernel<<<(g.H + 127) / 128, 128, 0, st>>>(u->t_G, ctx->ft, g.H, g.td, g.D, in0, u->t_temb, u->dW0, u->db0);
+  time_bwd_c_kernel<<<(g.H * (g.td + 1) + 127) / 128, 128, 0, st>>>(u->t_G, ctx->ft, g.H, g.td, g.D, in0, u->t_temb, u->dW0, u->db0);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "dppo_update actor backward");
 }
