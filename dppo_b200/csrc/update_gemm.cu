@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(kUThreads, 1) ugemm_rows_kernel(const RowGemmA
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int rt = t / a.NT, nt = t - rt * a.NT;
       const uint8_t* a_src = a.A + size_t(rt) * a.FCa * 2 * kImg;
-      const uint8_t* b_src = a.B + size_t(nt) * a.KC * 2 * b_plane;
+      // packed tile that holds this (possibly narrower) tile, and the rows of it
+      const uint32_t p_plane = uint32_t(a.NTP) * 128u;
+      const int sub_per = a.NTP / a.NTILE, pnt = nt / sub_per;
+      const uint8_t* b_src = a.B + size_t(pnt) * a.KC * 2 * p_plane + size_t(nt - pnt * sub_per) * b_plane;
       for (int kc = 0; kc < a.KC; ++kc) {
         const long long tw = clock64();
         mbar_wait(&bar.empty[stage], phase ^ 1);
@@ -434,7 +437,12 @@ __global__ void __launch_bounds__(kUThreads, 1) ugemm_rows_kernel(const RowGemmA
           uint8_t* dst = smem + size_t(stage) * stage_bytes;
           mbar_arrive_expect_tx(&bar.full[stage], stage_bytes);
           bulk_g2s(dst, a_src + size_t(kc) * 2 * kImg, 2 * kImg, &bar.full[stage]);
-          bulk_g2s(dst + 2 * kImg, b_src + size_t(kc) * 2 * b_plane, 2 * b_plane, &bar.full[stage]);
+          if (sub_per == 1) {
+            bulk_g2s(dst + 2 * kImg, b_src + size_t(kc) * 2 * b_plane, 2 * b_plane, &bar.full[stage]);
+          } else {  // hi and lo rows of the narrow tile are b_plane bytes each, p_plane apart in the packed tile
+            bulk_g2s(dst + 2 * kImg, b_src + size_t(kc) * 2 * p_plane, b_plane, &bar.full[stage]);
+            bulk_g2s(dst + 2 * kImg + b_plane, b_src + size_t(kc) * 2 * p_plane + p_plane, b_plane, &bar.full[stage]);
+          }
         }
         __syncwarp();
         if (++stage == uint32_t(a.nstage)) stage = 0, phase ^= 1;
@@ -1098,8 +1106,9 @@ constexpr size_t kUSmemBudget = 232448;
 int launch_row_gemm(const RowGemmArgs& a0, int sm_count, cudaStream_t st) {
   RowGemmArgs a = a0;
   if (a.R <= 0) return DPPO_OK;
-  if (a.NTILE < 16 || a.NTILE > 256 || a.NTILE % 16 || a.KC < 1 || a.NT < 1)
-    return set_error("row gemm: bad tile geometry NTILE=%d KC=%d NT=%d", a.NTILE, a.KC, a.NT), DPPO_ERR_INVALID;
+  if (a.NTP == 0) a.NTP = a.NTILE;
+  if (a.NTILE < 16 || a.NTILE > 256 || a.NTILE % 16 || a.KC < 1 || a.NT < 1 || a.NTP % a.NTILE)
+    return set_error("row gemm: bad tile geometry NTILE=%d (packed %d) KC=%d NT=%d", a.NTILE, a.NTP, a.KC, a.NT), DPPO_ERR_INVALID;
   if (a.out_op && ((a.op_col0 & 63) || (a.NT > 1 && (a.NTILE & 63)) || (a.op_col0 + a.NT * a.NTILE + 63) / 64 > a.FCo))
     return set_error("row gemm: operand output columns [%d, %d) must cover whole 64-feature chunks of %d", a.op_col0,
                      a.op_col0 + a.NT * a.NTILE, a.FCo), DPPO_ERR_INVALID;
@@ -1220,12 +1229,31 @@ int launch_ln_fwd(const float* x, int ld, int R, int F, const float* g, const fl
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ln_fwd_kernel launch");
 }
 
+// Column ranges per row tile of the LayerNorm kernels (grid.y): 4 for wide rows (more CTAs, more bytes in flight), and more
+// when a minibatch shard has too few row tiles to fill the device (2200 rows = 18 row tiles: 72 CTAs at split 4 took as
+// long as 8x the rows).
+static int ln_sm_count() {
+  static int n = 0;
+  if (n <= 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 1;
+  }
+  return n;
+}
+static int ln_column_split(int R, int F) {
+  const int ncc = F >> 6, rt = (R + 127) / 128;
+  int split = ncc >= 8 ? 4 : (ncc >= 2 ? 2 : 1);
+  while (rt * split < 2 * ln_sm_count() && split * 2 <= ncc && ncc % (split * 2) == 0) split *= 2;
+  return split;
+}
+
 int launch_ln_fwd_tiled(const float* x, const float* sums, int R, int F, const float* g, const float* b, float eps, int act,
                         float* stats, uint8_t* out_op, int FCo, cudaStream_t st) {
   if (F % 64 || F < 64 || ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15))
     return set_error("ln_fwd_tiled: F=%d unsupported or unaligned parameters", F), DPPO_ERR_INVALID;
   if (R <= 0) return DPPO_OK;
-  const int split = (F >> 6) >= 8 ? 4 : ((F >> 6) >= 2 ? 2 : 1);  // column ranges per row tile: more CTAs, more bytes in flight
+  const int split = ln_column_split(R, F);
   ln_fwd_tiled_kernel<<<dim3((R + 127) / 128, split), 256, 2 * kImg, st>>>(x, sums, R, F, g, b, eps, act, stats, out_op, FCo);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ln_fwd_tiled_kernel launch");
@@ -1243,7 +1271,7 @@ int launch_ln_bwd_tiled(const float* dz, const float* sums, const float* x, cons
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ln_bwd_tiled_kernel)");
     configured = true;
   }
-  const int split = (F >> 6) >= 8 ? 4 : ((F >> 6) >= 2 ? 2 : 1);
+  const int split = ln_column_split(R, F);
   ln_bwd_tiled_kernel<<<dim3((R + 127) / 128, split), 256, smem, st>>>(dz, sums, x, stats, g, R, F, res, out_f32, out_op, FCo, dg, db);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? DPPO_OK : cuda_fail(e, "ln_bwd_tiled_kernel launch");

@@ -37,6 +37,8 @@ struct RowGemmArgs {
   int R, RT;          // rows, row tiles of 128
   int KC;             // 64-wide contraction chunks
   int N, NTILE, NT;   // real output features; tile width (multiple of 16, <= 256); number of column tiles
+  int NTP;            // tile width B was PACKED for (0 = NTILE); a multiple of NTILE: a call on few rows runs narrower tiles
+                      // (more work units for the same bytes) on the same packed weights
   // ---- epilogue, per element v = acc[r][n].  fp32 side tensors are row-major [R][ld] (mode 0) or "tiled" (mode 1):
   // [row tile][n / 8][128 rows][8 floats], ld = feature count (multiple of 8) - the layout in which a warp of the
   // epilogue (lane = row, 8 consecutive features per access) reads / writes 1 KiB contiguous.

@@ -36,6 +36,7 @@ struct LayerW {
   uint8_t* Bf = nullptr;  // forward tiles (rows = N output features, contraction K)
   uint8_t* Bd = nullptr;  // dgrad tiles (rows = K input features, contraction N), null when no dgrad is needed
   int bd_rows = 0, bd_col0 = 0;  // dgrad restricted to input columns [bd_col0, bd_col0 + bd_rows)
+  int nt_f = 0, nt_d = 0;        // output-tile widths (NTILE) the forward / dgrad tiles are packed for, see call_ntile
 };
 
 struct BlockW {
@@ -167,23 +168,37 @@ static int alloc_resmlp(dppo_update* u, ResMlp& m, int R) {
   return DPPO_OK;
 }
 
+// Output-tile width of one row-GEMM CALL on `rows` rows, given the width the weights are packed for.  A work unit is one
+// 128-row x NTILE tile and costs its own ingest (128 x K of A plus NTILE x K of W, hi + lo); a shard of a minibatch
+// (strong scaling: 2200 rows = 18 row tiles) with 256-wide tiles leaves half of the SMs without a unit, so the call runs
+// narrower tiles of the same packed weights (RowGemmArgs.NTP) while twice the units still fit in one wave.
+static int call_ntile(int packed, int N, int rows, int sm_count) {
+  int nt = packed;
+  if (sm_count <= 0) return nt;
+  const int rt = (rows + 127) / 128;
+  while (nt >= 128 && nt % 128 == 0 && rt * ((N + nt / 2 - 1) / (nt / 2)) <= sm_count) nt /= 2;
+  return nt;
+}
+
 static int alloc_layer_tiles(dppo_update* u, LayerW& L, bool dgrad) {
-  UALLOC(L.Bf, packed_weight_bytes(L.N, L.K, row_gemm_ntile(L.N)));
+  L.nt_f = row_gemm_ntile(L.N);
+  UALLOC(L.Bf, packed_weight_bytes(L.N, L.K, L.nt_f));
   if (dgrad) {
     if (L.bd_rows == 0) L.bd_rows = L.K, L.bd_col0 = 0;
-    UALLOC(L.Bd, packed_weight_bytes(L.bd_rows, L.N, row_gemm_ntile(L.bd_rows)));
+    L.nt_d = row_gemm_ntile(L.bd_rows);
+    UALLOC(L.Bd, packed_weight_bytes(L.bd_rows, L.N, L.nt_d));
   }
   return DPPO_OK;
 }
 
 static void add_jobs(std::vector<PackWJob>& jobs, const LayerW& L) {
   PackWJob j{};
-  j.W = L.W, j.s_row = L.ld, j.s_col = 1, j.rows = L.N, j.K = L.K, j.NTILE = row_gemm_ntile(L.N);
+  j.W = L.W, j.s_row = L.ld, j.s_col = 1, j.rows = L.N, j.K = L.K, j.NTILE = L.nt_f;
   j.NT = (L.N + j.NTILE - 1) / j.NTILE, j.KC = (L.K + 63) / 64, j.out = L.Bf;
   jobs.push_back(j);
   if (L.Bd) {
     PackWJob d{};
-    d.W = L.W + L.bd_col0, d.s_row = 1, d.s_col = L.ld, d.rows = L.bd_rows, d.K = L.N, d.NTILE = row_gemm_ntile(L.bd_rows);
+    d.W = L.W + L.bd_col0, d.s_row = 1, d.s_col = L.ld, d.rows = L.bd_rows, d.K = L.N, d.NTILE = L.nt_d;
     d.NT = (d.rows + d.NTILE - 1) / d.NTILE, d.KC = (d.K + 63) / 64, d.out = L.Bd;
     jobs.push_back(d);
   }
@@ -358,6 +373,7 @@ __global__ void time_bwd_c_kernel(const float* __restrict__ Gs, int ft, int H, i
 }
 
 // ------------------------------------------------------------------------------------------------ residual MLP program
+static int g_plan_sm_count = 0;  // SM count of the device, set by dppo_update_create (0: calls keep the packed tile width)
 static RowGemmArgs gemm_args(const uint8_t* A, int FCa, const LayerW& L, bool dgrad, int R) {
   RowGemmArgs g{};
   g.A = A, g.FCa = FCa, g.R = R;
@@ -366,7 +382,8 @@ static RowGemmArgs gemm_args(const uint8_t* A, int FCa, const LayerW& L, bool dg
   } else {
     g.B = L.Bd, g.N = L.bd_rows, g.KC = (L.N + 63) / 64;
   }
-  g.NTILE = row_gemm_ntile(g.N);
+  g.NTP = dgrad ? L.nt_d : L.nt_f;
+  g.NTILE = call_ntile(g.NTP, g.N, R, g_plan_sm_count);
   g.NT = (g.N + g.NTILE - 1) / g.NTILE;
   return g;
 }
@@ -519,6 +536,7 @@ extern "C" int dppo_update_create(dppo_update** out, dppo_ctx* ctx, const dppo_r
   DPPO_CUDA(cudaSetDevice(ctx->device));
   dppo_update* u = new dppo_update();
   u->ctx = ctx, u->max_rows = max_rows, u->sm_count = ctx->sm_count;
+  g_plan_sm_count = ctx->sm_count;
   const int R = max_rows;
   int rc = [&]() -> int {
     ResMlp& a = u->actor;
