@@ -486,17 +486,22 @@ def bench_strong(args, dev, rank, world):
     bs = min(bs_glob, N * ft)
     lo, hi = D.minibatch_slice(bs, rank, world)
     fused = model.fused_update_reason() is None
+    overlap = grads.overlap_setup() if (fused and os.environ.get("DPPO_B200_OVERLAP", "1") == "1") else None
 
     def fwd_bwd(inds):
         grads.zero()
         if fused:
             model.update_minibatch(obs_k, chains_k, lp_k, ret_k, val_k, adv_k, inds, row_begin=lo, row_count=hi - lo,
-                                   reward_horizon=w["act_steps"], vf_coef=w["train"]["vf_coef"], scalars_out=grads.scalars)
+                                   reward_horizon=w["act_steps"], vf_coef=w["train"]["vf_coef"], scalars_out=grads.scalars,
+                                   actor_event=overlap[0] if overlap else None)
         else:
             res = model.loss_gathered(obs_k, chains_k, lp_k, ret_k, val_k, adv_k, inds, row_begin=lo, row_count=hi - lo,
                                       reward_horizon=w["act_steps"], scalars_out=grads.scalars)
             (res[0] + w["train"]["vf_coef"] * res[2]).backward()
-        grads.allreduce()
+        if overlap:  # actor segment next to the critic backward, the rest behind it (what the agent does)
+            grads.allreduce_split()
+        else:
+            grads.allreduce()
 
     from dppo_b200.agent.finetune.graphed import MinibatchStep
 
@@ -596,18 +601,22 @@ def bench_update(args, w, model, dev, E, rank, world):
     per_rank = bs // world
 
     fused = model.fused_update_reason() is None
+    overlap = grads.overlap_setup() if (fused and os.environ.get("DPPO_B200_OVERLAP", "1") == "1") else None
 
     def fwd_bwd(inds):
         grads.zero()
         if fused:  # the whole minibatch inside libdppo_b200 (hand-written tcgen05 forward / dgrad / wgrad kernels)
             model.update_minibatch(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo, row_count=hi - lo,
                                    reward_horizon=w["act_steps"], vf_coef=w["train"]["vf_coef"], with_actor=True,
-                                   scalars_out=grads.scalars)
+                                   scalars_out=grads.scalars, actor_event=overlap[0] if overlap else None)
         else:
             res = model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds, row_begin=lo,
                                       row_count=hi - lo, reward_horizon=w["act_steps"], scalars_out=grads.scalars)
             (res[0] + w["train"]["vf_coef"] * res[2]).backward()
-        grads.allreduce()  # gradients of both networks + loss diagnostics: one NCCL all-reduce
+        if overlap:  # multi-GPU: actor segment reduced next to the critic backward, the rest behind it
+            grads.allreduce_split()
+        else:
+            grads.allreduce()  # gradients of both networks + loss diagnostics: one NCCL all-reduce
 
     # the agent's minibatch unit: forward / backward / all-reduce + both AdamW steps + device-side KL check, one CUDA graph
     from dppo_b200.agent.finetune.graphed import MinibatchStep

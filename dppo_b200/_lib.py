@@ -21,7 +21,7 @@ EXPORTS = [
     "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain", "dppo_sample_nonfinite",
     "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64", "dppo_split3_pack", "dppo_reward_scale_f64", "dppo_adamw_flat",
     "dppo_update_create", "dppo_update_destroy", "dppo_update_bind", "dppo_update_forward", "dppo_update_backward",
-    "dppo_update_minibatch", "dppo_update_values", "dppo_update_buffers", "dppo_memset_zero", "dppo_adamw_flat_dev", "dppo_kl_check",
+    "dppo_update_minibatch", "dppo_update_values", "dppo_update_set_actor_event", "dppo_update_buffers", "dppo_memset_zero", "dppo_adamw_flat_dev", "dppo_kl_check",
 ]
 
 
@@ -144,6 +144,7 @@ def load(build_if_missing=True):
     lib.dppo_update_backward.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, vp]
     lib.dppo_update_minibatch.argtypes = [vp, C.POINTER(UpdateBatch), C.POINTER(LossHp), f32, i32, vp, vp, vp]
     lib.dppo_update_values.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.dppo_update_set_actor_event.argtypes = [vp, vp]
     lib.dppo_update_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.dppo_memset_zero.argtypes = [vp, C.c_size_t, vp]
     lib.dppo_adamw_flat_dev.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, vp, f32, vp, vp]

@@ -236,16 +236,24 @@ class TrainPPODiffusionAgent:
         fused = not self.use_bc_loss and self.model.fused_update_reason() is None
         with_actor = self.itr >= self.n_critic_warmup_itr and not self._actor_frozen
 
+        # multi-GPU: the actor's gradient segment is reduced next to the critic backward (two collectives, see
+        # FlatGradBuffer.allreduce_split); DPPO_B200_OVERLAP=0 keeps the single all-reduce behind the whole backward
+        overlap = self.grads.overlap_setup() if (fused and with_actor and os.environ.get("DPPO_B200_OVERLAP", "1") == "1") else None
+
         def fwd_bwd(inds_b):
-            """zero grads -> actor_ft / critic forward -> fused loss kernel -> backward -> one all-reduce (no host sync)"""
+            """zero grads -> actor_ft / critic forward -> fused loss kernel -> backward -> gradient all-reduce (no host sync)"""
             self.grads.zero()
             if fused:
                 # the whole minibatch inside libdppo_b200 (tcgen05 forward / dgrad / wgrad kernels, dppo_update_minibatch):
                 # gradients are accumulated straight into the views of the flat all-reduce buffer
                 self.model.update_minibatch(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
                                             row_count=hi - lo, reward_horizon=self.reward_horizon, vf_coef=self.vf_coef,
-                                            with_actor=with_actor, scalars_out=self.grads.scalars)
-                self.grads.allreduce()
+                                            with_actor=with_actor, scalars_out=self.grads.scalars,
+                                            actor_event=overlap[0] if overlap else None)
+                if overlap:
+                    self.grads.allreduce_split()
+                else:
+                    self.grads.allreduce()
                 return None
             res = self.model.loss_gathered(obs_k, chains_k, logprobs_k, ret_k, values_k, adv_k, inds_b, row_begin=lo,
                                            row_count=hi - lo, use_bc_loss=self.use_bc_loss,

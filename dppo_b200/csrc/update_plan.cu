@@ -81,6 +81,7 @@ using namespace dppo;
 struct dppo_update {
   dppo_ctx* ctx = nullptr;
   int max_rows = 0;
+  cudaEvent_t actor_done = nullptr;  // optional: recorded on the stream behind the actor backward (dppo_update_set_actor_event)
   int sm_count = 148;
   ResMlp actor, critic;
   // actor extras: time MLP, cond_mlp, assembled layer 0
@@ -826,6 +827,8 @@ extern "C" int dppo_update_backward(dppo_update* u, const float* grad_eps, const
     if (!grad_eps) return set_error("dppo_update_backward: grad_eps is null"), DPPO_ERR_INVALID;
     URUN(pack_grad(grad_eps, u->actor.Dout, u->actor.Dout, R, scale_pg, 1.f, u->actor.GOUT, u->actor.FCout, st));
     URUN(actor_backward(u, R, st));
+    // the actor gradients are final here: a caller overlaps their all-reduce with the critic backward below
+    if (u->actor_done) DPPO_CUDA(cudaEventRecord(u->actor_done, st));
   }
   if (with_critic) {
     if (!grad_vpred) return set_error("dppo_update_backward: grad_vpred is null"), DPPO_ERR_INVALID;
@@ -851,6 +854,14 @@ extern "C" int dppo_update_minibatch(dppo_update* u, const dppo_update_batch* bt
   }
   // loss = pg_loss + vf_coef * v_loss (the entropy term of a fixed-eta chain is a constant): grad_v is scaled by vf_coef
   return dppo_update_backward(u, u->geps, u->gv, nullptr, nullptr, vf_coef, with_actor, 1, stream);
+}
+
+// `event`: a cudaEvent_t (or NULL to switch it off) that every later dppo_update_backward / dppo_update_minibatch records
+// behind the actor backward, before the critic backward is enqueued
+extern "C" int dppo_update_set_actor_event(dppo_update* u, void* event) {
+  if (!u) return set_error("dppo_update_set_actor_event: null argument"), DPPO_ERR_INVALID;
+  u->actor_done = static_cast<cudaEvent_t>(event);
+  return DPPO_OK;
 }
 
 // stream-ordered zero fill (the flat gradient buffer before a minibatch) without a framework elementwise kernel

@@ -152,6 +152,31 @@ class FlatGradBuffer:
         if W > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
+    def overlap_setup(self):
+        """(event, stream) for allreduce_split: the event is handed to the update plan (UpdatePlan.set_actor_event), which
+        records it behind the actor backward.  None on CPU / a single process."""
+        _, W = world()
+        if W <= 1 or not self.flat.is_cuda or len(self.group_sizes) < 2:
+            return None
+        if getattr(self, "_overlap", None) is None:
+            ev = torch.cuda.Event()
+            ev.record()  # creates the cudaEvent_t
+            self._overlap = (ev, torch.cuda.Stream(device=self.flat.device))
+        return self._overlap
+
+    def allreduce_split(self):
+        """Two collectives instead of one: group 0 (actor_ft) starts as soon as the recorded event says its gradients are
+        final - issued from a side stream, so that it runs next to the critic backward still queued on the current stream -
+        the rest (critic + loss diagnostics) behind the current stream's work.  Both go through the process group's NCCL
+        stream in this order on every rank.  Captures into a CUDA graph as a fork / join."""
+        ev, side = self._overlap
+        cur = torch.cuda.current_stream()
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            dist.all_reduce(self.segment(0), op=dist.ReduceOp.SUM)
+        dist.all_reduce(self.flat[self.group_sizes[0]:], op=dist.ReduceOp.SUM)
+        cur.wait_stream(side)
+
     def release(self):
         """Drop the buffer (the parameters' .grad views included).  A buffer registered with the NCCL communicator must be
         gone before the process group is destroyed: destroy_process_group() with a live ncclMemAlloc'ed tensor hangs

@@ -160,13 +160,15 @@ class PPODiffusion(VPGDiffusion):
         return pg_loss, entropy_loss, v_loss, host[3], host[2], host[4], 0, eta_mean
 
     def update_minibatch(self, obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k, inds_all, row_begin=0,
-                         row_count=None, reward_horizon=4, vf_coef=0.5, with_actor=True, scalars_out=None):
+                         row_count=None, reward_horizon=4, vf_coef=0.5, with_actor=True, scalars_out=None, actor_event=None):
         """
         One PPO minibatch (slice) entirely inside libdppo_b200: gather -> actor_ft / critic forward -> fused loss ->
         backward of pg_loss + vf_coef * v_loss, gradients ACCUMULATED into the parameters' .grad tensors (the views of
         the agent's flat all-reduce buffer; the caller zeroes them).  Arguments as loss_gathered.  `scalars_out`
         (8 floats, device) receives the partial means [pg, v, kl, clipfrac, ratio, -, adv mean, adv std]; nothing is
-        read back to the host.  reference: train_ppo_diffusion_agent.py:316-364.
+        read back to the host.  `actor_event`: a recorded torch.cuda.Event the library records again behind the actor
+        backward (multi-GPU callers start the actor segment's all-reduce there, FlatGradBuffer.allreduce_split).
+        reference: train_ppo_diffusion_agent.py:316-364.
         """
         eng = self.engine(sync=False)
         row_count = inds_all.numel() - row_begin if row_count is None else row_count
@@ -183,6 +185,7 @@ class PPODiffusion(VPGDiffusion):
         batch = UpdatePlan._batch(row_count, inds_all.numel(), row_begin, obs=obs_k, chains=chains_k, old_logprobs=logprobs_k,
                                   returns=returns_k, old_values=values_k, advantages=advantages_k, inds_all=inds_all)
         scalars = scalars_out if scalars_out is not None else torch.empty(8, dtype=torch.float32, device=obs_k.device)
+        plan.set_actor_event(actor_event if with_actor else None)
         plan.minibatch(batch, hp, vf_coef, with_actor, scalars, eng._ws)
         return scalars
 

@@ -115,6 +115,13 @@ class UpdatePlan:
         _lib.check(self.lib.dppo_update_forward(self.handle, C.byref(batch), _lib.ptr(eps_out), _lib.ptr(vpred_out),
                                                 _lib.stream_ptr()), "dppo_update_forward")
 
+    def set_actor_event(self, event):
+        """`event`: a torch.cuda.Event that has been recorded once (so that it owns a cudaEvent_t), or None.  The backward
+        records it behind the actor backward (see dppo_update_set_actor_event)."""
+        handle = None if event is None else C.c_void_p(event.cuda_event)
+        _lib.check(self.lib.dppo_update_set_actor_event(self.handle, handle), "dppo_update_set_actor_event")
+        self._actor_event = event  # keep it alive
+
     def values(self, obs, out=None):
         """critic(obs) for (rows, cond_dim) observation rows, rows <= max_rows (bind_model first)."""
         rows = obs.shape[0]

@@ -265,6 +265,11 @@ int dppo_update_values(dppo_update* up, const float* obs, int n_rows, float* vpr
  * vf_coef an immediate factor on grad_vpred.  with_actor = 0 skips actor_ft (critic warm-up iterations).          */
 int dppo_update_backward(dppo_update* up, const float* grad_eps, const float* grad_vpred, const float* scale_pg,
                          const float* scale_v, float vf_coef, int with_actor, int with_critic, void* stream);
+/* Optional cudaEvent_t (NULL = off) that dppo_update_backward / dppo_update_minibatch record on the stream BEHIND the
+ * actor backward and in front of the critic backward: the actor's gradient segment is final there, so a multi-GPU
+ * caller can start its all-reduce on another stream while the critic backward runs (the reference's DDP-style overlap
+ * of the gradient reduction with backward).                                                   */
+int dppo_update_set_actor_event(dppo_update* up, void* event);
 /* forward + fused PPO loss (dppo_ppo_loss_fwd_bwd / dppo_ppo_loss_rows) + backward of pg_loss + vf_coef * v_loss.
  * scalars[8] as in dppo_ppo_loss_fwd_bwd; workspace >= 128 bytes.                                                 */
 int dppo_update_minibatch(dppo_update* up, const dppo_update_batch* batch, const dppo_loss_hp* hp, float vf_coef,

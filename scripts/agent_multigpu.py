@@ -31,7 +31,8 @@ dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:
     last = res[-1]
     print(f"{name}: world {world}, envs/rank {ag.n_envs}, itrs {len(res)}, pg_loss {last['pg_loss']:.4e} v_loss {last['v_loss']:.4e} "
-          f"kl {last['approx_kl']:.3e} minibatches {last['minibatches']}  params+stats identical on all ranks: {bool(ok.item())}")
+          f"kl {last['approx_kl']:.3e} minibatches {last['minibatches']}  params+stats identical on all ranks: {bool(ok.item())}"
+          f"  param checksum {float(flat.double().sum()):.12e} / {float(flat.double().pow(2).sum()):.12e}")
     assert ok.item() == 1
 from dppo_b200 import distributed as D
 
