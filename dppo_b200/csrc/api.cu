@@ -125,7 +125,7 @@ static int build_geometry(dppo_ctx* c) {
 using namespace dppo;
 
 extern "C" const char* dppo_last_error(void) { return g_err; }
-extern "C" int dppo_version(void) { return 101; }
+extern "C" int dppo_version(void) { return 102; }  // 102: dppo_update_values, dppo_update_set_actor_event
 
 // schedule + geometry + device allocations shared by the two denoiser kinds
 static int ctx_create_common(dppo_ctx** out, const dppo_mlp_desc* mlp, const dppo_unet_desc* unet, const dppo_sched_desc* s,
