@@ -126,3 +126,28 @@ def _grad_case(rank, world):
 def test_flat_gradient_allreduce_equals_full_batch():
     for aliased, err, lerr in _run(2, _grad_case):
         assert aliased and err < 1e-6 and lerr < 1e-6
+
+
+def _split_case(rank, world):
+    """The two collectives of FlatGradBuffer.allreduce_split (group 0, then the rest + scalars) cover the buffer exactly once."""
+    import torch.distributed as dist
+
+    torch.manual_seed(1)
+    a, c = torch.nn.Linear(7, 3), torch.nn.Linear(3, 1)  # 24 / 4 parameters: both groups need their 16-byte padding
+    buf = D.FlatGradBuffer([list(a.parameters()), list(c.parameters())], n_scalars=8)
+    g = torch.Generator().manual_seed(10 + rank)
+    buf.flat.copy_(torch.randn(buf.flat.numel(), generator=g))
+    whole = buf.flat.clone()
+    dist.all_reduce(whole)
+    setup = buf.overlap_setup()  # CPU / gloo: no side stream, the callers keep the single all-reduce
+    dist.all_reduce(buf.segment(0))
+    dist.all_reduce(buf.flat[buf.group_sizes[0]:])
+    views_ok = (a.weight.grad.data_ptr() == buf.segment(0).data_ptr()
+                and c.weight.grad.data_ptr() == buf.segment(1).data_ptr()
+                and buf.scalars.data_ptr() == buf.flat[sum(buf.group_sizes):].data_ptr())
+    return setup is None, views_ok, bool(torch.equal(buf.flat, whole))
+
+
+def test_split_allreduce_pieces_equal_the_single_allreduce():
+    for no_setup, views_ok, same in _run(2, _split_case):
+        assert no_setup and views_ok and same
