@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
 
   int cur_net = -1, buf = 0;
   float hreg = 0.f;  // residual stream h[oe][F] of the owning thread
+  float tb_next = 0.f, z_first = 0.f;
   for (int step = 0; step < a.S; ++step) {
     const StepRow row = s_rows[step];
     const int net = (row.ft && !a.use_base) ? 1 : 0;
@@ -189,7 +190,13 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
       cur_net = net;
       __syncthreads();
     }
-    const float tb = owner ? a.TB[net][size_t(row.t) * H + F] : 0.f;  // L2 latency hidden behind layer 0
+    // layer-0 bias row of this step: fetched one step ahead (the L2 latency of the load sat in front of layer 0's hand-off)
+    const float tb = step == 0 ? (owner ? a.TB[net][size_t(row.t) * H + F] : 0.f) : tb_next;
+    if (step + 1 < a.S) {
+      const StepRow nrow = s_rows[step + 1];
+      const int nnet = (nrow.ft && !a.use_base) ? 1 : 0;
+      tb_next = owner ? a.TB[nnet][size_t(nrow.t) * H + F] : 0.f;
+    }
 
     // every owning thread publishes one value into the next input buffer of all 16 CTAs (rows of FS consecutive floats).
     // (Measured and dropped: gathering four neighbouring features by shuffles into one 16-byte async store per quad and
@@ -262,6 +269,16 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
         }
         publish(pv);
       }
+      if (l == 2 * a.nb - 1 && warp < a.OR * ne) {
+        // the draw of this warp's first (row, env) pair of the output layer depends on nothing the network computes:
+        // Philox + Box-Muller while the last hidden layer's values are still in flight
+        const int r = warp / ne, e = warp % ne, j = int(rank) + kCS * r;
+        if (j < a.D) {
+          const int env = env0 + e;
+          z_first = a.noise ? a.noise[(size_t(step + 1) * a.E + env) * a.D + j]
+                            : philox_normal_s(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + j, uint32_t(step + 1));
+        }
+      }
       wait_full(buf, xbytes);
     }
 
@@ -284,8 +301,9 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
         const float* xr = xin + e * HP;
         const int env = env0 + e;
         // the draw does not depend on the network output: issue it (global load or Philox) ahead of the dot product
-        float z = a.noise ? a.noise[(size_t(step + 1) * a.E + env) * a.D + j]
-                          : philox_normal_s(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + j, uint32_t(step + 1));
+        float z = pq == warp ? z_first
+                             : (a.noise ? a.noise[(size_t(step + 1) * a.E + env) * a.D + j]
+                                        : philox_normal_s(a.seed, a.offset, uint64_t(a.env_offset + env) * a.D + j, uint32_t(step + 1)));
         float acc = 0.f;
 #pragma unroll 4
         for (int k = lane * 4; k < H; k += 128) {
