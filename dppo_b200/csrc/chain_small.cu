@@ -24,7 +24,7 @@ namespace dppo {
 namespace {
 
 constexpr int kCS = 16;        // CTAs per cluster (non-portable size; one cluster per GPC)
-constexpr int kThreadsS = 256;
+constexpr int kThreadsS = 256;  // 512 threads (half the dot product per thread, 128 registers) measured slower: 0.165 vs 0.146 ms
 constexpr int kMaxBlocks = 4;
 
 struct SmallArgs {
