@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_mlp_kernel(const ChainArgs 
 //   ingest   weight tiles this CTA streams x 16 KiB / 34.7 B/cycle          (L2 -> shared memory, per-SM limit)
 //   mma      MMAs x max(NE/2, 32 + NE/4)                                    (tensor floor vs. shared-memory operand read)
 //   epi      activation elements per epilogue thread x ~30 cycles
-//   exch     bytes pushed to the peers / ~25 B/cycle
+//   exch     bytes pushed to the peers / ~25 B/cycle (3 peers) or ~6 B/cycle (7 peers)
 // and the launch needs ceil(tiles / co-resident clusters) waves.  DPPO_B200_TILE_ENVS / DPPO_B200_CLUSTER override.
 struct LaunchShape {
   int NE, C;
@@ -833,7 +833,10 @@ static LaunchShape pick_shape(const dppo_ctx* ctx, int E) {
       const double mma = pairs * 4.0 * (g.nsplit == 2 ? 3.0 : 1.0) * per_mma;
       const double layers = 1.0 + 2.0 * g.nb;
       const double epi = layers * (double(NE) * g.H / C / 256.0) * 30.0 + 2000.0;
-      const double exch = C > 1 ? layers * (C - 1) * (2.0 * g.MT / C * NE * 128.0 * g.nsplit) / 25.0 + layers * 1500.0 : 0.0;
+      // pushes into up to 3 peers move ~25 B/cycle, into 7 peers ~6 B/cycle (fitted to furniture at 125 / 250 envs: NE = 32,
+      // C = 8 takes 267 k cycles per step where 25 B/cycle predicted 157 k, and NE = 16, C = 4 is the faster shape)
+      const double push_bw = C > 4 ? 6.0 : 25.0;
+      const double exch = C > 1 ? layers * (C - 1) * (2.0 * g.MT / C * NE * 128.0 * g.nsplit) / push_bw + layers * 1500.0 : 0.0;
       const double t = waves * ((ingest > mma ? ingest : mma) + epi + exch);
       if (t < best_t) best_t = t, best = LaunchShape{NE, C};
     }
