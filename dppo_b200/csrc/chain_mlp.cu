@@ -872,7 +872,7 @@ static int query_clusters_t(int C, size_t smem_bytes) {
   auto kfn = chain_mlp_kernel<NE, ACT, LN>;
   if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) return 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(C) * 148), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem_bytes;
+  cfg.gridDim = dim3(unsigned(C) * kDefaultSmCount), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = unsigned(C), attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;

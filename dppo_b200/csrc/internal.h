@@ -10,6 +10,11 @@
 
 namespace dppo {
 
+// SM count of a B200: a placeholder until the device attribute has been read (contexts and plans overwrite it) and the
+// fall-back when that query fails; launch shapes are sized from the queried value
+constexpr int kDefaultSmCount = 148;
+
+
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
@@ -71,7 +76,7 @@ struct PackedNet {
 struct dppo_ctx {
   int device = 0;
   int precision = 0;
-  int sm_count = 148;
+  int sm_count = dppo::kDefaultSmCount;
   dppo_mlp_desc net{};
   dppo::MlpGeom g{};
   // schedule

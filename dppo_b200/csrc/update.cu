@@ -512,10 +512,10 @@ static int device_sm_count() {
   static int cached[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return 148;
+  if (dev < 0 || dev >= 64) return kDefaultSmCount;
   if (!cached[dev]) {
     int n = 0;
-    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : kDefaultSmCount;
   }
   return cached[dev];
 }

@@ -82,7 +82,7 @@ struct dppo_update {
   dppo_ctx* ctx = nullptr;
   int max_rows = 0;
   cudaEvent_t actor_done = nullptr;  // optional: recorded on the stream behind the actor backward (dppo_update_set_actor_event)
-  int sm_count = 148;
+  int sm_count = kDefaultSmCount;
   ResMlp actor, critic;
   // actor extras: time MLP, cond_mlp, assembled layer 0
   const float *tw1 = nullptr, *tb1 = nullptr, *tw2 = nullptr, *tb2 = nullptr, *W0 = nullptr, *b0 = nullptr;
@@ -891,7 +891,7 @@ extern "C" int dppo_debug_linear(const float* x, int R, int K, const float* W, i
                                  const float* pre, int act_grad, const float* res, float* out_f32, int act_out,
                                  float* out_act_f32, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int sm = 148;
+  int sm = kDefaultSmCount;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
@@ -923,7 +923,7 @@ extern "C" int dppo_debug_linear(const float* x, int R, int K, const float* W, i
 extern "C" int dppo_debug_gemm_bench(int R, int K, int N, int flags, int ntile_cap, int max_stages, int reps, float* ms,
                                      unsigned long long* prof, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int sm = 148, dev = 0;
+  int sm = kDefaultSmCount, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
   set_row_gemm_tuning(ntile_cap, max_stages);
@@ -973,7 +973,7 @@ extern "C" int dppo_debug_gemm_bench(int R, int K, int N, int flags, int ntile_c
 // dW[N][K] += g[R][N]^T x[R][K], db[N] += column sums of g
 extern "C" int dppo_debug_wgrad(const float* gm, const float* x, int R, int N, int K, float* dW, float* db, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int sm = 148;
+  int sm = kDefaultSmCount;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
