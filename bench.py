@@ -7,8 +7,10 @@ One "step" = one rollout decision for every environment of the workload: the S-s
 = E * act_steps / t_step, the reference's own step accounting (train_ppo_diffusion_agent.py:151).
 
   value      chain kernel with inputs resident in HBM (CUDA events around each step, L2 flushed between steps)
-  e2e        the same through the reference-shaped call model(cond=...) with pinned HOST observations copied in and
-             trajectories + chains copied back every step (what the agent does at train_ppo_diffusion_agent.py:107-122)
+  e2e        the same through the reference-shaped call model(cond=...) with HOST observations in and trajectories +
+             chains in host memory on return, every step (what the agent does at train_ppo_diffusion_agent.py:107-122;
+             dppo_sample_chain_host: the kernel moves both directions over PCIe itself, the call synchronises);
+             e2e_explicit_copies is the same with copy launches around the device call
   update     PPO-update samples/s: fused gather+log-prob+loss kernel, autograd backward, optimiser steps (secondary)
   roofline   tensor-core roofline of the chain kernel from the algorithmic FLOPs S * F_net per decision
   cpu_baseline / --impl reference   the CPU oracle port of the reference path on this box's host cores
@@ -238,12 +240,12 @@ def run_b200(args, w, E, rank, world, local_rank):
     host_traj = torch.empty((E, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
     host_chain = torch.empty((E, ft + 1, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
 
+    # the drop-in call with HOST buffers: observations in host memory in, trajectories + chains in host memory out when the
+    # call returns (dppo_sample_chain_host behind VPGDiffusion.forward: the kernel prologue reads the page-locked
+    # observations over PCIe, the kernel stores the results into page-locked memory, the call synchronises)
     def e2e_step(i):
-        obs = host_obs[i % n_bufs].to(dev, non_blocking=True)
-        out = model(cond={"state": obs}, deterministic=False, return_chain=True)
-        host_traj.copy_(out.trajectories, non_blocking=True)
-        host_chain.copy_(out.chains, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the agent consumes the actions on the host every step
+        out = model(cond={"state": host_obs[i % n_bufs]}, deterministic=False, return_chain=True)
+        return out.trajectories, out.chains
 
     for i in range(args.warmup):
         e2e_step(i)
@@ -253,6 +255,26 @@ def run_b200(args, w, E, rank, world, local_rank):
         e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    traj_h, chain_h = e2e_step(0)
+    if traj_h.is_cuda or chain_h.is_cuda or not bool(torch.isfinite(chain_h).all()) or float(chain_h.abs().max()) == 0.0:
+        raise RuntimeError("e2e: the host call did not return host-resident results")
+
+    # the same with explicit copy launches around the device call (what the reference agent's code does literally)
+    def e2e_copies_step(i):
+        obs = host_obs[i % n_bufs].to(dev, non_blocking=True)
+        out = model(cond={"state": obs}, deterministic=False, return_chain=True)
+        host_traj.copy_(out.trajectories, non_blocking=True)
+        host_chain.copy_(out.chains, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the agent consumes the actions on the host every step
+
+    for i in range(args.warmup):
+        e2e_copies_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_copies_step(i)
+    barrier()
+    e2e_cp_s = time.perf_counter() - t0
 
     # the B200 agent keeps the rollout buffers on the device: only the action chunk returns to the host
     def e2e_resident_step(i):
@@ -307,10 +329,10 @@ def run_b200(args, w, E, rank, world, local_rank):
         torch.cuda.empty_cache()
         strong = bench_strong(args, dev, rank, world)
 
-    t = torch.tensor([total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s, e2e_cp_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s = t.tolist()
+    total_ms, e2e_s, wall, e2e_res_s, e2e_zc_s, e2e_cp_s = t.tolist()
     if rank == 0:
         act = w["act_steps"]
         value = world * E * act * args.steps / (total_ms * 1e-3)
@@ -341,11 +363,16 @@ def run_b200(args, w, E, rank, world, local_rank):
                       "scaling": "weak: every rank runs the workload's envs, no data-path collective in the rollout metric; "
                                  "the collective path is measured in `strong_scaling`"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
-                    "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "note": "model(cond={'state': host tensor}) -> dppo_sample_chain_host: host observations in, trajectories + chains in host memory when the call returns (the kernel moves them over PCIe itself; stream synchronised inside the call)"},
+            "e2e_explicit_copies": {
+                "value": world * E * act * args.steps / e2e_cp_s, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
+                "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_cp_s / args.steps,
+                "note": "obs.to(device) -> model(cond) -> two copy_ launches into pinned memory -> stream synchronise (round 1's e2e)"},
             "e2e_zero_copy": {
                 "value": world * E * act * args.steps / e2e_zc_s, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
                 "d2h_bytes_per_step": E * D * 4 * (ft + 2), "ms_per_step": 1e3 * e2e_zc_s / args.steps,
-                "note": "same call with pinned host tensors passed in: the kernel reads the observations from and stores trajectories + chains into page-locked host memory itself (no copy launches)"},
+                "note": "device-path call with caller-owned pinned tensors passed as out_trajectories / out_chains + a torch stream synchronise: the kernel reads the observations from and stores trajectories + chains into page-locked host memory itself (no copy launches)"},
             "e2e_device_resident_buffers": {
                 "value": world * E * act * args.steps / e2e_res_s, "unit": UNIT, "h2d_bytes_per_step": E * Do * 4,
                 "d2h_bytes_per_step": E * D * 4, "ms_per_step": 1e3 * e2e_res_s / args.steps,
@@ -395,7 +422,10 @@ def hopper_ratio(args, dev, cores):
     host_traj = torch.empty((E, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
     host_chain = torch.empty((E, ft + 1, w["horizon_steps"], w["action_dim"]), dtype=torch.float32).pin_memory()
 
-    def step(i):
+    def step(i):  # host observations in, host results out (dppo_sample_chain_host)
+        model(cond={"state": host_obs[i % 4]}, deterministic=False, return_chain=True)
+
+    def step_copies(i):
         obs = host_obs[i % 4].to(dev, non_blocking=True)
         out = model(cond={"state": obs}, deterministic=False, return_chain=True)
         host_traj.copy_(out.trajectories, non_blocking=True)
@@ -407,19 +437,22 @@ def hopper_ratio(args, dev, cores):
         torch.cuda.current_stream().synchronize()
 
     res = {}
-    for name, fn in (("e2e", step), ("e2e_zero_copy", step_zero_copy)):
+    for name, fn in (("e2e", step), ("e2e_explicit_copies", step_copies), ("e2e_zero_copy", step_zero_copy)):
         for i in range(20):
             fn(i)
         t0 = time.perf_counter()
-        n = 200
+        n = 400
         for i in range(n):
             fn(i)
         res[name] = E * w["act_steps"] * n / (time.perf_counter() - t0)
     times, kind = cpu_chain_seconds(w, E, 20, 3, cores)
     cpu = E * w["act_steps"] / (sum(times) / len(times))
-    return {"workload": workload_name(w, E), "e2e_env_steps_s": res["e2e"], "e2e_zero_copy_env_steps_s": res["e2e_zero_copy"],
+    return {"workload": workload_name(w, E), "e2e_env_steps_s": res["e2e"], "e2e_explicit_copies_env_steps_s": res["e2e_explicit_copies"],
+            "e2e_zero_copy_env_steps_s": res["e2e_zero_copy"],
             "cpu_env_steps_s": cpu, "cpu_kind": kind, "cores": cores, "ratio_e2e": res["e2e"] / cpu,
-            "ratio_e2e_zero_copy": res["e2e_zero_copy"] / cpu, "target": 50.0}
+            "ratio_e2e_explicit_copies": res["e2e_explicit_copies"] / cpu,
+            "ratio_e2e_zero_copy": res["e2e_zero_copy"] / cpu, "target": 50.0,
+            "note": "e2e = model(cond={'state': host tensor}): host observations in, host trajectories + chains out, one call"}
 
 
 def bench_strong(args, dev, rank, world):

@@ -14,11 +14,12 @@ ACT_RELU, ACT_MISH = 0, 1
 NET_ACTOR, NET_ACTOR_FT = 0, 1
 PRECISION_SPLIT3, PRECISION_BF16 = 0, 1
 PRECISIONS = {"split3": PRECISION_SPLIT3, "bf16": PRECISION_BF16}
+HOST_STATE_PINNED, HOST_OUT_PINNED = 1, 2  # dppo_sample_chain_host flags
 
 # every symbol include/dppo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "dppo_last_error", "dppo_version", "dppo_ctx_create", "dppo_ctx_destroy", "dppo_pack_mlp", "dppo_ctx_create_unet",
-    "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain", "dppo_sample_nonfinite",
+    "dppo_pack_unet", "dppo_unet_param_count", "dppo_sample_chain", "dppo_sample_chain_host", "dppo_sample_nonfinite",
     "dppo_chain_logprobs", "dppo_logprob_rows", "dppo_ppo_loss_fwd_bwd", "dppo_ppo_loss_rows", "dppo_gae_f64", "dppo_split3_pack", "dppo_reward_scale_f64", "dppo_adamw_flat",
     "dppo_update_create", "dppo_update_destroy", "dppo_update_bind", "dppo_update_forward", "dppo_update_backward",
     "dppo_update_minibatch", "dppo_update_values", "dppo_update_set_actor_event", "dppo_update_buffers", "dppo_memset_zero", "dppo_adamw_flat_dev", "dppo_kl_check",
@@ -127,6 +128,7 @@ def load(build_if_missing=True):
                  "dppo_unet_plan_dense", "dppo_unet_plan_side"):
         getattr(lib, name).restype = i32
     lib.dppo_sample_chain.argtypes = [vp, vp, i32, vp, u64, u64, i64, i32, i32, f32, vp, vp, vp]
+    lib.dppo_sample_chain_host.argtypes = [vp, vp, i32, u64, u64, i64, i32, i32, f32, vp, vp, i32, vp]
     lib.dppo_sample_nonfinite.argtypes = [vp, C.POINTER(C.c_int), i32, vp]
     lib.dppo_chain_logprobs.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.dppo_logprob_rows.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
@@ -209,6 +211,16 @@ def ptr_dev_or_pinned(t):
     if not t.is_contiguous():
         raise RuntimeError("dppo_b200 kernels need contiguous tensors")
     return C.c_void_p(t.data_ptr())
+
+
+def raw_stream():
+    """cudaStream_t of torch's current stream on the current device as a plain int (argtypes convert it)."""
+    import torch
+
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return raw(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def stream_ptr():

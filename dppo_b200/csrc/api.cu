@@ -125,7 +125,7 @@ static int build_geometry(dppo_ctx* c) {
 using namespace dppo;
 
 extern "C" const char* dppo_last_error(void) { return g_err; }
-extern "C" int dppo_version(void) { return 102; }  // 102: dppo_update_values, dppo_update_set_actor_event
+extern "C" int dppo_version(void) { return 103; }  // 103: dppo_sample_chain_host
 
 // schedule + geometry + device allocations shared by the two denoiser kinds
 static int ctx_create_common(dppo_ctx** out, const dppo_mlp_desc* mlp, const dppo_unet_desc* unet, const dppo_sched_desc* s,
@@ -228,6 +228,7 @@ extern "C" int dppo_ctx_destroy(dppo_ctx* c) {
   if (!c) return DPPO_OK;
   cudaFree(c->d_rows);
   cudaFree(c->d_nonfinite);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (int w = 0; w < 2; ++w) {
     cudaFree(c->nets[w].tiles);
     cudaFree(c->nets[w].side);
@@ -270,6 +271,51 @@ extern "C" int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, 
   return (ctx->kind == 1 ? sample_chain_unet_impl : sample_chain_impl)(
       ctx, state, n_envs, noise, seed, offset, env_offset, deterministic, use_base_policy, min_std, traj, chain, nullptr,
       nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer form (include/dppo_b200.h): page-locked caller buffers are used in place, pageable ones are staged through
+// the context's own page-locked area; returns with the results in the caller's buffers.
+extern "C" int dppo_sample_chain_host(dppo_ctx* ctx, const float* state, int n_envs, uint64_t seed, uint64_t offset,
+                                      int64_t env_offset, int deterministic, int use_base_policy, float min_std,
+                                      float* traj, float* chain, int flags, void* stream) {
+  if (!ctx || !state || !traj) return set_error("dppo_sample_chain_host: null argument"), DPPO_ERR_INVALID;
+  if (n_envs < 0) return set_error("dppo_sample_chain_host: n_envs=%d", n_envs), DPPO_ERR_INVALID;
+  if (n_envs == 0) return DPPO_OK;
+  const size_t Dc = size_t(ctx->kind == 1 ? ctx->unet->d.cond_dim : ctx->g.Dc_in), D = size_t(ctx->sample_dim);
+  const size_t sb = size_t(n_envs) * Dc * sizeof(float), tb = size_t(n_envs) * D * sizeof(float);
+  const size_t cb = chain ? tb * size_t(ctx->ft + 1) : 0;
+  auto up = [](size_t n) { return (n + 255) & ~size_t(255); };
+  const bool stage_in = !(flags & DPPO_HOST_STATE_PINNED), stage_out = !(flags & DPPO_HOST_OUT_PINNED);
+  const size_t need = (stage_in ? up(sb) : 0) + (stage_out ? up(tb) + up(cb) : 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (need > ctx->h_stage_bytes) {
+    // every earlier host call has synchronised before returning: nothing reads the old area any more
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr, ctx->h_stage_bytes = 0;
+    const size_t cap = need < (size_t(1) << 16) ? (size_t(1) << 16) : need + need / 2;
+    DPPO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stage), cap, cudaHostAllocPortable | cudaHostAllocMapped));
+    ctx->h_stage_bytes = cap;
+  }
+  uint8_t* p = ctx->h_stage;
+  const float* k_state = state;
+  float *k_traj = traj, *k_chain = chain;
+  if (stage_in) {
+    memcpy(p, state, sb);
+    k_state = reinterpret_cast<const float*>(p), p += up(sb);
+  }
+  if (stage_out) {
+    k_traj = reinterpret_cast<float*>(p), p += up(tb);
+    if (chain) k_chain = reinterpret_cast<float*>(p);
+  }
+  const int rc = dppo_sample_chain(ctx, k_state, n_envs, nullptr, seed, offset, env_offset, deterministic, use_base_policy,
+                                   min_std, k_traj, k_chain, stream);
+  if (rc != DPPO_OK) return rc;
+  DPPO_CUDA(cudaStreamSynchronize(st));
+  if (stage_out) {
+    memcpy(traj, k_traj, tb);
+    if (chain) memcpy(chain, k_chain, cb);
+  }
+  return DPPO_OK;
 }
 
 extern "C" int dppo_chain_logprobs(dppo_ctx* ctx, const float* state, const float* chains, int n_rows,

@@ -97,6 +97,8 @@ struct dppo_ctx {
   int chain_clusters[3][4] = {};  // co-resident clusters of the MLP chain kernel per (tile envs 16/32/64, cluster size 1/2/4/8)
   bool chain_clusters_known = false;
   int* d_nonfinite = nullptr;  // device flag OR-ed by the chain kernels when a sampled action element is not finite
+  uint8_t* h_stage = nullptr;  // page-locked staging area of dppo_sample_chain_host (pageable caller buffers)
+  size_t h_stage_bytes = 0;
   int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

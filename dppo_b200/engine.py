@@ -8,10 +8,16 @@ VPGDiffusion.step() swaps actor <- actor_ft (reference dppo/model/diffusion/diff
 
 import ctypes as C
 import math
+import operator
 
 import torch
 
 from dppo_b200 import _lib
+
+
+_VERSION = operator.attrgetter("_version")
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda dev: torch.cuda.current_stream(dev).cuda_stream)
+_CUR_DEVICE = torch.cuda.current_device
 
 
 def _mlp_param_list(net):
@@ -175,6 +181,10 @@ class ChainEngine:
         _lib.check(create(C.byref(self.ctx), C.byref(desc), C.byref(sd), _lib.PRECISIONS[precision], idx), "dppo_ctx_create")
         self._packed = {0: None, 1: None}
         self._plists = {}
+        self._host_io = {}  # batch size -> [next slot, ring of (trajectories, chains, traj ptr, chain ptr)] (sample_host)
+        self._sample_host_fn = self.lib.dppo_sample_chain_host
+        self.Ta, self.Da = int(model.horizon_steps), int(model.action_dim)
+        self.cond_numel = int(desc.cond_dim)
         self._ws = torch.zeros(32, dtype=torch.float64, device=dev)
 
     def __del__(self):
@@ -201,7 +211,7 @@ class ChainEngine:
             self._plists[which] = cached
             self._packed[which] = None
         ps = cached[1]
-        sig = (ps[0].data_ptr(), ps[-1].data_ptr()) + tuple([p._version for p in ps])
+        sig = (ps[0].data_ptr(), ps[-1].data_ptr(), *map(_VERSION, ps))
         if self._packed[which] == sig:
             return False
         for p in ps:
@@ -240,6 +250,49 @@ class ChainEngine:
                                        _lib.ptr_dev_or_pinned(traj), _lib.ptr_dev_or_pinned(chain), _lib.stream_ptr()),
             "dppo_sample_chain")
         return traj, chain
+
+    HOST_RING = 4            # result buffers per batch size of sample_host
+    PIN_CHECK_BYTES = 65536  # below this a staging memcpy inside the library is cheaper than asking whether `state` is pinned
+
+    def sample_host(self, state, seed=0, offset=0, env_offset=0, deterministic=False, use_base_policy=False,
+                    min_sampling_std=0.1, return_chain=True):
+        """Host observations in, host results out, one call (dppo_sample_chain_host): `state` is a CPU tensor (E, ...) -
+        pageable (staged by the library) or pinned (read in place); the kernel stores trajectories (E, Ta, Da) and chains
+        (E, ft+1, Ta, Da) straight into page-locked memory and the call returns when they are there.  The returned tensors
+        are views into a ring of HOST_RING page-locked buffers per batch size: they stay valid for the next
+        HOST_RING - 1 calls (the rollout loop consumes them within the step, reference train_ppo_diffusion_agent.py:112-122)."""
+        E = state.shape[0]
+        io = self._host_io.get(E)
+        if io is None:
+            io = self._host_io[E] = self._host_ring(E)
+        if state.dtype is not torch.float32 or not state.is_contiguous():
+            state = state.contiguous().float()
+        n = state.numel()
+        if n != E * self.cond_numel:
+            raise RuntimeError(f"state: expected {E} x {self.cond_numel} elements, got {tuple(state.shape)}")
+        slot = io[0]
+        io[0] = slot + 1 if slot + 1 < self.HOST_RING else 0
+        traj, chain, traj_p, chain_p = io[1][slot]
+        if not return_chain:
+            chain = chain_p = None
+        if E == 0:
+            return traj, chain
+        flags = _lib.HOST_OUT_PINNED
+        if n * 4 > self.PIN_CHECK_BYTES and state.is_pinned():
+            flags |= _lib.HOST_STATE_PINNED
+        rc = self._sample_host_fn(self.ctx, state.data_ptr(), E, seed, offset, env_offset, deterministic, use_base_policy,
+                                  min_sampling_std, traj_p, chain_p, flags, _RAW_STREAM(_CUR_DEVICE()))
+        if rc:
+            _lib.check(rc, "dppo_sample_chain_host")
+        return traj, chain
+
+    def _host_ring(self, E):
+        ring = []
+        for _ in range(self.HOST_RING):
+            t = torch.empty((E, self.Ta, self.Da), dtype=torch.float32).pin_memory()
+            c = torch.empty((E, self.ft + 1, self.Ta, self.Da), dtype=torch.float32).pin_memory()
+            ring.append((t, c, t.data_ptr(), c.data_ptr()))
+        return [0, ring]
 
     def nonfinite(self, reset=True):
         """True when a sampling launch since the last reset produced a NaN / Inf action element (synchronises the stream)."""

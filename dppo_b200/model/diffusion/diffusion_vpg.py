@@ -93,12 +93,14 @@ class VPGDiffusion(DiffusionModel):
     def engine(self, sync=True):
         """The kernel context (created on first use; rebuilt when the fine-tuning window is annealed).  `sync` refreshes
         the packed weight copies the chain kernels read (not needed by the loss kernels)."""
-        if self._engine is None or self._engine.ft != int(self.ft_denoising_steps):
-            self._engine = ChainEngine(self, precision=self.engine_precision)
+        eng = self._engine
+        if eng is None or eng.ft != self.ft_denoising_steps:
+            eng = self._engine = ChainEngine(self, precision=self.engine_precision)
         if sync:
-            self._engine.sync_weights(0, self.actor)
-            self._engine.sync_weights(1, self.actor_ft)
-        return self._engine
+            mods = self._modules  # plain dict lookups: nn.Module.__getattr__ costs ~1 us per sub-module
+            eng.sync_weights(0, mods["actor"])
+            eng.sync_weights(1, mods["actor_ft"])
+        return eng
 
     # ------------------------------------------------------------------ annealing (reference :102-136)
     def step(self):
@@ -123,11 +125,13 @@ class VPGDiffusion(DiffusionModel):
         return self.min_sampling_denoising_std()
 
     # ------------------------------------------------------------------ sampling (reference :227-315)
-    @torch.no_grad()
     def forward(self, cond, deterministic=False, return_chain=True, use_base_policy=False, noise=None, env_offset=0,
                 out_trajectories=None, out_chains=None):
         """
         cond["state"]: (B, To, Do).  Returns Sample(trajectories (B, Ta, Da), chains (B, ft+1, Ta, Da)).
+        With cond["state"] on the HOST and no explicit output tensors, the results come back on the host too: views into
+        a ring of page-locked buffers the kernel stored into directly (valid for the next 3 calls), complete on return -
+        the reference's obs.to(device) -> model(cond) -> .cpu().numpy() as one call without copy launches.
         `out_trajectories` / `out_chains`: optional preallocated float32 tensors of those shapes, on the device or in
         PINNED host memory - the kernel then stores straight into them (over PCIe for pinned memory, overlapped with the
         chain instead of a copy after it) and they are what Sample holds; cond["state"] may be pinned host memory too.
@@ -135,8 +139,26 @@ class VPGDiffusion(DiffusionModel):
         without it the kernel draws Philox normals seeded from torch's generator.  `env_offset` = global index of
         row 0 (env-sharded ranks then draw what one process would draw for the same envs).
         """
-        eng = self.engine()
         state = cond["state"]
+        if state.is_cuda or noise is not None or out_trajectories is not None or out_chains is not None:
+            return self._forward_device(state, deterministic, return_chain, use_base_policy, noise, env_offset,
+                                        out_trajectories, out_chains)
+        # host observations in -> host results out: one library call per decision (ChainEngine.sample_host).  This is the
+        # latency path of small env counts, so it touches no torch op (nothing autograd could record) and keeps the
+        # per-call Python work to the weight-cache check and one ctypes call.
+        eng = self.engine()
+        offset = self._rng_offset + 1
+        self.__dict__["_rng_offset"] = offset  # not through nn.Module.__setattr__ (2 us of isinstance checks)
+        min_std = self.min_sampling_denoising_std
+        if type(min_std) is not float:
+            min_std = float(min_std())
+        return Sample(*eng.sample_host(state, torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, offset, env_offset, deterministic,
+                                       use_base_policy, min_std, return_chain))
+
+    @torch.no_grad()
+    def _forward_device(self, state, deterministic, return_chain, use_base_policy, noise, env_offset, out_trajectories,
+                        out_chains):
+        eng = self.engine()
         B = state.shape[0]
         seed = offset = 0
         if noise is None:

@@ -160,6 +160,18 @@ int dppo_sample_chain(dppo_ctx* ctx, const float* state, int n_envs, const float
                       uint64_t offset, int64_t env_offset, int deterministic, int use_base_policy,
                       float min_sampling_denoising_std, float* traj, float* chain, void* stream);
 
+/* Host-buffer form of dppo_sample_chain: what the reference's rollout loop does around VPGDiffusion.forward
+ * (train_ppo_diffusion_agent.py:107-122: torch.from_numpy(obs).to(device) -> model(cond) -> .cpu().numpy()) as ONE call.
+ * `state`, `traj`, `chain` are HOST pointers; the call returns when the results are in `traj` / `chain` (it synchronises
+ * `stream`).  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are read and written by the
+ * kernel IN PLACE over PCIe - no copy launch on either side of the chain; say so in `flags`.  Pageable buffers are staged
+ * through a page-locked area owned by the context (one host memcpy per buffer).  Draws come from Philox (seed, offset). */
+#define DPPO_HOST_STATE_PINNED 1 /* `state` is page-locked: the kernel prologue reads it directly */
+#define DPPO_HOST_OUT_PINNED 2   /* `traj` and `chain` are page-locked: the kernel stores into them directly */
+int dppo_sample_chain_host(dppo_ctx* ctx, const float* state, int n_envs, uint64_t seed, uint64_t offset,
+                           int64_t env_offset, int deterministic, int use_base_policy,
+                           float min_sampling_denoising_std, float* traj, float* chain, int flags, void* stream);
+
 /* NaN / Inf guard (the reference documents NaN observations from IsaacGym, README.md:184): every dppo_sample_chain
  * launch ORs a device flag when an element of `traj` is not finite.  This call copies the flag to *flag (HOST int; it
  * synchronises `stream`) and, with reset != 0, clears it.  The sampling calls themselves never synchronise.        */

@@ -244,6 +244,57 @@ def test_zero_copy_pinned_io_matches_device_io(case):
     assert torch.equal(h_traj, want.trajectories.cpu()) and torch.equal(h_chain, want.chains.cpu())
 
 
+@pytest.mark.parametrize("case", ["hopper", "walker2d", "furniture", "square_unet"])
+def test_host_call_matches_device_call(case):
+    """model(cond={"state": HOST tensor}) -> dppo_sample_chain_host: host observations in (pageable = staged by the library,
+    pinned = read in place), host trajectories + chains out on return, bit-identical to the device call with the same
+    Philox keys; the returned views stay valid for the next 3 calls; the bare C entry point with pageable outputs agrees."""
+    import ctypes as C
+
+    from dppo_b200 import _lib
+
+    w, model, gold, inp = _setup(case)
+    state = inp["state"]
+    E, ft, Ta, Da = state.shape[0], w["ft_denoising_steps"], w["horizon_steps"], w["action_dim"]
+    torch.manual_seed(9)
+
+    def device_call(offset, **kw):
+        model._rng_offset = offset
+        out = model(cond={"state": state.cuda()}, **kw)
+        return out.trajectories.cpu(), None if out.chains is None else out.chains.cpu()
+
+    want = [device_call(i) for i in range(5)]
+    model._rng_offset = 0
+    outs = []
+    for i, st in enumerate([state.clone(), state.clone().pin_memory(), state.clone().double(), state.clone(), state.clone()]):
+        out = model(cond={"state": st})  # complete on return: no synchronise here
+        assert not out.trajectories.is_cuda and not out.chains.is_cuda
+        assert out.trajectories.shape == (E, Ta, Da) and out.chains.shape == (E, ft + 1, Ta, Da)
+        assert torch.equal(out.trajectories, want[i][0]) and torch.equal(out.chains, want[i][1]), (case, i)
+        outs.append(out)
+    for i in (1, 2, 3):  # ring of 4: results of the three calls before the last one are still intact
+        assert torch.equal(outs[i].chains, want[i][1])
+    # deterministic / base-policy / no-chain flags travel through the host call
+    model._rng_offset = 7
+    got = model(cond={"state": state}, deterministic=True, return_chain=False, use_base_policy=True)
+    wt, wc = device_call(7, deterministic=True, return_chain=False, use_base_policy=True)
+    assert got.chains is None and wc is None and torch.equal(got.trajectories, wt)
+    # the C entry point itself, every buffer pageable (flags = 0: staged in and out)
+    eng = model.engine()
+    st_np = np.ascontiguousarray(state.numpy().reshape(E, -1), dtype=np.float32)
+    traj_np, chain_np = np.zeros((E, Ta * Da), np.float32), np.zeros((E, ft + 1, Ta * Da), np.float32)
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    _lib.check(eng.lib.dppo_sample_chain_host(eng.ctx, st_np.ctypes.data, E, seed, 1, 0, 0, 0,
+                                              float(model.get_min_sampling_denoising_std()), traj_np.ctypes.data,
+                                              chain_np.ctypes.data, 0, _lib.raw_stream()), "dppo_sample_chain_host")
+    assert np.array_equal(traj_np.reshape(E, Ta, Da), want[0][0].numpy())
+    assert np.array_equal(chain_np.reshape(E, ft + 1, Ta, Da), want[0][1].numpy())
+    assert eng.lib.dppo_sample_chain_host(eng.ctx, None, E, 0, 0, 0, 0, 0, 0.1, traj_np.ctypes.data, None, 0, None) != 0
+    assert eng.lib.dppo_sample_chain_host(eng.ctx, st_np.ctypes.data, 0, 0, 0, 0, 0, 0, 0.1, traj_np.ctypes.data, None, 0, None) == 0
+    empty = model(cond={"state": torch.zeros(0, 1, w["obs_dim"])})
+    assert empty.trajectories.shape == (0, Ta, Da) and empty.chains.shape == (0, ft + 1, Ta, Da)
+
+
 @pytest.mark.parametrize("workload,n_envs,tile_envs,cluster,launches", [
     ("walker2d", 4096, 64, 2, 3000), ("walker2d", 2048, 32, 4, 3000), ("furniture", 500, 32, 4, 2000),
     ("transport_k20", 50, 16, 8, 2000), ("square_unet", 512, 16, 2, 1500), ("hopper", 40, 0, -1, 5000),
