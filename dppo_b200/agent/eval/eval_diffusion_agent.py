@@ -64,14 +64,12 @@ class EvalDiffusionAgent:
         rewards = np.zeros((self.n_steps, self.n_envs))
         obs = self.reset_env_all()
         firsts[0] = 1
-        pinned_obs = torch.empty((self.n_envs, self.n_cond_step, self.obs_dim), dtype=torch.float32).pin_memory()
-        pinned_act = torch.empty((self.n_envs, self.horizon_steps, self.action_dim), dtype=torch.float32).pin_memory()
         for step in range(self.n_steps):
-            pinned_obs.copy_(torch.from_numpy(np.ascontiguousarray(obs["state"], dtype=np.float32)))
-            samples = self.model(cond={"state": pinned_obs.to(self.device, non_blocking=True)}, deterministic=True)
-            pinned_act.copy_(samples.trajectories, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            obs, reward, terminated, truncated, _ = self.venv.step(pinned_act.numpy()[:, : self.act_steps])
+            # host observations in, host actions out: one library call per decision (dppo_sample_chain_host), the action
+            # chunk is in page-locked host memory when it returns
+            state = torch.from_numpy(np.ascontiguousarray(obs["state"], dtype=np.float32))
+            samples = self.model(cond={"state": state}, deterministic=True)
+            obs, reward, terminated, truncated, _ = self.venv.step(samples.trajectories.numpy()[:, : self.act_steps])
             rewards[step] = reward
             firsts[step + 1] = terminated | truncated
         # episodes that start and finish inside the run

@@ -69,6 +69,10 @@ class DiffusionEval(DiffusionModel):
             seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
             self._rng_offset += 1
             offset = self._rng_offset
+            if not state.is_cuda:
+                # host observations in -> host actions out, one library call (ChainEngine.sample_host)
+                traj, _ = eng.sample_host(state, seed, offset, 0, True, not hasattr(self, "actor_ft"), 0.0, False)
+                return Sample(traj, None)
         traj, _ = eng.sample(state.to(self.device), noise=noise, seed=seed, offset=offset, deterministic=True,
                              use_base_policy=not hasattr(self, "actor_ft"), min_sampling_std=0.0, return_chain=False)
         return Sample(traj.view(B, self.horizon_steps, self.action_dim), None)

@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from dppo_b200 import _lib
-from dppo_b200.engine import _mlp_param_list
+from dppo_b200.engine import _mlp_param_list, mlp_desc_of
 
 
 def critic_param_list(critic):
@@ -47,6 +47,17 @@ def unsupported_reason(model):
         return "learned eta"
     if model.ft_denoising_steps < 1:
         return "no fine-tuned denoising step"
+    # the geometry limits of dppo_update_create (csrc/update_plan.cu: 64-wide K chunks and output tiles, LayerNorm
+    # epilogues written for Mish) - such models keep the autograd route instead of failing at the first minibatch
+    desc = mlp_desc_of(model.actor_ft)
+    widths = {"actor hidden": desc.hidden_dim, "critic hidden": q.hidden_dim}
+    if desc.cond_hidden:
+        widths["cond_mlp hidden"], widths["cond_mlp output"] = desc.cond_hidden, desc.cond_out
+    for what, n in widths.items():
+        if n % 64:
+            return f"{what} width {n} is not a multiple of 64"
+    if (desc.use_layernorm and desc.activation != _lib.ACT_MISH) or (q.use_layernorm and q.activation_type != "Mish"):
+        return "LayerNorm with an activation other than Mish"
     return None
 
 

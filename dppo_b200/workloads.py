@@ -77,6 +77,37 @@ WORKLOADS = {
     ),
 }
 
+# The remaining DiffusionMLP geometries among the reference's state-based fine-tuning YAMLs (parity cases, not bench lines)
+WORKLOADS["kitchen"] = dict(  # dppo/cfg/gym/finetune/kitchen-{complete,mixed,partial}-v0/ft_ppo_diffusion_mlp.yaml
+    yaml="gym/finetune/kitchen-complete-v0/ft_ppo_diffusion_mlp.yaml",
+    n_envs=40, obs_dim=60, action_dim=9, horizon_steps=4, act_steps=4, cond_steps=1,
+    denoising_steps=20, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+    actor=dict(kind="mlp", time_dim=16, mlp_dims=[256, 256, 256], cond_mlp_dims=[128, 32], residual_style=True),
+    critic=_CRITIC_256, ppo=_GYM_PPO,
+    train=dict(n_steps=70, gamma=0.99, gae_lambda=0.95, batch_size=5600, update_epochs=10, vf_coef=0.5,
+               target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=0, max_episode_steps=280),
+)
+WORKLOADS["avoid"] = dict(  # dppo/cfg/d3il/finetune/avoid_m{1,2,3}/ft_ppo_diffusion_mlp.yaml
+    yaml="d3il/finetune/avoid_m1/ft_ppo_diffusion_mlp.yaml",
+    n_envs=50, obs_dim=4, action_dim=2, horizon_steps=4, act_steps=4, cond_steps=1,
+    denoising_steps=20, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+    actor=dict(kind="mlp", time_dim=16, mlp_dims=[512, 512, 512], activation_type="ReLU", residual_style=True),
+    critic=_CRITIC_256,
+    ppo=dict(gamma_denoising=0.95, clip_ploss_coef=0.1, clip_ploss_coef_base=0.1, clip_ploss_coef_rate=1,
+             randn_clip_value=3, min_sampling_denoising_std=0.1, min_logprob_denoising_std=0.1),
+    train=dict(n_steps=25, gamma=0.99, gae_lambda=0.95, batch_size=6250, update_epochs=10, vf_coef=0.5,
+               target_kl=1, actor_lr=1e-5, critic_lr=1e-3, n_critic_warmup_itr=1, max_episode_steps=100),
+)
+WORKLOADS["square_mlp"] = dict(  # dppo/cfg/robomimic/finetune/square/ft_ppo_diffusion_mlp.yaml
+    yaml="robomimic/finetune/square/ft_ppo_diffusion_mlp.yaml",
+    n_envs=50, obs_dim=23, action_dim=7, horizon_steps=4, act_steps=4, cond_steps=1,
+    denoising_steps=20, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+    actor=dict(kind="mlp", time_dim=32, mlp_dims=[1024, 1024, 1024], cond_mlp_dims=[512, 64], residual_style=True),
+    critic=_CRITIC_256, ppo=_ROBOMIMIC_PPO,
+    train=dict(n_steps=400, gamma=0.999, gae_lambda=0.95, batch_size=10000, update_epochs=10, vf_coef=0.5,
+               target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=2, max_episode_steps=400),
+)
+
 # variants: same networks, different schedules
 WORKLOADS["transport_k20"] = dict(deepcopy(WORKLOADS["transport"]), denoising_steps=20)
 WORKLOADS["furniture_ddpm100"] = dict(deepcopy(WORKLOADS["furniture"]), use_ddim=False, ddim_steps=None, eta=None)

@@ -2,6 +2,7 @@
 Golden-vector generator (run in the build container only; needs /root/reference, which does not travel to the GPU box).
 
     python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py kitchen    # only the named cases (the others keep their recorded bytes)
 
 For each workload it instantiates the UNMODIFIED reference classes (dppo.model.diffusion.diffusion_ppo.PPODiffusion
 with DiffusionMLP / Unet1D / CriticObs / EtaFixed) on CPU in fp32, with the seeded weight recipe of
@@ -70,7 +71,10 @@ def run_forward(model, state, noise, deterministic):
 
 def main():
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])
     for case, spec in GOLDEN_CASES.items():
+        if only and case not in only:
+            continue
         w = get_workload(spec["workload"])
         E = spec["n_envs"]
         model = build_model(

@@ -21,6 +21,11 @@ GOLDEN_CASES = {
     "furniture": dict(workload="furniture", n_envs=40, mb_rows=96),
     "furniture_ddpm100": dict(workload="furniture_ddpm100", n_envs=16, mb_rows=48),
     "square_unet": dict(workload="square_unet", n_envs=40, mb_rows=128),
+    # the other DiffusionMLP geometries of the reference's fine-tuning YAMLs (H = 256 with a 128 / 32 cond_mlp; a 2-D action
+    # with a 4-D observation; H = 1024 with cond_mlp and no LayerNorm)
+    "kitchen": dict(workload="kitchen", n_envs=40, mb_rows=96),
+    "avoid": dict(workload="avoid", n_envs=50, mb_rows=96),
+    "square_mlp": dict(workload="square_mlp", n_envs=24, mb_rows=64),
 }
 
 # optional branches of the hot path (tests/golden/make_golden_variants.py): base workload + constructor overrides

@@ -12,7 +12,7 @@ from dppo_b200.workloads import chain_evals, get_workload
 from tests.helpers import GOLDEN_CASES, build_model, load_golden, make_inputs, oracle_cfgs, oracle_params, our_classes
 
 pytestmark = pytest.mark.gpu
-MLP_CASES = ["hopper", "walker2d", "transport_k20", "transport", "furniture", "furniture_ddpm100"]
+MLP_CASES = ["hopper", "walker2d", "transport_k20", "transport", "furniture", "furniture_ddpm100", "kitchen", "avoid", "square_mlp"]
 ALL_CASES = MLP_CASES + ["square_unet"]
 
 

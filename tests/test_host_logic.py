@@ -148,3 +148,19 @@ def test_committed_bench_lines_carry_the_contract_keys():
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
         assert d["e2e"]["value"] < d["value"]  # the end-to-end number is never the device-timed one
+
+
+def test_update_route_per_reference_yaml_geometry():
+    """Which route the PPO update takes for every DiffusionMLP / Unet1D geometry among the reference's state-based
+    fine-tuning YAMLs: the tcgen05 program where dppo_update_create's limits hold, else the autograd route WITH a reason
+    (kitchen's 32-wide cond_mlp output once reached dppo_update_create and failed the first minibatch)."""
+    from dppo_b200.update_engine import unsupported_reason
+    from dppo_b200.workloads import get_workload
+    from tests.helpers import build_model, our_classes
+
+    want = {"hopper": None, "walker2d": None, "avoid": None, "transport": None, "furniture": None, "square_mlp": None,
+            "kitchen": "cond_mlp output width 32 is not a multiple of 64", "square_unet": "actor is not a DiffusionMLP"}
+    for name, reason in want.items():
+        model = build_model(get_workload(name), "cpu", our_classes(), perturb=False)
+        assert unsupported_reason(model) == reason, name
+        assert model.fused_update_reason() == reason, name
