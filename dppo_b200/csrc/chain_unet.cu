@@ -43,6 +43,7 @@ struct UArgs {
   const uint8_t* tiles[2];
   const float* side[2];
   int chunk_x, chunk_state, chunk_state_act, KS, total_chunks, film_dim;
+  int gn_blocks;  // 32-lane feature blocks of the widest layer when some GroupNorm group is not a power of two, else 0
   // schedule
   const StepRow* rows;
   int S, ft, first_step, eval_mode, use_ddim;
@@ -87,17 +88,21 @@ __device__ __forceinline__ float act_f(float x) {
 
 struct USmem {
   uint8_t *op_hi, *op_lo, *ring;
-  float *film, *eps;
+  float *film, *eps, *gn_part;
   uint64_t *full, *empty, *layer_done, *x_full, *xt_full, *film_full, *film_free;
   uint32_t* tmem_slot;
   uint32_t film_stride;  // floats between the two FiLM buffers
 };
 
-__host__ __device__ inline size_t usmem_fixed_bytes(int NE, int total_chunks, int nsplit, int film_dim, int D, int C) {
+// segmented GroupNorm scratch: per 32-lane feature block {head, tail} x {sum, sum of squares} x NE environments
+__host__ __device__ inline size_t ugn_part_bytes(int NE, int gn_blocks) { return size_t(gn_blocks) * 4 * NE * sizeof(float); }
+
+__host__ __device__ inline size_t usmem_fixed_bytes(int NE, int total_chunks, int nsplit, int film_dim, int D, int C,
+                                                    int gn_blocks) {
   const size_t op = size_t(total_chunks) * NE * 128 * nsplit;
   const size_t film = C * ((size_t(NE) * film_dim * 4 + 127) & ~size_t(127));
   const size_t eps = (size_t(NE) * D * 4 + 127) & ~size_t(127);
-  return op + film + eps + 16 * kMaxStages + 160 + 1024 /* alignment slack */;
+  return op + film + eps + ugn_part_bytes(NE, gn_blocks) + 16 * kMaxStages + 160 + 1024 /* alignment slack */;
 }
 
 template <int NE>
@@ -112,6 +117,7 @@ __device__ __forceinline__ USmem ucarve(uint8_t* base, const UArgs& a) {
   s.film = reinterpret_cast<float*>(p), p += film_bytes * a.C;
   s.film_stride = uint32_t(film_bytes / 4);
   s.eps = reinterpret_cast<float*>(p), p += (size_t(NE) * a.D * 4 + 127) & ~size_t(127);
+  s.gn_part = reinterpret_cast<float*>(p), p += ugn_part_bytes(NE, a.gn_blocks);
   s.full = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.empty = reinterpret_cast<uint64_t*>(p), p += 8 * kMaxStages;
   s.layer_done = reinterpret_cast<uint64_t*>(p), p += 8;
@@ -124,7 +130,9 @@ __device__ __forceinline__ USmem ucarve(uint8_t* base, const UArgs& a) {
 }
 
 // ============================================================================================== the kernel
-template <int NE, int ACT>
+// SEG: the segmented GroupNorm path (group sizes that are not powers of two) is compiled in; the SEG = false
+// instantiations are the kernels every power-of-two geometry runs (same registers / code as before the path existed)
+template <int NE, int ACT, bool SEG>
 __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) {
   constexpr int CPT = NE / 2;  // accumulator columns (environments) per epilogue thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -428,6 +436,66 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             e_film += clock64() - tw;
             film_buf = s.film + (film_n & 1) * s.film_stride;
           }
+          // GroupNorm groups whose size is not a power of two (5 channels x 4 positions = 20 lowered features) straddle
+          // warps and M tiles: every warp reduces the runs of its 32 lanes by a segmented shuffle scan and the two pieces
+          // of a straddling group meet through shared memory (first pass: partial sums of the runs that touch lane 0 /
+          // lane 31 of each 32-feature block; second pass, below: statistics = own run + the neighbour block's piece)
+          const bool gn_seg = SEG && gs && (gs & (gs - 1));
+          struct SegInfo {
+            uint32_t same;     // bit k: lane + 2^k is in this warp and in the same group
+            int first;         // first lane of this lane's run
+            bool prev, next;   // the group began in the previous 32-feature block / continues in the next one
+          };
+          auto seg_info = [&](int mt) {
+            SegInfo si;
+            const int f = mt * 128 + fl, blk0 = f - lane;
+            const bool valid = f < nf;
+            const int g = valid ? f / gs : -1;
+            si.same = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              const int fn = f + (1 << k);
+              if (valid && lane + (1 << k) < 32 && fn < nf && fn / gs == g) si.same |= 1u << k;
+            }
+            si.first = valid ? max(g * gs - blk0, 0) : lane;
+            si.prev = valid && g * gs < blk0;
+            si.next = valid && (g + 1) * gs > blk0 + 32;
+            return si;
+          };
+          // after the scan the first lane of every run holds the run's sum (runs are at most 32 lanes long)
+          auto seg_scan = [&](float (&x)[CPT], const SegInfo& si) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              const bool take = (si.same >> k) & 1u;
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) {
+                const float t = __shfl_down_sync(0xffffffffu, x[c], 1 << k);
+                if (take) x[c] += t;
+              }
+            }
+          };
+          if (gn_seg) {
+            for (int mt = 0; mt < MTl; ++mt) {
+              float v[CPT], sq[CPT];
+              tmem_ld(tmem + lane_addr + uint32_t(acc_tile + mt) * NE + col0, v);
+              const float b = mt < 2 ? pb[mt & 1] : bias[mt * 128 + fl];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) v[c] += b, sq[c] = v[c] * v[c];
+              const SegInfo si = seg_info(mt);
+              seg_scan(v, si);
+              seg_scan(sq, si);
+              float* part = s.gn_part + size_t(mt * 4 + q) * 4 * NE + col0;
+              if (lane == 0 && si.prev) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) part[c] = v[c], part[NE + c] = sq[c];
+              }
+              if (lane == si.first && si.next) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) part[2 * NE + c] = v[c], part[3 * NE + c] = sq[c];
+              }
+            }
+            named_bar_sync(1, kEpiThreads);
+          }
           for (int mt = 0; mt < MTl; ++mt) {
             float v[CPT];
             tmem_ld(tmem + lane_addr + uint32_t(acc_tile + mt) * NE + col0, v);
@@ -435,7 +503,25 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
             const float b = mt < 2 ? pb[mt & 1] : bias[f];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) v[c] += b;
-            if (gs) {
+            if (gn_seg) {
+              const float inv = 1.f / float(gs);
+              const float g = mt < 2 ? pg[mt & 1] : gamma[f], be = mt < 2 ? pbe[mt & 1] : beta[f];
+              const SegInfo si = seg_info(mt);
+              float sm[CPT], sq[CPT];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) sm[c] = v[c], sq[c] = v[c] * v[c];
+              seg_scan(sm, si);
+              seg_scan(sq, si);
+              const float* part = s.gn_part + size_t(mt * 4 + q) * 4 * NE + col0;
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) {
+                float a1 = __shfl_sync(0xffffffffu, sm[c], si.first), a2 = __shfl_sync(0xffffffffu, sq[c], si.first);
+                if (si.prev) a1 += part[c - 4 * NE + 2 * NE], a2 += part[c - 4 * NE + 3 * NE];  // tail of the previous block
+                if (si.next) a1 += part[c + 4 * NE], a2 += part[c + 4 * NE + NE];                // head of the next block
+                const float mean = a1 * inv, var = fmaxf(a2 * inv - mean * mean, 0.f);
+                v[c] = (v[c] - mean) * rsqrtf(var + gn_eps) * g + be;
+              }
+            } else if (gs) {
               // GroupNorm over gs consecutive features (lanes) of each environment column: mean, then centred variance.
               // Stage-major loops keep CPT independent shuffles in flight per butterfly stage.
               const float inv = 1.f / float(gs);
@@ -623,9 +709,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_unet_kernel(const UArgs a) 
   if (C > 1) cluster_sync_all();  // no CTA leaves while its peer can still signal it or store into it
 }
 
-template <int NE, int ACT>
+template <int NE, int ACT, bool SEG>
 int ulaunch(const UArgs& a, size_t smem_bytes, cudaStream_t st) {
-  auto kfn = chain_unet_kernel<NE, ACT>;
+  auto kfn = chain_unet_kernel<NE, ACT, SEG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -671,7 +757,7 @@ static UShape pick_unet_shape(const dppo_ctx* ctx, int E) {
     for (int NE = 16; NE <= 64; NE *= 2) {
       if (forced_ne > 0 && NE != forced_ne) continue;
       if (2 * P.MTmax * NE > 512) continue;
-      const size_t fixed = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D, C);
+      const size_t fixed = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D, C, P.gn_segmented ? P.MTmax * 4 : 0);
       if (fixed + 2 * kTile > budget) continue;
       int nstage = int((budget - fixed) / kTile);
       if (nstage > kMaxStages) nstage = kMaxStages;
@@ -705,6 +791,7 @@ int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float
   for (int w = 0; w < 2; ++w) a.tiles[w] = ctx->nets[w].tiles, a.side[w] = ctx->nets[w].side;
   a.chunk_x = P.chunk_x, a.chunk_state = P.chunk_state, a.chunk_state_act = P.chunk_state_act, a.KS = P.KS;
   a.total_chunks = P.total_chunks, a.film_dim = P.film_dim;
+  a.gn_blocks = P.gn_segmented ? P.MTmax * 4 : 0;
   a.rows = ctx->d_rows, a.S = ctx->S, a.ft = ctx->ft, a.use_ddim = ctx->use_ddim;
   a.eval_mode = chains_in != nullptr;
   a.first_step = a.eval_mode ? ctx->S - ctx->ft : 0;
@@ -720,13 +807,14 @@ int sample_chain_unet_impl(dppo_ctx* ctx, const float* state, int E, const float
   const int NE = shape.NE;
   if (NE == 0) return set_error("unet chain kernel: no tile size fits this geometry in shared memory / TMEM"), DPPO_ERR_UNSUPPORTED;
   a.nstage = shape.nstage, a.C = shape.C;
-  const size_t smem_bytes = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D, a.C) + size_t(a.nstage) * kTile;
-#define DPPO_ULAUNCH(NE_) \
-  (P.d.activation == DPPO_ACT_RELU ? ulaunch<NE_, DPPO_ACT_RELU>(a, smem_bytes, st) : ulaunch<NE_, DPPO_ACT_MISH>(a, smem_bytes, st))
+  const size_t smem_bytes = usmem_fixed_bytes(NE, P.total_chunks, P.nsplit, P.film_dim, P.D, a.C, a.gn_blocks) + size_t(a.nstage) * kTile;
+#define DPPO_ULAUNCH_A(NE_, ACT_) (a.gn_blocks ? ulaunch<NE_, ACT_, true>(a, smem_bytes, st) : ulaunch<NE_, ACT_, false>(a, smem_bytes, st))
+#define DPPO_ULAUNCH(NE_) (P.d.activation == DPPO_ACT_RELU ? DPPO_ULAUNCH_A(NE_, DPPO_ACT_RELU) : DPPO_ULAUNCH_A(NE_, DPPO_ACT_MISH))
   if (NE == 64) return DPPO_ULAUNCH(64);
   if (NE == 32) return DPPO_ULAUNCH(32);
   return DPPO_ULAUNCH(16);
 #undef DPPO_ULAUNCH
+#undef DPPO_ULAUNCH_A
 }
 
 }  // namespace dppo

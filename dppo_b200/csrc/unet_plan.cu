@@ -102,13 +102,17 @@ struct Builder {
   }
 
   int gn_group(int C, int T) {
+    // a group is a run of gs consecutive lowered features.  Powers of two never straddle a warp's 32 TMEM lanes (shuffle
+    // butterflies); any other size <= 32 (robomimic can / lift: 5 channels x 4 positions = 20) takes the kernel's
+    // segmented path, whose groups may span two warps or two M tiles and exchange partial sums through shared memory
     const int gs = C / d.n_groups * T;
-    if (C % d.n_groups || gs < 1 || gs > 32 || ilog2_exact(gs) < 0) {
-      set_error("unet: GroupNorm group of %d channels x %d positions = %d features; the kernel needs a power of two <= 32",
+    if (C % d.n_groups || gs < 1 || gs > 32) {
+      set_error("unet: GroupNorm group of %d channels x %d positions = %d features; the kernel needs groups of <= 32 features",
                 d.n_groups ? C / d.n_groups : 0, T, gs);
       err = DPPO_ERR_UNSUPPORTED;
       return 1;
     }
+    if (ilog2_exact(gs) < 0) P.gn_segmented = 1;
     return gs;
   }
 

@@ -34,7 +34,7 @@ struct ULayer {
   int32_t kind;                    // U_EPI_*
   int32_t acc_tile, mt, nf;        // accumulator tiles read by the epilogue, valid output features
   int32_t bias_off, bias_tstride;  // floats into the side table; tstride != 0: row t of a per-timestep table
-  int32_t gn_size;                 // features per GroupNorm group (0 = no norm; power of two <= 32)
+  int32_t gn_size;                 // features per GroupNorm group (0 = no norm; <= 32; not a power of two: segmented path)
   int32_t gamma_off, beta_off;
   float gn_eps;
   int32_t act;                     // 1 = apply the net's activation
@@ -108,6 +108,7 @@ struct UnetPlan {
   int total_chunks = 0;
   int KA = 0, MTmax = 0;   // widest activation in chunks (even), its M tiles
   int film_dim = 0;        // floats per env of the FiLM buffer
+  int gn_segmented = 0;    // 1: some GroupNorm group size is not a power of two (kernel needs its partial-sum scratch)
   std::vector<ULayer> layers;
   std::vector<UPackJob> jobs;
   std::vector<USideJob> side_jobs;

@@ -108,6 +108,17 @@ WORKLOADS["square_mlp"] = dict(  # dppo/cfg/robomimic/finetune/square/ft_ppo_dif
                target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=2, max_episode_steps=400),
 )
 
+WORKLOADS["can_unet"] = dict(  # dppo/cfg/robomimic/finetune/{can,lift}/ft_ppo_diffusion_unet.yaml (DDPM-20; dim 40: GroupNorm groups of 20)
+    yaml="robomimic/finetune/can/ft_ppo_diffusion_unet.yaml",
+    n_envs=50, obs_dim=23, action_dim=7, horizon_steps=4, act_steps=4, cond_steps=1,
+    denoising_steps=20, ft_denoising_steps=10, use_ddim=False, ddim_steps=None, eta=None,
+    actor=dict(kind="unet", diffusion_step_embed_dim=16, dim=40, dim_mults=[1, 2], kernel_size=5, n_groups=8,
+               smaller_encoder=False, cond_predict_scale=True),
+    critic=_CRITIC_256, ppo=_ROBOMIMIC_PPO,
+    train=dict(n_steps=300, gamma=0.999, gae_lambda=0.95, batch_size=7500, update_epochs=10, vf_coef=0.5,
+               target_kl=1, actor_lr=1e-4, critic_lr=1e-3, n_critic_warmup_itr=2, max_episode_steps=300),
+)
+
 # variants: same networks, different schedules
 WORKLOADS["transport_k20"] = dict(deepcopy(WORKLOADS["transport"]), denoising_steps=20)
 WORKLOADS["furniture_ddpm100"] = dict(deepcopy(WORKLOADS["furniture"]), use_ddim=False, ddim_steps=None, eta=None)

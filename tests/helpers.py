@@ -26,6 +26,8 @@ GOLDEN_CASES = {
     "kitchen": dict(workload="kitchen", n_envs=40, mb_rows=96),
     "avoid": dict(workload="avoid", n_envs=50, mb_rows=96),
     "square_mlp": dict(workload="square_mlp", n_envs=24, mb_rows=64),
+    # Unet1D with dim 40 (robomimic can / lift): GroupNorm groups of 20 lowered features (segmented path of chain_unet.cu)
+    "can_unet": dict(workload="can_unet", n_envs=50, mb_rows=96),
 }
 
 # optional branches of the hot path (tests/golden/make_golden_variants.py): base workload + constructor overrides

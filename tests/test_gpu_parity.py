@@ -13,7 +13,7 @@ from tests.helpers import GOLDEN_CASES, build_model, load_golden, make_inputs, o
 
 pytestmark = pytest.mark.gpu
 MLP_CASES = ["hopper", "walker2d", "transport_k20", "transport", "furniture", "furniture_ddpm100", "kitchen", "avoid", "square_mlp"]
-ALL_CASES = MLP_CASES + ["square_unet"]
+ALL_CASES = MLP_CASES + ["square_unet", "can_unet"]
 
 
 def rel_err(a, b):
@@ -295,10 +295,24 @@ def test_host_call_matches_device_call(case):
     assert empty.trajectories.shape == (0, Ta, Da) and empty.chains.shape == (0, ft + 1, Ta, Da)
 
 
+@pytest.mark.parametrize("tile_envs,cluster", [(16, 1), (16, 2), (32, 1), (32, 2)])
+def test_segmented_groupnorm_launch_shapes(tile_envs, cluster):
+    """Unet1D with dim 40 (robomimic can / lift): GroupNorm groups of 20 lowered features straddle warps and M tiles; every
+    tile size / track split of the segmented path against the vectors recorded from the unmodified reference."""
+    w, model, gold, inp = _setup("can_unet")
+    model.engine().set_launch_shape(tile_envs, cluster)
+    state, noise = inp["state"].cuda(), inp["noise"].cuda()
+    out = model(cond={"state": state}, noise=noise)
+    assert_close(out.chains.cpu().numpy(), gold["chains"], 1e-3, f"can_unet NE={tile_envs} C={cluster} chains")
+    with torch.no_grad():
+        lp = model.get_logprobs({"state": state}, torch.from_numpy(gold["chains"]).cuda())
+    assert_close(lp.cpu().numpy(), gold["logprobs"], 1e-3, f"can_unet NE={tile_envs} C={cluster} log-probs")
+
+
 @pytest.mark.parametrize("workload,n_envs,tile_envs,cluster,launches", [
     ("walker2d", 4096, 64, 2, 3000), ("walker2d", 2048, 32, 4, 3000), ("furniture", 500, 32, 4, 2000),
     ("transport_k20", 50, 16, 8, 2000), ("square_unet", 512, 16, 2, 1500), ("hopper", 40, 0, -1, 5000),
-    ("walker2d", 4096, 0, -2, 3000), ("walker2d", 301, 0, -2, 2000),
+    ("walker2d", 4096, 0, -2, 3000), ("walker2d", 301, 0, -2, 2000), ("can_unet", 200, 16, 2, 1500),
 ])
 def test_back_to_back_launch_stress(workload, n_envs, tile_envs, cluster, launches):
     """Protocol stress: thousands of back-to-back launches of every cluster protocol (a handshake race once hung one launch

@@ -86,10 +86,15 @@ def run_program(plan, x, t, state, act="Mish"):
         f = np.arange(n)
         if L.kind == EPI_OPERAND:
             if L.gn_size:
-                g = v.reshape(B, n // L.gn_size, L.gn_size)
+                # groups are runs of gn_size consecutive VALID features (a size that is not a power of two does not divide
+                # the 128-feature tiles: the padding features behind nf belong to no group)
+                nv = L.nf
+                assert nv % L.gn_size == 0
+                g = v[:, :nv].reshape(B, nv // L.gn_size, L.gn_size)
                 m = g.mean(-1, keepdims=True)
                 var = ((g - m) ** 2).mean(-1, keepdims=True)
-                v = ((g - m) / np.sqrt(var + L.gn_eps)).reshape(B, n) * side[L.gamma_off: L.gamma_off + n] + side[L.beta_off: L.beta_off + n]
+                v[:, :nv] = ((g - m) / np.sqrt(var + L.gn_eps)).reshape(B, nv)
+                v = v * side[L.gamma_off: L.gamma_off + n] + side[L.beta_off: L.beta_off + n]
             if L.act:
                 v = actf(v)
             if L.film:
@@ -129,6 +134,10 @@ CASES = [
     dict(Da=7, Ta=4, cond=23, e=16, dim=64, mults=(1, 2), k=5, groups=8, cps=False, small=True),
     dict(Da=3, Ta=8, cond=11, e=8, dim=32, mults=(1, 2, 4), k=3, groups=8, cps=True, small=False),
     dict(Da=10, Ta=4, cond=58, e=16, dim=64, mults=(1,), k=5, groups=8, cps=False, small=False),
+    # robomimic can / lift (cfg/robomimic/finetune/{can,lift}/ft_ppo_diffusion_unet.yaml): dim 40 -> GroupNorm groups of
+    # 5 channels x 4 positions (10 x 2 on the second level) = 20 lowered features, the segmented path of the kernel
+    dict(Da=7, Ta=4, cond=23, e=16, dim=40, mults=(1, 2), k=5, groups=8, cps=True, small=False),
+    dict(Da=7, Ta=4, cond=19, e=16, dim=24, mults=(1, 2), k=5, groups=8, cps=True, small=False),  # groups of 12 / 12
 ]
 
 
@@ -174,6 +183,6 @@ def test_plan_rejects_unsupported_shapes():
     h = C.c_void_p()
     assert lib.dppo_unet_plan_create(C.byref(d), 20, 0, C.byref(h)) < 0
     assert b"power of two" in lib.dppo_last_error()
-    d.horizon_steps, d.dim = 4, 40  # 5 channels x 4 positions per group: not a power of two
+    d.horizon_steps, d.dim = 4, 128  # 16 channels x 4 positions per group = 64 features: more than a warp's 32 TMEM lanes
     assert lib.dppo_unet_plan_create(C.byref(d), 20, 0, C.byref(h)) < 0
     assert b"GroupNorm" in lib.dppo_last_error()
