@@ -2,7 +2,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
+#include <chrono>
 
 #include "internal.h"
 #include "unet_plan.h"
@@ -229,6 +233,7 @@ extern "C" int dppo_ctx_destroy(dppo_ctx* c) {
   cudaFree(c->d_rows);
   cudaFree(c->d_nonfinite);
   if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_done) cudaFreeHost(c->h_done);
   for (int w = 0; w < 2; ++w) {
     cudaFree(c->nets[w].tiles);
     cudaFree(c->nets[w].side);
@@ -307,10 +312,40 @@ extern "C" int dppo_sample_chain_host(dppo_ctx* ctx, const float* state, int n_e
     k_traj = reinterpret_cast<float*>(p), p += up(tb);
     if (chain) k_chain = reinterpret_cast<float*>(p);
   }
+  if (!ctx->h_done) {
+    DPPO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_done), 64, cudaHostAllocPortable | cudaHostAllocMapped));
+    *ctx->h_done = 0;
+  }
+  static int env_ticket = -1;  // DPPO_B200_TICKET=0: always wait through the driver (A/B switch)
+  if (env_ticket < 0) {
+    const char* e = getenv("DPPO_B200_TICKET");
+    env_ticket = e ? atoi(e) : 1;
+  }
+  ctx->done_want = env_ticket, ctx->done_armed = 0;
   const int rc = dppo_sample_chain(ctx, k_state, n_envs, nullptr, seed, offset, env_offset, deterministic, use_base_policy,
                                    min_std, k_traj, k_chain, stream);
+  ctx->done_want = 0;
   if (rc != DPPO_OK) return rc;
-  DPPO_CUDA(cudaStreamSynchronize(st));
+  bool done = false;
+  if (ctx->done_armed) {
+    // the latency case (small-batch kernel): poll the ticket the kernel's last cluster stores into page-locked memory
+    // behind its results; past a deadline (a trapped or very long launch) fall through to the driver's synchronise,
+    // which also reports the error
+    volatile unsigned* flag = ctx->h_done;
+    const unsigned want = ctx->done_seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 1; !done; ++spins) {
+      if (*flag == want) {
+        done = true;
+      } else if ((spins & 4095u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(5)) {
+        break;
+      } else {
+        __builtin_ia32_pause();
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (!done) DPPO_CUDA(cudaStreamSynchronize(st));
   if (stage_out) {
     memcpy(traj, k_traj, tb);
     if (chain) memcpy(chain, k_chain, cb);

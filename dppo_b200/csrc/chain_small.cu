@@ -47,6 +47,12 @@ struct SmallArgs {
   uint64_t seed, offset;
   int64_t env_offset;
   int* nonfinite;  // OR-ed with 1 when a final action element is NaN / Inf
+  // completion ticket of the host-buffer call (dppo_sample_chain_host), nullptr otherwise: the last cluster to finish
+  // stores `done_seq` into page-locked host memory behind a system-scope fence, so the host sees the results ~ a kernel
+  // tear-down + stream-synchronise wake-up earlier than through the driver
+  unsigned* done_counter;
+  unsigned* done_flag;
+  unsigned done_seq;
 };
 
 __device__ __forceinline__ float philox_normal_s(uint64_t seed, uint64_t offset, uint64_t elem, uint32_t slot) {
@@ -345,6 +351,17 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
     wait_full(2, x0bytes);
   }
   cluster_sync_all();  // nobody leaves while a peer's stores into it may still be in flight
+  if (a.done_flag && rank == 0 && threadIdx.x == 0) {
+    // the release / acquire cluster barrier above orders every result store of this cluster before this point; the fence
+    // makes them visible system-wide (cumulative) before the ticket, the last ticket holder publishes the sequence number
+    __threadfence_system();
+    const unsigned clusters = gridDim.x / kCS;
+    if (atomicAdd(a.done_counter, 1u) == clusters - 1) {
+      *a.done_counter = 0;  // the next launch is stream-ordered behind this one
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(a.done_flag) = a.done_seq;
+    }
+  }
 }
 
 template <int EPC>
@@ -413,6 +430,11 @@ int sample_chain_small_impl(dppo_ctx* ctx, const float* state, int E, const floa
   a.state = state, a.noise = noise, a.traj = traj, a.chain = chain;
   a.seed = seed, a.offset = offset, a.env_offset = env_offset;
   a.nonfinite = ctx->d_nonfinite;
+  if (ctx->done_want && ctx->h_done) {
+    a.done_counter = reinterpret_cast<unsigned*>(ctx->d_nonfinite) + 1;
+    a.done_flag = ctx->h_done, a.done_seq = ++ctx->done_seq;
+    ctx->done_armed = 1;
+  }
   // spread the environments over as many clusters as the device co-schedules
   const int clusters = E < ctx->small_clusters ? E : ctx->small_clusters;
   const int epc = (E + clusters - 1) / clusters;

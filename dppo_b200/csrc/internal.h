@@ -99,6 +99,11 @@ struct dppo_ctx {
   int* d_nonfinite = nullptr;  // device flag OR-ed by the chain kernels when a sampled action element is not finite
   uint8_t* h_stage = nullptr;  // page-locked staging area of dppo_sample_chain_host (pageable caller buffers)
   size_t h_stage_bytes = 0;
+  // completion ticket of dppo_sample_chain_host (small-batch kernel): page-locked word the kernel's last cluster stores
+  // done_seq into; done_want = the running call asks for it, done_armed = the launched kernel will write it
+  unsigned* h_done = nullptr;
+  unsigned done_seq = 0;
+  int done_want = 0, done_armed = 0;
   int force_ne = 0, force_c = 0;          // launch-shape override of the chain kernel (0 = cost model), dppo_debug_set_shape
   unsigned long long* d_prof = nullptr;  // optional cycle counters written by the chain kernel (dppo_debug_set_prof)
 };

@@ -181,6 +181,7 @@ class ChainEngine:
         _lib.check(create(C.byref(self.ctx), C.byref(desc), C.byref(sd), _lib.PRECISIONS[precision], idx), "dppo_ctx_create")
         self._packed = {0: None, 1: None}
         self._plists = {}
+        self._current = None  # (actor, actor_ft, their parameters, signature, split) as of the last full synchronisation
         self._host_io = {}  # batch size -> [next slot, ring of (trajectories, chains, traj ptr, chain ptr)] (sample_host)
         self._sample_host_fn = self.lib.dppo_sample_chain_host
         self.Ta, self.Da = int(model.horizon_steps), int(model.action_dim)
@@ -222,6 +223,21 @@ class ChainEngine:
         _lib.check(pack(self.ctx, which, arr, len(ps), _lib.stream_ptr()), "dppo_pack_unet" if self.is_unet else "dppo_pack_mlp")
         self._packed[which] = sig
         return True
+
+    def weights_current(self, actor, actor_ft):
+        """Per-decision fast path of the cache check: True when neither network (module identity, storage address of the
+        first parameter, every parameter's version counter) changed since `mark_current`."""
+        c = self._current
+        if c is None or c[0] is not actor or c[1] is not actor_ft:
+            return False
+        ps = c[2]
+        return c[3] == (ps[0].data_ptr(), ps[c[4]].data_ptr(), *map(_VERSION, ps))
+
+    def mark_current(self, actor, actor_ft):
+        """Record the state both packed copies were just synchronised with (after sync_weights(0, ...) and (1, ...))."""
+        pa, pf = self._plists[0][1], self._plists[1][1]
+        ps = pa + pf
+        self._current = (actor, actor_ft, ps, (ps[0].data_ptr(), ps[len(pa)].data_ptr(), *map(_VERSION, ps)), len(pa))
 
     # ------------------------------------------------------------------ rollout
     def sample(self, state, noise=None, seed=0, offset=0, env_offset=0, deterministic=False, use_base_policy=False,
