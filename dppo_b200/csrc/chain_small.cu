@@ -82,7 +82,7 @@ __host__ __device__ inline size_t small_smem_floats(int FS, int K0p, int H, int 
          + size_t(KS) * EPC * FS                                                  // k-slice partial sums
          + size_t(2 * nb) * FS + size_t(OR)                                       // bias slices (b1 / b2 per block, output)
          + size_t(S) * (sizeof(StepRow) / 4) + 4                                  // the schedule rows
-         + 8;                                                                     // three mbarriers (8-byte aligned)
+         + 12;                                                                    // four mbarriers (8-byte aligned)
 }
 
 template <int EPC>
@@ -127,12 +127,32 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
   const uint32_t xbytes = uint32_t(EPC) * H * 4u;     // one layer-input buffer: FS x EPC values from each of the 16 CTAs
   const uint32_t x0bytes = uint32_t(ne) * a.D * 4u;   // the next sample: one value per (environment, action element)
   uint32_t bph = 0;                                   // phase bits of sbar[0..2]
-  if (t == 0) {
-    for (int i = 0; i < 3; ++i) mbar_init(&sbar[i], 1);
-    fence_mbar_init();
-    mbar_arrive_expect_tx(&sbar[0], xbytes);
-    mbar_arrive_expect_tx(&sbar[1], xbytes);
-    mbar_arrive_expect_tx(&sbar[2], x0bytes);
+  // Launch latency of the weights-stationary scheme: the first network's hidden-layer slices (2 nb x FS rows of H floats,
+  // 128 KB at H = 512) are fetched by bulk async copies issued here, one row per copy, completing on sbar[3]; they run
+  // under the prologue (observation read over PCIe when `state` is page-locked host memory, x_T draws, the cluster
+  // barrier) and layer 0 waits for them only where it used to load them through registers.
+  const int net_first = (a.rows[0].ft && !a.use_base) ? 1 : 0;
+  const int wh_rows = 2 * a.nb * FS;
+  // the observation values of this cluster are requested now and stored into the layer-0 input behind the weight fetch
+  const int n_state = ne * a.Dc;
+  const bool state_early = n_state <= kThreadsS;
+  float state_pre = 0.f;
+  if (state_early && t < n_state) state_pre = a.state[size_t(env0) * a.Dc + t];
+  if (warp == 0) {
+    if (t == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(&sbar[i], 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(&sbar[0], xbytes);
+      mbar_arrive_expect_tx(&sbar[1], xbytes);
+      mbar_arrive_expect_tx(&sbar[2], x0bytes);
+      mbar_arrive_expect_tx(&sbar[3], uint32_t(wh_rows) * uint32_t(H) * 4u);
+    }
+    __syncwarp();
+    for (int i = lane; i < wh_rows; i += 32) {
+      const int l = i / FS, r = i % FS;
+      const float* src = ((l & 1) ? a.w2[net_first][l >> 1] : a.w1[net_first][l >> 1]) + size_t(int(rank) * FS + r) * H;
+      bulk_g2s(wh + size_t(l) * FS * HS + size_t(r) * HS, src, uint32_t(H) * 4u, &sbar[3]);
+    }
   }
   // wait for a full buffer, then (one thread) expect the bytes of its next use.  Nobody can complete that next phase
   // before every thread here has passed this wait: it needs this CTA's own stores of a later layer, behind a __syncthreads.
@@ -145,10 +165,11 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
   for (int i = t; i < a.S; i += kThreadsS) s_rows[i] = a.rows[i];
   for (int i = t; i < EPC * K0p; i += kThreadsS) x0[i] = 0.f;
   __syncthreads();
-  for (int i = t; i < ne * a.Dc; i += kThreadsS) {
-    const int e = i / a.Dc, k = i % a.Dc;
-    x0[e * K0p + a.D + k] = a.state[size_t(env0 + e) * a.Dc + k];
-  }
+  if (!state_early)
+    for (int i = t; i < n_state; i += kThreadsS) {
+      const int e = i / a.Dc, k = i % a.Dc;
+      x0[e * K0p + a.D + k] = a.state[size_t(env0 + e) * a.Dc + k];
+    }
   for (int i = t; i < ne * a.D; i += kThreadsS) {
     const int e = i / a.D, j = i % a.D, env = env0 + e;
     const float x = a.noise ? a.noise[size_t(env) * a.D + j]
@@ -173,13 +194,20 @@ __global__ void __launch_bounds__(kThreadsS, 1) chain_small_kernel(const SmallAr
         w0[r * K0p + k] = a.W0[net][size_t(int(rank) * FS + r) * a.in0 + (k < a.D ? k : k + a.td)];
       }
       const int q4 = H / 4;
-      for (int l = 0; l < 2 * a.nb; ++l) {
-        const float* src = (l & 1) ? a.w2[net][l >> 1] : a.w1[net][l >> 1];
-        float* dst = wh + size_t(l) * FS * HS;
-        for (int i = t; i < FS * q4; i += kThreadsS) {
-          const int r = i / q4, c = i % q4;
-          *reinterpret_cast<float4*>(dst + r * HS + c * 4) =
-              *reinterpret_cast<const float4*>(src + size_t(int(rank) * FS + r) * H + c * 4);
+      if (step == 0) {
+        // hidden-layer slices of the first network: the bulk copies issued at kernel start; the observation values
+        // requested there land in the layer-0 input now (every thread observes the barrier: async-proxy writes)
+        if (state_early && t < n_state) x0[(t / a.Dc) * K0p + a.D + t % a.Dc] = state_pre;
+        mbar_wait(&sbar[3], 0);
+      } else {
+        for (int l = 0; l < 2 * a.nb; ++l) {
+          const float* src = (l & 1) ? a.w2[net][l >> 1] : a.w1[net][l >> 1];
+          float* dst = wh + size_t(l) * FS * HS;
+          for (int i = t; i < FS * q4; i += kThreadsS) {
+            const int r = i / q4, c = i % q4;
+            *reinterpret_cast<float4*>(dst + r * HS + c * 4) =
+                *reinterpret_cast<const float4*>(src + size_t(int(rank) * FS + r) * H + c * 4);
+          }
         }
       }
       for (int i = t; i < a.OR * q4; i += kThreadsS) {
