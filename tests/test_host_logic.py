@@ -128,7 +128,8 @@ def test_committed_bench_lines_carry_the_contract_keys():
     import os
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lines = sorted(glob.glob(os.path.join(root, "profiles", "r1*_bench*.json")))
+    lines = sorted(glob.glob(os.path.join(root, "profiles", "r1*_bench*.json")) +
+                   glob.glob(os.path.join(root, "profiles", "r2", "r2y_bench*.json")))  # + the final tree of round 2
     assert lines, "no bench lines under profiles/"
     for path in lines:
         d = json.load(open(path))
