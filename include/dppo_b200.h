@@ -17,6 +17,7 @@
 #ifndef DPPO_B200_H_
 #define DPPO_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

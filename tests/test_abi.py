@@ -49,3 +49,30 @@ def test_no_cpu_fallback():
 
     with pytest.raises(RuntimeError):
         _lib.ptr(torch.zeros(4))
+
+
+def test_header_is_self_contained_c_and_a_c_program_links(tmp_path):
+    """include/dppo_b200.h compiles on its own as C99 and as C++ (a cgo / JNI / plain C consumer includes nothing else), and
+    a C program that includes it links against libdppo_b200.so and gets errors back as codes (no GPU needed)."""
+    import subprocess
+
+    prog = tmp_path / "use.c"
+    prog.write_text(
+        '#include "dppo_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  float obs[4] = {0}, traj[4];\n"
+        "  int rc = dppo_sample_chain_host(0, obs, 1, 0, 0, 0, 0, 0, 0.1f, traj, 0, DPPO_HOST_STATE_PINNED | DPPO_HOST_OUT_PINNED, 0);\n"
+        '  printf("%d %d %s\\n", dppo_version(), rc, dppo_last_error());\n'
+        "  return rc == DPPO_ERR_INVALID ? 0 : 1;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(prog)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-fsyntax-only", str(prog)], check=True)
+    _lib.load()
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "use"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(prog), "-L", libdir, "-ldppo_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    version, rc, msg = out.stdout.split(" ", 2)
+    assert int(version) >= 103 and int(rc) == -1 and "null" in msg
