@@ -120,6 +120,8 @@ class TrainPPODiffusionAgent:
         self.bc_loss_coeff = cfg.train.get("bc_loss_coeff", 0)
         self.reward_horizon = cfg.get("reward_horizon", self.act_steps)
         self.cuda_graph_update = cfg.train.get("cuda_graph_update", True)
+        self.host_rollout = cfg.train.get("host_rollout", True)  # one host-buffer library call per decision (rollout())
+        self._pinned_obs = None
         if self.model.learn_eta:
             raise NotImplementedError("learned eta is outside the hot path (no YAML enables it)")
 
@@ -171,25 +173,45 @@ class TrainPPODiffusionAgent:
         obs_buf = torch.empty((n, E, self.n_cond_step, self.obs_dim), dtype=torch.float32, device=dev)
         chains_buf = torch.empty((n, E, ft + 1, self.horizon_steps, self.action_dim), dtype=torch.float32, device=dev)
         reward_trajs, terminated_trajs = np.zeros((n, E)), np.zeros((n, E))
-        pinned_obs = torch.empty((E, self.n_cond_step, self.obs_dim), dtype=torch.float32).pin_memory()
         pinned_act = torch.empty((E, self.horizon_steps, self.action_dim), dtype=torch.float32).pin_memory()
+        # Host-buffer decisions (default): the observations of the whole rollout live in ONE page-locked buffer the
+        # simulator's arrays are copied into; every decision is one library call that reads its slice from there, stores
+        # the chains into the device-resident rollout buffer and the action chunk into page-locked memory and returns when
+        # they are there (dppo_sample_chain_host) - no copy launch, no torch op per step; the observations follow in one
+        # H2D copy after the loop.  With injected noise (parity hook) or `host_rollout: False` every step runs the device
+        # call with explicit copies instead.
+        host_rollout = self.host_rollout and "noise" not in self.test_hooks
+        shape = (n if host_rollout else 1, E, self.n_cond_step, self.obs_dim)
+        if self._pinned_obs is None or tuple(self._pinned_obs.shape) != shape:  # page-locking tens of MB costs milliseconds
+            self._pinned_obs = torch.empty(shape, dtype=torch.float32).pin_memory()
+        pinned_obs_all = self._pinned_obs
+        obs_np = pinned_obs_all.numpy()
         env_steps = 0
         for step in range(n):
-            pinned_obs.copy_(torch.from_numpy(np.ascontiguousarray(prev_obs_venv["state"], dtype=np.float32)))
-            obs_buf[step].copy_(pinned_obs, non_blocking=True)
-            # the kernel stores the chains straight into the device-resident rollout buffer and the action chunk straight
-            # into pinned host memory: no copy launches after it
-            noise = self.test_hooks["noise"](E).to(dev) if "noise" in self.test_hooks else None
-            self.model(cond={"state": obs_buf[step]}, deterministic=eval_mode, return_chain=True, env_offset=self.env_begin,
-                       out_trajectories=pinned_act, out_chains=chains_buf[step], noise=noise)
-            torch.cuda.current_stream().synchronize()  # the simulator needs the action chunk on the host
-            action_venv = pinned_act.numpy()[:, : self.act_steps]
+            if host_rollout:
+                np.copyto(obs_np[step], prev_obs_venv["state"], casting="same_kind")
+                out = self.model(cond={"state": pinned_obs_all[step]}, deterministic=eval_mode, return_chain=True,
+                                 env_offset=self.env_begin, out_chains=chains_buf[step])
+                action_venv = out.trajectories.numpy()[:, : self.act_steps]
+            else:
+                np.copyto(obs_np[0], prev_obs_venv["state"], casting="same_kind")
+                obs_buf[step].copy_(pinned_obs_all[0], non_blocking=True)
+                # the kernel stores the chains straight into the device-resident rollout buffer and the action chunk
+                # straight into pinned host memory: no copy launches after it
+                noise = self.test_hooks["noise"](E).to(dev) if "noise" in self.test_hooks else None
+                self.model(cond={"state": obs_buf[step]}, deterministic=eval_mode, return_chain=True, env_offset=self.env_begin,
+                           out_trajectories=pinned_act, out_chains=chains_buf[step], noise=noise)
+                torch.cuda.current_stream().synchronize()  # the simulator needs the action chunk on the host
+                action_venv = pinned_act.numpy()[:, : self.act_steps]
             obs_venv, reward_venv, terminated_venv, truncated_venv, _ = self.venv.step(action_venv)
             done_venv = terminated_venv | truncated_venv
             reward_trajs[step], terminated_trajs[step] = reward_venv, terminated_venv
             firsts_trajs[step + 1] = done_venv
             prev_obs_venv = obs_venv
             env_steps += E * self.act_steps if not eval_mode else 0
+        if host_rollout:
+            obs_buf.copy_(pinned_obs_all, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the pinned buffer is refilled by the next rollout
         return obs_buf, chains_buf, reward_trajs, terminated_trajs, prev_obs_venv, done_venv, env_steps
 
     @torch.no_grad()

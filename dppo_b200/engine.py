@@ -271,12 +271,14 @@ class ChainEngine:
     PIN_CHECK_BYTES = 65536  # below this a staging memcpy inside the library is cheaper than asking whether `state` is pinned
 
     def sample_host(self, state, seed=0, offset=0, env_offset=0, deterministic=False, use_base_policy=False,
-                    min_sampling_std=0.1, return_chain=True):
+                    min_sampling_std=0.1, return_chain=True, chain_out=None):
         """Host observations in, host results out, one call (dppo_sample_chain_host): `state` is a CPU tensor (E, ...) -
         pageable (staged by the library) or pinned (read in place); the kernel stores trajectories (E, Ta, Da) and chains
         (E, ft+1, Ta, Da) straight into page-locked memory and the call returns when they are there.  The returned tensors
         are views into a ring of HOST_RING page-locked buffers per batch size: they stay valid for the next
-        HOST_RING - 1 calls (the rollout loop consumes them within the step, reference train_ppo_diffusion_agent.py:112-122)."""
+        HOST_RING - 1 calls (the rollout loop consumes them within the step, reference train_ppo_diffusion_agent.py:112-122).
+        `chain_out`: optional contiguous float32 tensor (E, ft+1, Ta, Da) in device-accessible memory - a slice of a
+        device-resident rollout buffer or a pinned host tensor - the chains are stored there instead of in the ring."""
         E = state.shape[0]
         io = self._host_io.get(E)
         if io is None:
@@ -291,6 +293,11 @@ class ChainEngine:
         traj, chain, traj_p, chain_p = io[1][slot]
         if not return_chain:
             chain = chain_p = None
+        elif chain_out is not None:
+            if (chain_out.dtype is not torch.float32 or chain_out.numel() != chain.numel() or not chain_out.is_contiguous()
+                    or not (chain_out.is_cuda or chain_out.is_pinned())):
+                raise RuntimeError(f"chain_out: expected a contiguous float32 CUDA / pinned tensor of {tuple(chain.shape)}")
+            chain, chain_p = chain_out.view(chain.shape), chain_out.data_ptr()
         if E == 0:
             return traj, chain
         flags = _lib.HOST_OUT_PINNED

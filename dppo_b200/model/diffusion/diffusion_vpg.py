@@ -142,9 +142,10 @@ class VPGDiffusion(DiffusionModel):
                 out_trajectories=None, out_chains=None):
         """
         cond["state"]: (B, To, Do).  Returns Sample(trajectories (B, Ta, Da), chains (B, ft+1, Ta, Da)).
-        With cond["state"] on the HOST and no explicit output tensors, the results come back on the host too: views into
+        With cond["state"] on the HOST and no `out_trajectories`, the results come back on the host too: views into
         a ring of page-locked buffers the kernel stored into directly (valid for the next 3 calls), complete on return -
-        the reference's obs.to(device) -> model(cond) -> .cpu().numpy() as one call without copy launches.
+        the reference's obs.to(device) -> model(cond) -> .cpu().numpy() as one call without copy launches; an
+        `out_chains` tensor (device-resident rollout buffer slice or pinned) then receives the chains instead of the ring.
         `out_trajectories` / `out_chains`: optional preallocated float32 tensors of those shapes, on the device or in
         PINNED host memory - the kernel then stores straight into them (over PCIe for pinned memory, overlapped with the
         chain instead of a copy after it) and they are what Sample holds; cond["state"] may be pinned host memory too.
@@ -153,7 +154,7 @@ class VPGDiffusion(DiffusionModel):
         row 0 (env-sharded ranks then draw what one process would draw for the same envs).
         """
         state = cond["state"]
-        if state.is_cuda or noise is not None or out_trajectories is not None or out_chains is not None:
+        if state.is_cuda or noise is not None or out_trajectories is not None:
             return self._forward_device(state, deterministic, return_chain, use_base_policy, noise, env_offset,
                                         out_trajectories, out_chains)
         # host observations in -> host results out: one library call per decision (ChainEngine.sample_host).  This is the
@@ -166,7 +167,7 @@ class VPGDiffusion(DiffusionModel):
         if type(min_std) is not float:
             min_std = float(min_std())
         return Sample(*eng.sample_host(state, torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, offset, env_offset, deterministic,
-                                       use_base_policy, min_std, return_chain))
+                                       use_base_policy, min_std, return_chain, out_chains))
 
     @torch.no_grad()
     def _forward_device(self, state, deterministic, return_chain, use_base_policy, noise, env_offset, out_trajectories,

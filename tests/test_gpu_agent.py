@@ -46,6 +46,30 @@ def test_prologue_matches_oracle_gae_and_model_calls(tmp_path):
     np.testing.assert_allclose(ret.cpu().numpy(), ret_o, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("workload,n_envs", [("hopper", 8), ("furniture", 70), ("square_unet", 24)])
+def test_host_buffer_rollout_equals_device_call_rollout(tmp_path, workload, n_envs):
+    """rollout() with one dppo_sample_chain_host call per decision (observations from one page-locked buffer, chains into
+    the device-resident rollout buffer, actions into page-locked memory) == the device call with explicit copies, bit for
+    bit: same Philox keys, same simulator trajectory."""
+    outs = []
+    for host in (True, False):
+        w, ag = _agent(tmp_path / str(host), workload, n_envs=n_envs, n_steps=5, batch_size=64, update_epochs=1)
+        ag.host_rollout = host
+        torch.manual_seed(77)
+        firsts = np.zeros((ag.n_steps + 1, ag.n_envs))
+        firsts[0] = 1
+        ag.model.train()
+        obs_buf, chains_buf, rew, term, last_obs, done, steps = ag.rollout(ag.reset_env_all(), False, firsts)
+        torch.cuda.synchronize()
+        outs.append((obs_buf.cpu(), chains_buf.cpu(), rew.copy(), term.copy(), last_obs["state"].copy(), firsts.copy(), steps))
+        assert not ag.model.engine(sync=False).nonfinite()
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[6] == b[6]
+    for i in (2, 3, 4, 5):
+        assert np.array_equal(a[i], b[i])
+    assert float(a[1].abs().max()) > 0
+
+
 def test_run_two_iterations_updates_and_checkpoints(tmp_path):
     w, ag = _agent(tmp_path, n_envs=8, n_steps=8, batch_size=128, update_epochs=2, n_train_itr=2)
     before = {k: v.clone() for k, v in ag.model.actor_ft.state_dict().items()}
