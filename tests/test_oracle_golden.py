@@ -11,7 +11,7 @@ from dppo_b200.workloads import get_workload
 from oracle import dppo_oracle as O
 from tests.helpers import GOLDEN_CASES, build_model, load_golden, make_inputs, oracle_cfgs, oracle_params, our_classes, param_checksums
 
-FAST_CASES = ["hopper", "walker2d", "transport_k20", "furniture", "square_unet"]
+FAST_CASES = ["hopper", "walker2d", "transport_k20", "furniture", "square_unet", "kitchen", "avoid", "square_mlp", "can_unet"]
 
 
 def _setup(case):
@@ -53,7 +53,7 @@ def test_chain_and_logprobs(case):
     np.testing.assert_allclose(chains2.numpy(), gold["chains"], rtol=0, atol=2e-6)
 
 
-@pytest.mark.parametrize("case", ["hopper", "furniture", "square_unet"])
+@pytest.mark.parametrize("case", ["hopper", "furniture", "square_unet", "kitchen", "can_unet"])
 def test_loss_and_gradients(case):
     w, model, gold, inp, nc, dc = _setup(case)
     p = oracle_params(model, requires_grad=True)
